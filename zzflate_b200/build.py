@@ -1,0 +1,48 @@
+"""In-tree build of libzzflate_b200.so (kernels + C-ABI + host driver) for sm_100a.
+
+nvcc cross-compiles without a GPU; the resulting .so stays next to this file (git-ignored) so that it
+travels with the repository snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB = PKG_DIR / "libzzflate_b200.so"
+SOURCES = ["zz_kernels.cu", "zz_cabi.cu", "zz_host.cpp"]
+DEPS = SOURCES + ["zz_kernels.cuh", "../../include/zzgpu.h", "../../include/zzflate.h",
+                  "../../include/encoder.h", "../../include/crc.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any((CSRC / d).resolve().stat().st_mtime > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc_path(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []),
+           *[str(CSRC / s) for s in SOURCES], "-o", str(LIB)]
+    subprocess.check_call(cmd, cwd=str(CSRC))
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

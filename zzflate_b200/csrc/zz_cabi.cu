@@ -1,0 +1,416 @@
+// C-ABI layer (include/zzgpu.h): per-device context, scratch, staging and the kernel pipeline.
+// Replaces WriteDeflateStream (zzflate/zzflate.cpp:81-156) and the checksum calls of
+// AppendChecksum (zzflate.cpp:170-192) for the host driver in zz_host.cpp.
+#include "../../include/zzgpu.h"
+#include "zz_kernels.cuh"
+
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+
+namespace {
+
+using namespace zz;
+
+constexpr uint32_t kMaxSlots = 4096;        // chunks per batch (scratch is sized for one batch)
+constexpr int kMaxDevices = 16;
+
+thread_local std::string t_lastError;
+thread_local int t_device = -1;
+
+struct Ctx {
+    int device = -1;
+    bool ready = false;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    uint32_t slots = 0;
+    uint32_t slotChunk = 0;
+    uint16_t* cand = nullptr; uint32_t* tokA = nullptr; uint16_t* tokD = nullptr; uint32_t* hist = nullptr;
+    ChunkCodes* codes = nullptr; ChunkState* state = nullptr;
+    uint64_t* total = nullptr;              // device [4]
+    uint64_t* hTotal = nullptr;             // pinned [4]
+    uint32_t* ck = nullptr; size_t ckCap = 0;
+    uint32_t* hCk = nullptr; size_t hCkCap = 0;
+    uint8_t* dIn = nullptr; size_t dInCap = 0;
+    uint8_t* dOut = nullptr; size_t dOutCap = 0;
+};
+
+Ctx g_ctx[kMaxDevices];
+std::mutex g_mu;
+
+int fail(int status, const char* what, cudaError_t e = cudaSuccess)
+{
+    t_lastError = what;
+    if (e != cudaSuccess) { t_lastError += ": "; t_lastError += cudaGetErrorString(e); }
+    return status;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ZZGPU_E_CUDA, #call, e_); } while (0)
+
+void freeScratch(Ctx& c)
+{
+    cudaFree(c.cand); cudaFree(c.tokA); cudaFree(c.tokD); cudaFree(c.hist); cudaFree(c.codes); cudaFree(c.state);
+    c.cand = nullptr; c.tokA = nullptr; c.tokD = nullptr; c.hist = nullptr; c.codes = nullptr; c.state = nullptr;
+    c.slots = 0;
+}
+
+int ensureCtx(Ctx*& out)
+{
+    int dev = t_device;
+    if (dev < 0) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) return fail(ZZGPU_E_NO_DEVICE, "no CUDA device", e);
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+        t_device = dev;
+    }
+    if (dev >= kMaxDevices) return fail(ZZGPU_E_ARG, "device index too large");
+    Ctx& c = g_ctx[dev];
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!c.ready) {
+            CK(cudaSetDevice(dev));
+            CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            for (auto& e : c.ev) CK(cudaEventCreate(&e));
+            CK(cudaMalloc(&c.total, 4 * sizeof(uint64_t)));
+            CK(cudaMallocHost(&c.hTotal, 4 * sizeof(uint64_t)));
+            CK(configure_kernels());
+            c.device = dev;
+            c.ready = true;
+        }
+    }
+    CK(cudaSetDevice(dev));
+    out = &c;
+    return ZZGPU_OK;
+}
+
+int ensureScratch(Ctx& c, uint32_t slots, uint32_t chunk)
+{
+    if (c.slots >= slots && c.slotChunk >= chunk) return ZZGPU_OK;
+    freeScratch(c);
+    CK(cudaMalloc(&c.cand, (size_t)slots * chunk * sizeof(uint16_t)));
+    CK(cudaMalloc(&c.tokA, (size_t)slots * kMaxTokens * sizeof(uint32_t)));
+    CK(cudaMalloc(&c.tokD, (size_t)slots * kMaxTokens * sizeof(uint16_t)));
+    CK(cudaMalloc(&c.hist, (size_t)slots * kHistStride * sizeof(uint32_t)));
+    CK(cudaMalloc(&c.codes, (size_t)slots * sizeof(ChunkCodes)));
+    CK(cudaMalloc(&c.state, (size_t)slots * sizeof(ChunkState)));
+    c.slots = slots; c.slotChunk = chunk;
+    return ZZGPU_OK;
+}
+
+template <class T>
+int ensureBuf(T*& p, size_t& cap, size_t need, bool pinned = false)
+{
+    if (cap >= need && p) return ZZGPU_OK;
+    if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
+    size_t bytes = std::max<size_t>(need, 256) * sizeof(T);
+    cudaError_t e = pinned ? cudaMallocHost(&p, bytes) : cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(ZZGPU_E_NOMEM, "allocation failed", e);
+    cap = std::max<size_t>(need, 256);
+    return ZZGPU_OK;
+}
+
+bool validParams(int level, uint32_t chunk, uint32_t dict)
+{
+    return level >= 0 && level <= 3 && chunk >= 1024 && chunk <= ZZGPU_MAX_CHUNK && (chunk % 32) == 0 &&
+           dict <= ZZGPU_MAX_DICT;
+}
+
+// Runs the device pipeline over all chunks of the call.  d_src points at stream position 0 of the call in
+// device memory (history bytes before it), d_dst receives the stream.
+int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap,
+                int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t& launches)
+{
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    const uint32_t slots = (uint32_t)std::min<uint64_t>(nchunks, kMaxSlots);
+    int rc = ensureScratch(c, slots, chunk); if (rc) return rc;
+    if (wantCk) { rc = ensureBuf(c.ck, c.ckCap, 2 * nchunks); if (rc) return rc; }
+    CK(cudaMemsetAsync(c.total, 0, 4 * sizeof(uint64_t), c.stream));
+    for (uint64_t first = 0; first < nchunks; first += slots) {
+        Job job{};
+        job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
+        job.first_chunk = first; job.nchunks = (uint32_t)std::min<uint64_t>(slots, nchunks - first);
+        job.final_stream = final; job.level = level; job.want_checksums = wantCk;
+        job.cand = c.cand; job.tokA = c.tokA; job.tokD = c.tokD; job.hist = c.hist; job.codes = c.codes; job.state = c.state;
+        job.dst = d_dst; job.cap = cap; job.total = c.total; job.ck = c.ck;
+        if (level >= 2) {
+            launches += launch_candidates(job, c.stream);
+            launches += launch_parse(job, c.stream);
+        }
+        if (level == 1) {
+            launches += launch_fixed(job, c.stream);
+        } else {
+            launches += launch_huffman(job, c.stream);
+        }
+        launches += launch_offsets(job, c.stream);
+        launches += launch_emit(job, c.stream);
+        if (wantCk) launches += launch_checksums(job, c.stream);
+    }
+    CK(cudaGetLastError());
+    return ZZGPU_OK;
+}
+
+int foldChecksums(Ctx& c, size_t n, uint32_t chunk, int wantCk, uint32_t* adler0, uint32_t* crc)
+{
+    if (!wantCk) return ZZGPU_OK;
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    int rc = ensureBuf(c.hCk, c.hCkCap, 2 * nchunks, true); if (rc) return rc;
+    CK(cudaMemcpyAsync(c.hCk, c.ck, 2 * nchunks * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    uint32_t a = 0, r = 0;
+    for (uint64_t k = 0; k < nchunks; ++k) {
+        const size_t len = (size_t)std::min<uint64_t>(chunk, n - k * chunk);
+        a = adler32_combine(a, c.hCk[2 * k], len);
+        r = crc32_combine(r, c.hCk[2 * k + 1], len);
+    }
+    if (adler0) *adler0 = a;
+    if (crc) *crc = r;
+    return ZZGPU_OK;
+}
+
+const uint8_t kEmptyFinalStored[5] = { 0x01, 0x00, 0x00, 0xFF, 0xFF };     // R7: empty input still gets one final block
+
+}  // namespace
+
+extern "C" {
+
+int zzgpu_init(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(ZZGPU_E_NO_DEVICE, "no CUDA device", e);
+    if (device < 0 || device >= count) return fail(ZZGPU_E_ARG, "bad device index");
+    t_device = device;
+    Ctx* c = nullptr;
+    return ensureCtx(c);
+}
+
+void zzgpu_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& c : g_ctx) {
+        if (!c.ready) continue;
+        cudaSetDevice(c.device);
+        cudaStreamSynchronize(c.stream);
+        freeScratch(c);
+        cudaFree(c.total); cudaFreeHost(c.hTotal); cudaFree(c.ck); cudaFreeHost(c.hCk); cudaFree(c.dIn); cudaFree(c.dOut);
+        for (auto& e : c.ev) cudaEventDestroy(e);
+        cudaStreamDestroy(c.stream);
+        c.total = nullptr; c.hTotal = nullptr; c.ck = nullptr; c.hCk = nullptr; c.dIn = nullptr; c.dOut = nullptr;
+        c.ckCap = c.hCkCap = c.dInCap = c.dOutCap = 0;
+        c.ready = false;
+    }
+}
+
+int zzgpu_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+const char* zzgpu_strerror(int status)
+{
+    switch (status) {
+    case ZZGPU_OK: return "ok";
+    case ZZGPU_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case ZZGPU_E_CUDA: return "CUDA error";
+    case ZZGPU_E_ARG: return "invalid argument";
+    case ZZGPU_E_CAPACITY: return "destination buffer too small";
+    case ZZGPU_E_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+
+const char* zzgpu_last_error(void) { return t_lastError.c_str(); }
+
+size_t zzgpu_bound(size_t n, int level, uint32_t chunk)
+{
+    if (chunk == 0) chunk = ZZGPU_DEFAULT_CHUNK;
+    const size_t chunks = n ? (n + chunk - 1) / chunk : 1;
+    const size_t per = level == 1 ? ((size_t)chunk * 9 + 7) / 8 + 16 : (size_t)chunk + 16;
+    return chunks * per;
+}
+
+int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int final, int src_mem,
+                     uint8_t* dst, size_t cap, int dst_mem,
+                     int level, uint32_t chunk, uint32_t dict, int want_checksums,
+                     size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats)
+{
+    if (chunk == 0) chunk = ZZGPU_DEFAULT_CHUNK;
+    if (!validParams(level, chunk, dict) || !out_len || (!src && n) || (!dst && cap)) return fail(ZZGPU_E_ARG, "invalid argument");
+    Ctx* cp = nullptr;
+    int rc = ensureCtx(cp); if (rc) return rc;
+    Ctx& c = *cp;
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (adler0) *adler0 = 0;
+    if (crc) *crc = 0;
+
+    if (n == 0) {
+        *out_len = 0;
+        if (final) {
+            if (cap < 5) return fail(ZZGPU_E_CAPACITY, "destination too small");
+            if (dst_mem == ZZGPU_MEM_HOST) memcpy(dst, kEmptyFinalStored, 5);
+            else { CK(cudaMemcpyAsync(dst, kEmptyFinalStored, 5, cudaMemcpyHostToDevice, c.stream)); CK(cudaStreamSynchronize(c.stream)); }
+            *out_len = 5;
+        }
+        return ZZGPU_OK;
+    }
+
+    uint64_t launches = 0;
+    const size_t hist = std::min<size_t>(history, (size_t)dict + kPreExtra);    // bytes the kernels may look at
+    CK(cudaEventRecord(c.ev[0], c.stream));
+    const uint8_t* d_src = src;
+    size_t h2d = 0, d2h = 0;
+    if (src_mem == ZZGPU_MEM_HOST) {
+        rc = ensureBuf(c.dIn, c.dInCap, hist + n + 64); if (rc) return rc;
+        CK(cudaMemcpyAsync(c.dIn, src - hist, hist + n, cudaMemcpyHostToDevice, c.stream));
+        d_src = c.dIn + hist;
+        h2d = hist + n;
+    }
+    uint8_t* d_dst = dst;
+    size_t d_cap = cap;
+    if (dst_mem == ZZGPU_MEM_HOST) {
+        d_cap = std::min(cap, zzgpu_bound(n, level, chunk));
+        rc = ensureBuf(c.dOut, c.dOutCap, d_cap + 64); if (rc) return rc;
+        d_dst = c.dOut;
+    }
+    CK(cudaEventRecord(c.ev[1], c.stream));
+    rc = runPipeline(c, d_src, n, hist, final, d_dst, d_cap, level, chunk, dict, want_checksums, launches);
+    if (rc) return rc;
+    CK(cudaEventRecord(c.ev[2], c.stream));
+    CK(cudaMemcpyAsync(c.hTotal, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    const uint64_t total = c.hTotal[0], flags = c.hTotal[1];
+    if (flags & 1) return fail(ZZGPU_E_CAPACITY, "destination too small");
+    if (flags & ~1ull) return fail(ZZGPU_E_CUDA, "internal consistency check failed (emit size mismatch)");
+    if (total > cap) return fail(ZZGPU_E_CAPACITY, "destination too small");
+    if (dst_mem == ZZGPU_MEM_HOST) {
+        CK(cudaMemcpyAsync(dst, c.dOut, total, cudaMemcpyDeviceToHost, c.stream));
+        d2h = total;
+    }
+    CK(cudaEventRecord(c.ev[3], c.stream));
+    rc = foldChecksums(c, n, chunk, want_checksums, adler0, crc); if (rc) return rc;
+    CK(cudaStreamSynchronize(c.stream));
+    *out_len = (size_t)total;
+    if (stats) {
+        stats->chunks = (n + chunk - 1) / chunk;
+        stats->matches = c.hTotal[2];
+        stats->stored_chunks = c.hTotal[3];
+        stats->kernel_launches = launches;
+        cudaEventElapsedTime(&stats->device_ms, c.ev[1], c.ev[2]);
+        cudaEventElapsedTime(&stats->total_ms, c.ev[0], c.ev[3]);
+        stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
+    }
+    return ZZGPU_OK;
+}
+
+int zzgpu_deflate(const uint8_t* src, size_t n, int src_mem, uint8_t* dst, size_t cap, int dst_mem,
+                  int level, uint32_t chunk, uint32_t dict,
+                  size_t* out_len, uint32_t* adler, uint32_t* crc, zzgpu_stats* stats)
+{
+    const int want = (adler ? 1 : 0) | (crc ? 2 : 0);
+    uint32_t a0 = 0, r = 0;
+    int rc = zzgpu_deflate_ex(src, n, 0, 1, src_mem, dst, cap, dst_mem, level, chunk, dict, want, out_len, &a0, &r, stats);
+    if (rc) return rc;
+    if (adler) *adler = zz::adler32_combine(1, a0, n);
+    if (crc) *crc = r;
+    return ZZGPU_OK;
+}
+
+int zzgpu_checksums(const uint8_t* src, size_t n, int src_mem, uint32_t adler_start, uint32_t crc_start,
+                    uint32_t* adler, uint32_t* crc)
+{
+    if (!src && n) return fail(ZZGPU_E_ARG, "invalid argument");
+    Ctx* cp = nullptr;
+    int rc = ensureCtx(cp); if (rc) return rc;
+    Ctx& c = *cp;
+    std::lock_guard<std::mutex> lk(c.mu);
+    uint32_t a0 = 0, r = 0;
+    if (n) {
+        const uint8_t* d_src = src;
+        if (src_mem == ZZGPU_MEM_HOST) {
+            rc = ensureBuf(c.dIn, c.dInCap, n + 64); if (rc) return rc;
+            CK(cudaMemcpyAsync(c.dIn, src, n, cudaMemcpyHostToDevice, c.stream));
+            d_src = c.dIn;
+        }
+        const uint32_t chunk = ZZGPU_MAX_CHUNK;
+        const uint64_t nchunks = (n + chunk - 1) / chunk;
+        rc = ensureBuf(c.ck, c.ckCap, 2 * nchunks); if (rc) return rc;
+        for (uint64_t first = 0; first < nchunks; first += 32768) {
+            Job job{};
+            job.src = d_src; job.n = n; job.chunk = chunk; job.dict = 0; job.first_chunk = first;
+            job.nchunks = (uint32_t)std::min<uint64_t>(32768, nchunks - first);
+            job.final_stream = 1; job.ck = c.ck;
+            launch_checksums(job, c.stream);
+        }
+        CK(cudaGetLastError());
+        rc = foldChecksums(c, n, chunk, 3, &a0, &r); if (rc) return rc;
+    }
+    if (adler) *adler = zz::adler32_combine(adler_start, a0, n);
+    if (crc) *crc = zz::crc32_combine(crc_start, r, n);
+    return ZZGPU_OK;
+}
+
+uint32_t zzgpu_adler32_combine(uint32_t first, uint32_t second_start0, size_t len_second)
+{
+    return zz::adler32_combine(first, second_start0, len_second);
+}
+
+uint32_t zzgpu_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2)
+{
+    return zz::crc32_combine(crc1, crc2, len2);
+}
+
+int zzgpu_debug_chunk(const uint8_t* src, size_t n, int src_mem, int level, uint32_t chunk, uint32_t dict,
+                      uint64_t chunk_index, uint16_t* cand, uint32_t* tokens, uint32_t max_tokens, uint32_t* n_tokens,
+                      uint32_t* hist, uint8_t* lengths, uint32_t* info)
+{
+    if (chunk == 0) chunk = ZZGPU_DEFAULT_CHUNK;
+    if (!validParams(level, chunk, dict) || level < 2 || !src || n == 0) return fail(ZZGPU_E_ARG, "invalid argument");
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    if (nchunks > kMaxSlots || chunk_index >= nchunks) return fail(ZZGPU_E_ARG, "debug tap needs a single batch");
+    Ctx* cp = nullptr;
+    int rc = ensureCtx(cp); if (rc) return rc;
+    Ctx& c = *cp;
+    std::lock_guard<std::mutex> lk(c.mu);
+    const uint8_t* d_src = src;
+    if (src_mem == ZZGPU_MEM_HOST) {
+        rc = ensureBuf(c.dIn, c.dInCap, n + 64); if (rc) return rc;
+        CK(cudaMemcpyAsync(c.dIn, src, n, cudaMemcpyHostToDevice, c.stream));
+        d_src = c.dIn;
+    }
+    const size_t cap = zzgpu_bound(n, level, chunk);
+    rc = ensureBuf(c.dOut, c.dOutCap, cap + 64); if (rc) return rc;
+    uint64_t launches = 0;
+    rc = runPipeline(c, d_src, n, 0, 1, c.dOut, cap, level, chunk, dict, 0, launches); if (rc) return rc;
+    CK(cudaStreamSynchronize(c.stream));
+    const size_t slot = (size_t)chunk_index;
+    ChunkState st;
+    CK(cudaMemcpy(&st, c.state + slot, sizeof st, cudaMemcpyDeviceToHost));
+    if (cand) CK(cudaMemcpy(cand, c.cand + slot * chunk, (size_t)chunk * 2, cudaMemcpyDeviceToHost));
+    if (n_tokens) *n_tokens = st.ntok;
+    if (tokens) {
+        const uint32_t cnt = std::min(st.ntok, max_tokens);
+        std::vector<uint32_t> a(cnt); std::vector<uint16_t> d(cnt);
+        if (cnt) {
+            CK(cudaMemcpy(a.data(), c.tokA + slot * kMaxTokens, cnt * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(d.data(), c.tokD + slot * kMaxTokens, cnt * 2, cudaMemcpyDeviceToHost));
+        }
+        for (uint32_t i = 0; i < cnt; ++i) { tokens[3 * i] = a[i] & 0xFFFF; tokens[3 * i + 1] = a[i] >> 16; tokens[3 * i + 2] = d[i]; }
+    }
+    if (hist) CK(cudaMemcpy(hist, c.hist + slot * kHistStride, 316 * 4, cudaMemcpyDeviceToHost));
+    if (lengths) {
+        ChunkCodes* cc = c.codes + slot;
+        CK(cudaMemcpy(lengths, cc->lens, 335, cudaMemcpyDeviceToHost));
+    }
+    if (info) { info[0] = st.block_type; info[1] = st.hdr_bits; info[2] = st.out_bytes; info[3] = (uint32_t)st.total_bits; }
+    return ZZGPU_OK;
+}
+
+}  // extern "C"

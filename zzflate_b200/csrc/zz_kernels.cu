@@ -1,0 +1,1016 @@
+// sm_100a kernels of the deflate-encode hot path.
+//
+// Pipeline per batch of chunks (one chunk = up to 64 KiB of input + up to 32 KiB of dictionary):
+//
+//   K-CAND   k_candidates  hash heads: nearest earlier position with the same 13-bit hash, per position
+//                          (replaces CalcHash / the table probe+insert of FirstPass / AddHashEntries,
+//                           zzflate/encoder.cpp:11-17,388-390,474-480)
+//   K-MATCH  k_parse       match verification, greedy acceptance with backward extension, histograms
+//                          (FirstPass, countMatchBackward, remain, GetFrequencies; encoder.cpp:375-471)
+//   K-HUFF   k_huffman     code lengths (libstdc++-heap Huffman with the reference's limiter), canonical
+//                          codes, code-length RLE, exact block size, stored fallback decision, block header
+//                          (huffman.cpp:67-216, huffman.h:49-81, encoder.cpp:171-187,250-293)
+//   K-OFFS   k_offsets     exclusive scan of chunk sizes -> output offsets (stitch of zzflate.cpp:136-154)
+//   K-EMIT   k_emit        bit emission of header, records, EOB and the aligning stored block
+//                          (WriteRecords / WriteDistance / StartBlock / outputbitstream; encoder.cpp:135-169,
+//                           UncompressedFallback / WriteUncompressedBlock; encoder.cpp:305-317,482-502)
+//   K-CKSUM  k_checksums   per-chunk Adler-32 / CRC-32 partials (adler.cpp:17, crc.cpp:24)
+//
+// Everything is integer work; nothing here is a dense contraction, so tensor cores are not used.
+#include "zz_kernels.cuh"
+#include <cstdio>
+
+namespace zz {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// geometry of one chunk
+// ------------------------------------------------------------------------------------------------
+struct Geom {
+    long long off;   // offset of the chunk in this call's input
+    int n;           // bytes in the chunk
+    int dict;        // dictionary bytes that prime the hash table
+    int pre;         // readable history kept in the window (dict + slack for backward extension)
+    int body;        // bytes of the main block: n-1 for non-final chunks (zzflate.cpp:116), n for the final one
+    int final;
+    int t0;          // tokeniser target: positions >= t0 are never probed (encoder.cpp:222)
+};
+
+__device__ __forceinline__ Geom chunk_geom(const Job& job, unsigned slot)
+{
+    Geom g;
+    unsigned long long c = job.first_chunk + slot;
+    g.off = (long long)(c * job.chunk);
+    unsigned long long rem = job.n - (unsigned long long)g.off;
+    g.n = (int)(rem < job.chunk ? rem : job.chunk);
+    unsigned long long before = (unsigned long long)g.off + job.history;
+    g.dict = (int)(before < job.dict ? before : job.dict);
+    unsigned long long pre = (unsigned long long)g.dict + kPreExtra;
+    g.pre = (int)(before < pre ? before : pre);
+    g.final = ((unsigned long long)g.off + g.n == job.n) && job.final_stream;
+    g.body = g.final ? g.n : g.n - 1;
+    g.t0 = g.body > kMaxMatch ? g.body - kMaxMatch : 0;
+    return g;
+}
+
+__device__ __forceinline__ unsigned hash3(unsigned v24)            // encoder.cpp:11-17
+{
+    return (v24 * 0x00d68664u) >> (32 - kHashBits);
+}
+
+// distance -> distance symbol / extra bits (luts.cpp:64,79-116 regenerated arithmetically)
+__device__ __forceinline__ int dist_symbol(int d, int& extraBits, int& extraVal)
+{
+    int t = d - 1;
+    if (t < 4) { extraBits = 0; extraVal = 0; return t; }
+    int nb = 31 - __clz(t);
+    extraBits = nb - 1;
+    extraVal = t & ((1 << extraBits) - 1);
+    return 2 * nb + ((t >> extraBits) & 1);
+}
+
+// match length -> length symbol / extra bits (luts.cpp:5-58)
+__device__ __forceinline__ int len_symbol(int len, int& extraBits, int& extraVal)
+{
+    int l = len - 3;
+    if (l < 8) { extraBits = 0; extraVal = 0; return 257 + l; }
+    if (len == 258) { extraBits = 0; extraVal = 0; return 285; }
+    int nb = 31 - __clz(l);
+    extraBits = nb - 2;
+    extraVal = l & ((1 << extraBits) - 1);
+    return 257 + 4 * extraBits + 4 + ((l >> extraBits) & 3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-CAND : one warp per chunk, table in shared memory
+// ------------------------------------------------------------------------------------------------
+constexpr int kEmptySlot = -(1 << 30);
+
+__global__ void __launch_bounds__(32) k_candidates(Job job)
+{
+    __shared__ int table[kHashSize];
+    const unsigned slot = blockIdx.x;
+    const Geom g = chunk_geom(job, slot);
+    const int lane = threadIdx.x;
+    for (int i = lane; i < kHashSize; i += 32) table[i] = kEmptySlot;
+    __syncwarp();
+
+    const uint8_t* base = job.src + g.off;
+    const long long limit = (long long)job.n - g.off;          // bytes readable at and after the chunk start
+    uint16_t* cand = job.cand + (size_t)slot * job.chunk;
+
+    for (int j0 = -g.dict; j0 < g.n; j0 += 32) {
+        const int j = j0 + lane;
+        unsigned v = 0;
+        if (j < g.n) {
+            v = (j < limit) ? base[j] : 0u;
+            v |= (j + 1 < limit) ? ((unsigned)base[j + 1] << 8) : 0u;
+            v |= (j + 2 < limit) ? ((unsigned)base[j + 2] << 16) : 0u;
+        }
+        const unsigned h = hash3(v);
+        // position 0 of a block is neither probed nor inserted (encoder.cpp:384); dictionary positions are
+        // inserted only (AddHashEntries, encoder.cpp:474)
+        const bool act = (j != 0) && (j < g.n);
+        const unsigned key = act ? h : (0x10000u + lane);
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const unsigned lower = grp & ((1u << lane) - 1u);
+        const bool last = (grp >> lane) == 1u;
+        const int old = act ? table[h] : kEmptySlot;
+        __syncwarp();
+        if (act && last) table[h] = j;
+        __syncwarp();
+        if (j >= 0 && j < g.n) {
+            const int p = lower ? (j0 + 31 - __clz(lower)) : old;
+            const int d = j - p;
+            cand[j] = (uint16_t)((act && d < kMaxDistance) ? d : 0);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory window helpers
+// ------------------------------------------------------------------------------------------------
+constexpr int kPreCap = kMaxDict + kPreExtra;                       // 33056, multiple of 16
+constexpr int kWinBytes = kPreCap + 16 + kMaxChunk + 64;            // + alignment slack + tail pad
+static_assert(kPreCap % 16 == 0, "window base must keep 16-byte phase");
+
+// Copies src[lo, hi) (positions relative to the chunk start) into win so that position i lands at byte
+// wb + i, where wb = kPreCap + ((uintptr)(chunk start) & 15): global and shared 16-byte phases agree and the
+// interior moves as 128-bit loads/stores.
+__device__ __forceinline__ void load_window(uint8_t* win, int wb, const uint8_t* chunk0, int lo, int hi, int padTo)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int s_lo = wb + lo, s_hi = wb + hi;
+    int a_lo = (s_lo + 15) & ~15, a_hi = s_hi & ~15;
+    if (a_lo >= a_hi) {
+        for (int s = s_lo + tid; s < s_hi; s += nt) win[s] = chunk0[s - wb];
+    } else {
+        for (int s = s_lo + tid; s < a_lo; s += nt) win[s] = chunk0[s - wb];
+        for (int s = a_hi + tid; s < s_hi; s += nt) win[s] = chunk0[s - wb];
+        const uint4* gsrc = reinterpret_cast<const uint4*>(chunk0 + (a_lo - wb));
+        uint4* sdst = reinterpret_cast<uint4*>(win + a_lo);
+        const int nvec = (a_hi - a_lo) >> 4;
+        for (int k = tid; k < nvec; k += nt) sdst[k] = __ldg(gsrc + k);
+    }
+    for (int s = s_hi + tid; s < wb + padTo; s += nt) win[s] = 0;
+}
+
+__device__ __forceinline__ unsigned ld4(const uint8_t* win, int o)          // unaligned 4-byte load
+{
+    const unsigned* w = reinterpret_cast<const unsigned*>(win) + (o >> 2);
+    return __funnelshift_r(w[0], w[1], (o & 3) * 8);
+}
+
+__device__ __forceinline__ unsigned long long ld8(const uint8_t* win, int o)
+{
+    const unsigned* w = reinterpret_cast<const unsigned*>(win) + (o >> 2);
+    unsigned a = w[0], b = w[1], c = w[2];
+    int sh = (o & 3) * 8;
+    unsigned lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// Parse-independent part of the acceptance rule: need = 4 - min(fwd,4); a position is usable
+// when the candidate supplies `need` bytes backwards.  Returns need (0..4) or 7 when unusable.
+__device__ __forceinline__ int position_info(const uint8_t* win, int wb, int j, int d, int pre)
+{
+    if (d == 0) return 7;
+    const int p = j - d;
+    unsigned x = ld4(win, wb + j) ^ ld4(win, wb + p);
+    int fwd4 = x ? ((__ffs(x) - 1) >> 3) : 4;
+    if (fwd4 == 4) return 0;
+    const int need = 4 - fwd4;
+    unsigned y = ld4(win, wb + j - 4) ^ ld4(win, wb + p - 4);
+    int back4 = y ? (__clz(y) >> 3) : 4;
+    int room = p + pre;                                  // bytes of real history before the candidate (R4 clamp)
+    if (back4 > room) back4 = room;
+    return back4 >= need ? need : 7;
+}
+
+struct ParseShared {
+    int pos;            // start of the next FirstPass batch
+    int ntok;
+    int nexcl;          // batch starts that were never inserted into the hash table
+    int excl[4];
+    int npatch;         // positions whose candidate changes because of an excluded batch start
+    int patchJ[4];
+    int patchD[4];
+    int fixS;           // excluded position whose successor still has to be found, or -1
+    int fixJ;
+};
+
+// candidate of j with the never-inserted batch starts removed from the hash chain
+__device__ int effective_cand(const uint16_t* cand, const ParseShared* ps, int j)
+{
+    int d = cand[j];
+    for (;;) {
+        if (d == 0) return 0;
+        const int p = j - d;
+        bool hit = false;
+        for (int k = 0; k < ps->nexcl; ++k) hit |= (ps->excl[k] == p);
+        if (!hit) return d;
+        const int dd = p > 0 ? cand[p] : 0;
+        if (dd == 0) return 0;
+        d += dd;
+        if (d >= kMaxDistance) return 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-MATCH : one CTA per chunk
+// ------------------------------------------------------------------------------------------------
+constexpr int kParseThreads = 1024;
+constexpr int kParseSmem = kWinBytes + kMaxChunk /*info*/ + (kMaxChunk / 32) * 4 /*okbits*/;
+
+// Walks positions [a,b) of a chunk against its sorted match list; calls lit(pos) for every literal and
+// match(k, start, len) for every match that starts inside [a,b).
+template <class Lit, class Match>
+__device__ __forceinline__ void walk_positions(const uint32_t* tokA, int ntok, int a, int b, Lit lit, Match match)
+{
+    int lo = 0, hi = ntok;                              // first match whose end is > a
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        uint32_t t = tokA[mid];
+        int end = (int)(t & 0xFFFF) + (int)(t >> 16);
+        if (end > a) hi = mid; else lo = mid + 1;
+    }
+    int k = lo, pos = a;
+    while (pos < b) {
+        int ms = 0x7fffffff, ln = 0;
+        if (k < ntok) { uint32_t t = tokA[k]; ms = (int)(t & 0xFFFF); ln = (int)(t >> 16); }
+        if (ms < pos) { pos = ms + ln; ++k; continue; }           // inside a match that started before a
+        const int litEnd = ms < b ? ms : b;
+        for (; pos < litEnd; ++pos) lit(pos);
+        if (pos == ms && pos < b) { match(k, ms, ln); pos += ln; ++k; }
+    }
+}
+
+__global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* win = smem;
+    uint8_t* info = smem + kWinBytes;
+    unsigned* okbits = reinterpret_cast<unsigned*>(smem + kWinBytes + kMaxChunk);
+    __shared__ ParseShared ps;
+
+    const unsigned slot = blockIdx.x;
+    const Geom g = chunk_geom(job, slot);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kParseThreads >> 5;
+    const uint8_t* chunk0 = job.src + g.off;
+    const int wb = kPreCap + (int)(reinterpret_cast<uintptr_t>(chunk0) & 15);
+    const uint16_t* cand = job.cand + (size_t)slot * job.chunk;
+    uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
+    uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
+
+    load_window(win, wb, chunk0, -g.pre, g.n, g.n + 48);
+    if (tid == 0) { ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npatch = 0; ps.fixS = -1; ps.fixJ = -1; }
+    __syncthreads();
+
+    // ---- phase A: per-position usability (parse independent) ----
+    const int t0 = g.t0;
+    const int nsteps = (t0 + 31) >> 5;
+    for (int s = warp; s < nsteps; s += nwarps) {
+        const int j = s * 32 + lane;
+        int inf = 7;
+        if (j >= 1 && j < t0) inf = position_info(win, wb, j, cand[j], g.pre);
+        info[j] = (uint8_t)inf;
+        const unsigned m = __ballot_sync(0xffffffffu, inf != 7);
+        if (lane == 0) okbits[s] = m;
+    }
+    __syncthreads();
+
+    // ---- phase B: greedy acceptance, batch by batch (WriteBlock2Pass loop, encoder.cpp:225-234) ----
+    for (;;) {
+        const int pos = ps.pos;
+        if (pos >= t0) break;
+        const int fixS = ps.fixS;
+        if (fixS >= 0) {
+            // the batch start fixS was never inserted: its successor in the hash chain must see fixS's
+            // own predecessor instead.  Find the successor (first j > fixS whose raw candidate is fixS).
+            int hiJ = fixS + kMaxDistance; if (hiJ > t0) hiJ = t0;
+            for (int j = fixS + 1 + tid; j < hiJ; j += kParseThreads)
+                if ((int)cand[j] == j - fixS) atomicMin(&ps.fixJ, j);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (fixS >= 0) {
+                const int fj = ps.fixJ;
+                if (fj < 0x7fffffff && lane == 0) {
+                    const int d = effective_cand(cand, &ps, fj);
+                    const int k = ps.npatch++;
+                    ps.patchJ[k] = fj; ps.patchD[k] = d;
+                    const int inf = position_info(win, wb, fj, d, g.pre);
+                    info[fj] = (uint8_t)inf;
+                    unsigned bit = 1u << (fj & 31);
+                    if (inf != 7) okbits[fj >> 5] |= bit; else okbits[fj >> 5] &= ~bit;
+                }
+                __syncwarp();
+            }
+            int E = pos + kBatch; if (E > t0) E = t0;
+            int B = pos + 1, jmin = pos + 1;            // FirstPass: backRefEnd = j = startPos + 1
+            int ntok = ps.ntok;
+            for (;;) {
+                int j = -1;
+                {
+                    const int x = jmin + lane;
+                    const int inf = (x < E) ? info[x] : 7;
+                    const bool el = (inf != 7) && (x - B >= inf);
+                    const unsigned m = __ballot_sync(0xffffffffu, el);
+                    if (m) {
+                        j = jmin + __ffs(m) - 1;
+                    } else {
+                        // every usable position at distance >= 4 from B is acceptable: scan the bitmap
+                        int start = jmin + 32;
+                        int w0 = start >> 5;
+                        const int wEnd = (E + 31) >> 5;
+                        while (w0 < wEnd) {
+                            const int w = w0 + lane;
+                            unsigned bits = (w < wEnd) ? okbits[w] : 0u;
+                            if (w == (start >> 5)) bits &= ~0u << (start & 31);
+                            const unsigned any = __ballot_sync(0xffffffffu, bits != 0);
+                            if (any) {
+                                const int src = __ffs(any) - 1;
+                                const unsigned b = __shfl_sync(0xffffffffu, bits, src);
+                                j = (w0 + src) * 32 + __ffs(b) - 1;
+                                break;
+                            }
+                            w0 += 32;
+                        }
+                    }
+                }
+                if (j < 0 || j >= E) break;
+                // exact match at j: forward to 258, backward into the pending literals (encoder.cpp:399-416)
+                int d = cand[j];
+                for (int k = 0; k < ps.npatch; ++k) if (ps.patchJ[k] == j) d = ps.patchD[k];
+                const int p = j - d;
+                int fwd;
+                {
+                    const unsigned long long xa = ld8(win, wb + j + lane * 8) ^ ld8(win, wb + p + lane * 8);
+                    const unsigned mm = __ballot_sync(0xffffffffu, xa != 0);
+                    if (mm) {
+                        const int src = __ffs(mm) - 1;
+                        const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src);
+                        fwd = src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
+                    } else {
+                        fwd = 256;
+                        if (win[wb + j + 256] == win[wb + p + 256]) { fwd = 257; if (win[wb + j + 257] == win[wb + p + 257]) fwd = 258; }
+                    }
+                }
+                int lb = 0;
+                int maxBack = j - B;
+                {
+                    int room = p + g.pre; if (room < maxBack) maxBack = room;       // R4: clamp at stream start
+                    if (maxBack > 258) maxBack = 258;                               // R6: cap (reference breaks at 259)
+                    if (maxBack > 0) {
+                        const unsigned long long xb = ld8(win, wb + j - 8 - lane * 8) ^ ld8(win, wb + p - 8 - lane * 8);
+                        const unsigned mm = __ballot_sync(0xffffffffu, xb != 0);
+                        if (mm) {
+                            const int src = __ffs(mm) - 1;
+                            const unsigned long long xs = __shfl_sync(0xffffffffu, xb, src);
+                            lb = src * 8 + (__clzll((long long)xs) >> 3);
+                        } else {
+                            lb = 256;
+                            if (win[wb + j - 257] == win[wb + p - 257]) { lb = 257; if (win[wb + j - 258] == win[wb + p - 258]) lb = 258; }
+                        }
+                        if (lb > maxBack) lb = maxBack;
+                    }
+                }
+                int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
+                const int ms = j - lb;
+                if (lane == 0) {
+                    tokA[ntok] = (uint32_t)ms | ((uint32_t)m << 16);
+                    tokD[ntok] = (uint16_t)d;
+                }
+                ++ntok;
+                B = ms + m;
+                jmin = B + 1;
+            }
+            if (lane == 0) {
+                ps.ntok = ntok;
+                const int newpos = B > E ? B : E;
+                ps.fixS = -1; ps.fixJ = 0x7fffffff;
+                if (B < E && newpos < t0) {            // next batch start was not covered by a match: never inserted
+                    ps.excl[ps.nexcl++] = newpos;
+                    ps.fixS = newpos;
+                }
+                ps.pos = newpos;
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+
+    // ---- phase C: histograms (GetFrequencies, encoder.cpp:442-471) ----
+    unsigned* hist = reinterpret_cast<unsigned*>(info);            // per-warp private copies (info is dead)
+    for (int i = tid; i < nwarps * kHistStride; i += kParseThreads) hist[i] = 0;
+    __syncthreads();
+    {
+        const int ntok = ps.ntok;
+        unsigned* myh = hist + warp * kHistStride;
+        const int per = (g.body + kParseThreads - 1) / kParseThreads;
+        int a = tid * per, b = a + per; if (b > g.body) b = g.body;
+        if (a < b) {
+            walk_positions(tokA, ntok, a, b,
+                [&](int pos) { atomicAdd(&myh[win[wb + pos]], 1u); },
+                [&](int k, int, int ln) {
+                    int eb, ev;
+                    atomicAdd(&myh[len_symbol(ln, eb, ev)], 1u);
+                    atomicAdd(&myh[286 + dist_symbol(tokD[k], eb, ev)], 1u);
+                });
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 316; i += kParseThreads) {
+        unsigned s = 0;
+        for (int w = 0; w < nwarps; ++w) s += hist[w * kHistStride + i];
+        if (i == 256) s += 1;                                       // end-of-block (encoder.cpp:470)
+        job.hist[(size_t)slot * kHistStride + i] = s;
+    }
+    if (tid == 0) job.state[slot].ntok = ps.ntok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-HUFF : one thread per chunk (tie-breaks follow the libstdc++ heap layout, so the tree build is serial)
+// ------------------------------------------------------------------------------------------------
+struct HRec { int f; int id; };
+
+__device__ void heap_push_(HRec* h, int hole, int top, HRec v)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > top && h[parent].f > v.f) {
+        h[hole] = h[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    h[hole] = v;
+}
+
+__device__ void heap_adjust(HRec* h, int hole, int len, HRec v)
+{
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (h[child].f > h[child - 1].f) child--;
+        h[hole] = h[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        h[hole] = h[child - 1];
+        hole = child - 1;
+    }
+    heap_push_(h, hole, top, v);
+}
+
+// CalcLengths (huffman.cpp:122-154).  n <= 286.  Work arrays are caller-provided.
+__device__ __noinline__ void calc_lengths(const int* freqs, int n, int maxLength, uint8_t* lens,
+                             HRec* heap, unsigned short* left, unsigned short* right, uint8_t* depth)
+{
+    int total = 0;
+    for (int i = 0; i < n; ++i) total += freqs[i];
+    int minFreq = 0;
+    for (;;) {
+        int rn = 0;
+        for (int i = 0; i < n; ++i) {
+            if (freqs[i] == 0) continue;
+            HRec r; r.f = freqs[i] > minFreq ? freqs[i] : minFreq; r.id = i;
+            heap[rn++] = r;
+        }
+        if (rn >= 2)
+            for (int parent = (rn - 2) / 2; ; --parent) { heap_adjust(heap, parent, rn, heap[parent]); if (parent == 0) break; }
+        int tn = n;                                              // tree index of the next internal node
+        while (rn >= 2) {
+            HRec a, b;
+            if (rn > 1) { HRec v = heap[rn - 1]; heap[rn - 1] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
+            a = heap[--rn];
+            if (rn > 1) { HRec v = heap[rn - 1]; heap[rn - 1] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
+            b = heap[--rn];
+            left[tn - n] = (unsigned short)a.id; right[tn - n] = (unsigned short)b.id;
+            HRec r; r.f = a.f + b.f; r.id = tn;
+            heap[rn++] = r;
+            heap_push_(heap, rn - 1, 0, r);
+            ++tn;
+        }
+        for (int i = 0; i < tn; ++i) depth[i] = 0;
+        int maxDepth = 0;
+        for (int i = tn - 1; i != 0 && i > 0; --i) {                // index 0 is not visited (huffman.cpp:108)
+            if (i < n) { if (depth[i] > maxDepth) maxDepth = depth[i]; continue; }
+            const uint8_t dd = (uint8_t)(depth[i] + 1);
+            depth[left[i - n]] = dd; depth[right[i - n]] = dd;
+        }
+        if (maxDepth <= maxLength) {
+            for (int i = 0; i < n; ++i) lens[i] = freqs[i] == 0 ? 0 : (depth[i] > 1 ? depth[i] : 1);
+            return;
+        }
+        int step = total / (1 << maxLength);
+        minFreq += step > 1 ? step : 1;
+    }
+}
+
+__device__ __forceinline__ unsigned bit_reverse(unsigned v, int len) { return __brev(v) >> (32 - len); }
+
+// huffman::generate (huffman.h:49-81): canonical codes, bit-reversed.  out[i] = bits | len << 16 (0 if unused)
+__device__ __noinline__ void generate_codes(const uint8_t* lens, int n, uint32_t* out)
+{
+    int blCount[16];
+    for (int i = 0; i < 16; ++i) blCount[i] = 0;
+    for (int i = 0; i < n; ++i) blCount[lens[i]]++;
+    unsigned nextCode[16];
+    unsigned bits = 0;
+    blCount[0] = 0;
+    nextCode[0] = 0;
+    for (int b = 1; b < 16; ++b) { bits = (bits + blCount[b - 1]) << 1; nextCode[b] = bits; }
+    for (int i = 0; i < n; ++i) {
+        const int len = lens[i];
+        if (len == 0) { out[i] = 0; continue; }
+        out[i] = bit_reverse(nextCode[len], len) | ((uint32_t)len << 16);
+        nextCode[len]++;
+    }
+}
+
+// FromLengths / AddRecords (huffman.cpp:158-216): records as value | payLoad << 8
+__device__ __noinline__ int rle_lengths(const uint8_t* lens, int n, unsigned short* rec, int* freqs19)
+{
+    int vn = 0, current = -1, count = 0;
+    for (int i = 0; i <= n; ++i) {
+        const int v = i < n ? lens[i] : -2;
+        if (v == current) { count++; continue; }
+        if (count > 0) {
+            if (current == 0) {
+                while (count >= 3) { int w = count < 138 ? count : 138; count -= w; rec[vn++] = (unsigned short)((w < 11 ? 17 : 18) | (w << 8)); }
+            } else {
+                rec[vn++] = (unsigned short)current; count--;
+                while (count >= 3) { int w = count < 6 ? count : 6; count -= w; rec[vn++] = (unsigned short)(16 | (w << 8)); }
+            }
+            for (int k = 0; k < count; ++k) rec[vn++] = (unsigned short)current;
+        }
+        current = v; count = 1;
+    }
+    for (int i = 0; i < vn; ++i) freqs19[rec[i] & 0xFF]++;
+    return vn;
+}
+
+struct HdrWriter {
+    uint8_t* out; unsigned long long acc; int used; int pos;
+    __device__ void put(unsigned bits, int n) {
+        acc |= (unsigned long long)bits << used; used += n;
+        while (used >= 8) { out[pos++] = (uint8_t)acc; acc >>= 8; used -= 8; }
+    }
+    __device__ void flush() { if (used > 0) { out[pos++] = (uint8_t)acc; acc = 0; used = 0; } }
+};
+
+__device__ const uint8_t kOrder[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };   // luts.cpp:62
+
+__device__ __forceinline__ int len_extra_bits(int sym) { return (sym < 265 || sym == 285) ? 0 : (sym - 261) >> 2; }
+__device__ __forceinline__ int dist_extra_bits(int sym) { return sym < 4 ? 0 : (sym - 2) >> 1; }
+
+__device__ __forceinline__ uint32_t stored_size(int body)           // WriteUncompressedBlock: <= 65535 bytes + 5 per block
+{
+    if (body <= 0) return 0;
+    const int blocks = (body + 0xFFFE) / 0xFFFF;
+    return (uint32_t)(body + 5 * blocks);
+}
+
+constexpr int kHuffThreads = 32;
+
+__global__ void __launch_bounds__(kHuffThreads) k_huffman(Job job)
+{
+    const unsigned slot = blockIdx.x * kHuffThreads + threadIdx.x;
+    if (slot >= job.nchunks) return;
+    const Geom g = chunk_geom(job, slot);
+    ChunkState& st = job.state[slot];
+    ChunkCodes& cc = job.codes[slot];
+    const uint32_t tail = g.final ? 0u : 6u;                        // aligning 1-byte stored block (zzflate.cpp:116-120)
+
+    if (job.level == 0 || g.body == 0) {
+        st.block_type = 0; st.hdr_bits = 0; st.total_bits = 0;
+        st.out_bytes = stored_size(g.body) + tail;
+        if (job.level == 0) st.ntok = 0;
+        return;
+    }
+
+    HRec heap[286];
+    unsigned short left[286], right[286];
+    uint8_t depth[572];
+    int freq[286];
+    int metaF[19];
+    unsigned short symRec[288], distRec[32];
+    uint32_t metaCodes[19];
+    uint8_t metaL[19];
+
+    const uint32_t* hist = job.hist + (size_t)slot * kHistStride;
+    long long bits = 0;
+
+    for (int i = 0; i < 19; ++i) metaF[i] = 0;
+    for (int i = 0; i < 286; ++i) freq[i] = (int)hist[i];
+    calc_lengths(freq, 286, 15, cc.lens, heap, left, right, depth);
+    generate_codes(cc.lens, 286, cc.lit);
+    const int nSym = rle_lengths(cc.lens, 286, symRec, metaF);
+    for (int i = 0; i < 286; ++i) bits += (long long)freq[i] * (cc.lens[i] + len_extra_bits(i));
+
+    for (int i = 0; i < 30; ++i) freq[i] = (int)hist[286 + i];
+    calc_lengths(freq, 30, 15, cc.lens + 286, heap, left, right, depth);
+    generate_codes(cc.lens + 286, 30, cc.dist);
+    const int nDist = rle_lengths(cc.lens + 286, 30, distRec, metaF);
+    for (int i = 0; i < 30; ++i) bits += (long long)freq[i] * (cc.lens[286 + i] + dist_extra_bits(i));
+
+    calc_lengths(metaF, 19, 7, metaL, heap, left, right, depth);
+    generate_codes(metaL, 19, metaCodes);
+    for (int i = 0; i < 19; ++i) cc.lens[316 + i] = metaL[i];
+
+    long long total = 3 + 5 + 5 + 4 + 3 * 19 + bits;
+    for (int pass = 0; pass < 2; ++pass) {
+        const unsigned short* rec = pass ? distRec : symRec;
+        const int cnt = pass ? nDist : nSym;
+        for (int i = 0; i < cnt; ++i) {
+            const int v = rec[i] & 0xFF;
+            total += metaL[v] + (v == 16 ? 2 : v == 17 ? 3 : v == 18 ? 7 : 0);
+        }
+    }
+    st.total_bits = (uint64_t)total;
+    const long long required = (total + 8) / 8;                      // encoder.cpp:269
+    if (required >= g.body) {                                        // UncompressedFallback (encoder.cpp:271-274)
+        st.block_type = 0; st.hdr_bits = 0;
+        st.out_bytes = stored_size(g.body) + tail;
+        return;
+    }
+    st.block_type = 2;
+    HdrWriter w; w.out = cc.hdr; w.acc = 0; w.used = 0; w.pos = 0;
+    w.put(g.final ? 1u : 0u, 1); w.put(2u, 2);                       // StartBlock (encoder.cpp:143-147)
+    w.put(29u, 5); w.put(29u, 5); w.put(15u, 4);                     // encoder.cpp:283-285
+    for (int i = 0; i < 19; ++i) w.put(metaL[kOrder[i]], 3);
+    int hdrBits = 17 + 57;
+    for (int pass = 0; pass < 2; ++pass) {                           // WriteLengths (encoder.cpp:20-35)
+        const unsigned short* rec = pass ? distRec : symRec;
+        const int cnt = pass ? nDist : nSym;
+        for (int i = 0; i < cnt; ++i) {
+            const int v = rec[i] & 0xFF, pl = rec[i] >> 8;
+            const uint32_t c = metaCodes[v];
+            w.put(c & 0xFFFF, (int)(c >> 16)); hdrBits += (int)(c >> 16);
+            if (v == 16) { w.put((unsigned)(pl - 3), 2); hdrBits += 2; }
+            else if (v == 17) { w.put((unsigned)(pl - 3), 3); hdrBits += 3; }
+            else if (v == 18) { w.put((unsigned)(pl - 11), 7); hdrBits += 7; }
+        }
+    }
+    w.flush();
+    st.hdr_bits = (uint32_t)hdrBits;
+    // dynamic block occupies `total` bits; a non-final chunk appends 3 header bits, pads, then LEN/NLEN + 1 byte
+    st.out_bytes = g.final ? (uint32_t)((total + 7) / 8) : (uint32_t)((total + 3 + 7) / 8) + 5u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-OFFS : exclusive scan of chunk sizes
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_offsets(Job job)
+{
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry;
+    __shared__ unsigned long long cnt[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry = job.total[0]; cnt[0] = 0; cnt[1] = 0; }
+    __syncthreads();
+    unsigned long long matches = 0, stored = 0;
+    for (unsigned base = 0; base < job.nchunks; base += 1024) {
+        const unsigned slot = base + tid;
+        unsigned long long v = 0;
+        if (slot < job.nchunks) {
+            v = job.state[slot].out_bytes;
+            matches += job.state[slot].ntok;
+            stored += job.state[slot].block_type == 0 ? 1 : 0;
+        }
+        unsigned long long inc = v;
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long s = wsum[lane];
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const unsigned long long before = carry + (warp ? wsum[warp - 1] : 0) + inc - v;
+        if (slot < job.nchunks) job.state[slot].out_off = before;
+        __syncthreads();
+        if (tid == 0) carry += wsum[31];
+        __syncthreads();
+    }
+    atomicAdd(&cnt[0], matches); atomicAdd(&cnt[1], stored);
+    __syncthreads();
+    if (tid == 0) { job.total[0] = carry; job.total[2] += cnt[0]; job.total[3] += cnt[1]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-EMIT : one CTA per chunk
+// ------------------------------------------------------------------------------------------------
+constexpr int kEmitThreads = 1024;
+constexpr int kOutWords = (kMaxChunk + 64) / 4;
+constexpr int kEmitWinBytes = 16 + kMaxChunk + 64;
+constexpr int kEmitSmem = kEmitWinBytes + kOutWords * 4 + (286 + 259 + 30) * 4;
+
+struct BitWriter {
+    unsigned* out; unsigned long long acc; int used; int word;
+    __device__ __forceinline__ void init(unsigned* o, unsigned bitOffset) { out = o; acc = 0; word = (int)(bitOffset >> 5); used = (int)(bitOffset & 31); }
+    __device__ __forceinline__ void put(unsigned bits, int n) {          // n <= 32
+        acc |= (unsigned long long)bits << used; used += n;
+        if (used >= 32) { atomicOr(&out[word], (unsigned)acc); acc >>= 32; used -= 32; ++word; }
+    }
+    __device__ __forceinline__ void flush() { if (used > 0) atomicOr(&out[word], (unsigned)acc); }
+};
+
+__device__ __forceinline__ void copy_out(uint8_t* D, const unsigned* out32, unsigned bytes)
+{
+    const uint8_t* out8 = reinterpret_cast<const uint8_t*>(out32);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(D) & 3);
+    unsigned head = mis ? 4 - mis : 0; if (head > bytes) head = bytes;
+    if ((unsigned)tid < head) D[tid] = out8[tid];
+    const unsigned nfull = (bytes - head) >> 2;
+    unsigned* Dw = reinterpret_cast<unsigned*>(D + head);
+    const int sh = (int)head * 8;
+    for (unsigned i = tid; i < nfull; i += nt) Dw[i] = __funnelshift_r(out32[i], out32[i + 1], sh);
+    const unsigned done = head + nfull * 4;
+    if ((unsigned)tid < bytes - done) D[done + tid] = out8[done + tid];
+}
+
+__global__ void __launch_bounds__(kEmitThreads, 1) k_emit(Job job)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* win = smem;
+    unsigned* out = reinterpret_cast<unsigned*>(smem + kEmitWinBytes);
+    unsigned* litc = out + kOutWords;        // bits | len << 24
+    unsigned* lenc = litc + 286;             // merged length codes (CreateMergedLengthCodes, encoder.cpp:126-133)
+    unsigned* dstc = lenc + 259;
+    __shared__ unsigned wsum[32];
+    __shared__ unsigned sTotalBits;
+
+    const unsigned slot = blockIdx.x;
+    const Geom g = chunk_geom(job, slot);
+    const ChunkState st = job.state[slot];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* chunk0 = job.src + g.off;
+    if (st.out_off + st.out_bytes > job.cap) {                        // never write past the caller's buffer
+        if (tid == 0) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 1ull);
+        return;
+    }
+    uint8_t* D = job.dst + st.out_off;
+
+    if (st.block_type == 0) {
+        // stored blocks of <= 65535 bytes (encoder.cpp:482-502), then the aligning block for non-final chunks
+        int written = 0; unsigned o = 0;
+        while (written < g.body) {
+            const int len = min(g.body - written, 0xFFFF);
+            if (tid == 0) {
+                D[o] = (uint8_t)((g.final && written + len == g.body) ? 1 : 0);
+                D[o + 1] = (uint8_t)len; D[o + 2] = (uint8_t)(len >> 8);
+                D[o + 3] = (uint8_t)~len; D[o + 4] = (uint8_t)((~len) >> 8);
+            }
+            for (int i = tid; i < len; i += kEmitThreads) D[o + 5 + i] = chunk0[written + i];
+            o += 5 + len; written += len;
+        }
+        if (!g.final && tid == 0) {
+            D[o] = 0; D[o + 1] = 1; D[o + 2] = 0; D[o + 3] = 0xFE; D[o + 4] = 0xFF; D[o + 5] = chunk0[g.n - 1];
+        }
+        return;
+    }
+
+    const int wb = (int)(reinterpret_cast<uintptr_t>(chunk0) & 15);   // phase-preserving base (0..15)
+    load_window(win, wb, chunk0, 0, g.n, g.n + 16);
+    for (int i = tid; i < kOutWords; i += kEmitThreads) out[i] = 0;
+    const ChunkCodes& cc = job.codes[slot];
+    for (int i = tid; i < 286; i += kEmitThreads) { uint32_t c = cc.lit[i]; litc[i] = (c & 0xFFFF) | ((c >> 16) << 24); }
+    for (int i = tid; i < 30; i += kEmitThreads) { uint32_t c = cc.dist[i]; dstc[i] = (c & 0xFFFF) | ((c >> 16) << 24); }
+    __syncthreads();
+    for (int i = tid; i < 259; i += kEmitThreads) {
+        unsigned v = 0;
+        if (i >= 3) {
+            int eb, ev; const int sym = len_symbol(i, eb, ev);
+            const unsigned c = litc[sym]; const unsigned cl = c >> 24;
+            v = ((c & 0xFFFFFF) | ((unsigned)ev << cl)) | ((cl + eb) << 24);
+        }
+        lenc[i] = v;
+    }
+    const uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
+    const uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
+    const int ntok = (int)st.ntok;
+    __syncthreads();
+
+    const int per = (g.body + kEmitThreads - 1) / kEmitThreads;
+    int a = tid * per, b = a + per; if (b > g.body) b = g.body; if (a > b) a = b;
+
+    // pass 1: bits produced by this thread's positions
+    unsigned mybits = 0;
+    walk_positions(tokA, ntok, a, b,
+        [&](int pos) { mybits += litc[win[wb + pos]] >> 24; },
+        [&](int k, int, int ln) {
+            int eb, ev; const int ds = dist_symbol(tokD[k], eb, ev);
+            mybits += (lenc[ln] >> 24) + (dstc[ds] >> 24) + eb;
+        });
+    unsigned inc = mybits;
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned s = wsum[lane];
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    const unsigned start = st.hdr_bits + (warp ? wsum[warp - 1] : 0) + inc - mybits;
+    if (tid == kEmitThreads - 1) sTotalBits = start + mybits;
+
+    // header bit string
+    for (unsigned i = tid; i < (st.hdr_bits + 31) / 32; i += kEmitThreads) {
+        const uint8_t* h = cc.hdr + i * 4;
+        unsigned v = h[0] | (h[1] << 8) | (h[2] << 16) | ((unsigned)h[3] << 24);
+        const unsigned rem = st.hdr_bits - i * 32;
+        if (rem < 32) v &= (1u << rem) - 1u;
+        atomicOr(&out[i], v);
+    }
+
+    // pass 2: write
+    BitWriter bw; bw.init(out, start);
+    walk_positions(tokA, ntok, a, b,
+        [&](int pos) { const unsigned c = litc[win[wb + pos]]; bw.put(c & 0xFFFFFF, (int)(c >> 24)); },
+        [&](int k, int, int ln) {
+            const unsigned lc = lenc[ln];
+            bw.put(lc & 0xFFFFFF, (int)(lc >> 24));
+            const int d = tokD[k];
+            int eb, ev; const int ds = dist_symbol(d, eb, ev);
+            const unsigned dc = dstc[ds]; const int dl = (int)(dc >> 24);
+            bw.put((dc & 0xFFFFFF) | ((unsigned)ev << dl), dl + eb);
+        });
+    bw.flush();
+    __syncthreads();
+
+    if (tid == 0) {
+        unsigned q = sTotalBits;
+        const unsigned eob = litc[256];
+        BitWriter e; e.init(out, q); e.put(eob & 0xFFFFFF, (int)(eob >> 24)); e.flush();
+        q += eob >> 24;
+        if ((unsigned long long)q != st.total_bits)                 // K-HUFF's exact size and K-EMIT must agree
+            atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 2ull);
+        unsigned bytes = (q + 7) >> 3;
+        if (!g.final) {
+            const unsigned bp = (q + 3 + 7) >> 3;                   // 3 header bits of the stored block, then pad
+            uint8_t* o8 = reinterpret_cast<uint8_t*>(out);
+            o8[bp] = 1; o8[bp + 1] = 0; o8[bp + 2] = 0xFE; o8[bp + 3] = 0xFF; o8[bp + 4] = win[wb + g.n - 1];
+            bytes = bp + 5;
+        }
+        if (bytes != st.out_bytes) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 4ull);
+    }
+    __syncthreads();
+    copy_out(D, out, st.out_bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-CKSUM : per-chunk Adler-32 (start 0) and CRC-32
+// ------------------------------------------------------------------------------------------------
+__constant__ uint32_t c_crcTable[256];
+__constant__ uint32_t c_powL[257];      // x^(8*256*q) mod P, reflected (q <= 256: a full 64 KiB chunk)
+__constant__ uint32_t c_pow1[256];      // x^(8*r) mod P, reflected
+
+__host__ __device__ inline uint32_t gf2_mulmod(uint32_t a, uint32_t b)
+{
+    uint32_t p = 0;
+    for (int i = 0; i < 32; ++i) {
+        if (a & 0x80000000u) p ^= b;
+        a <<= 1;
+        b = (b >> 1) ^ ((b & 1) ? 0xEDB88320u : 0);
+    }
+    return p;
+}
+
+constexpr int kCkThreads = 256;
+constexpr int kCkSlice = 256;
+
+__global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
+{
+    __shared__ uint32_t tab[256];
+    __shared__ unsigned long long redA[8], redB[8];
+    __shared__ uint32_t redC[8];
+    const unsigned slot = blockIdx.x;
+    const Geom g = chunk_geom(job, slot);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    tab[tid] = c_crcTable[tid];
+    __syncthreads();
+    const uint8_t* p = job.src + g.off;
+    const int lo = tid * kCkSlice;
+    int hi = lo + kCkSlice; if (hi > g.n) hi = g.n;
+    unsigned long long s1 = 0, s2 = 0; uint32_t crc = 0;
+    if (lo < hi) {
+        const int len = hi - lo;
+        for (int i = 0; i < len; ++i) {
+            const unsigned v = p[lo + i];
+            s1 += v; s2 += (unsigned long long)(len - i) * v;
+            crc = (crc >> 8) ^ tab[(crc ^ v) & 0xFF];
+        }
+        const int after = g.n - hi;
+        s2 += (unsigned long long)after * s1;                        // b = sum (n - i) * d[i]
+        crc = gf2_mulmod(gf2_mulmod(crc, c_powL[after >> 8]), c_pow1[after & 255]);
+    }
+    for (int o = 16; o; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
+    }
+    if (lane == 0) { redA[warp] = s1; redB[warp] = s2; redC[warp] = crc; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long a = 0, b = 0; uint32_t c = 0;
+        for (int w = 0; w < kCkThreads / 32; ++w) { a += redA[w]; b += redB[w]; c ^= redC[w]; }
+        uint32_t* ck = job.ck + 2 * (job.first_chunk + slot);
+        ck[0] = (uint32_t)(((b % 65521ull) << 16) | (a % 65521ull));
+        // standard CRC = raw(M) ^ (0xFFFFFFFF * x^(8n)) ^ 0xFFFFFFFF
+        const uint32_t init = gf2_mulmod(gf2_mulmod(0xFFFFFFFFu, c_powL[g.n >> 8]), c_pow1[g.n & 255]);
+        ck[1] = c ^ init ^ 0xFFFFFFFFu;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side: launch wrappers and checksum folds
+// ------------------------------------------------------------------------------------------------
+cudaError_t configure_kernels()
+{
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kParseSmem); if (e) return e;
+    e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem); if (e) return e;
+    uint32_t tab[256], powL[257], pow1[256];
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int j = 0; j < 8; ++j) c = (c >> 1) ^ ((c & 1) * 0xEDB88320u);
+        tab[i] = c;
+    }
+    const uint32_t x8 = 0x00800000u;                                  // x^8
+    uint32_t xL = 0x80000000u;                                        // x^(8*256) by repeated multiplication
+    for (int i = 0; i < 256; ++i) xL = gf2_mulmod(xL, x8);
+    pow1[0] = 0x80000000u; powL[0] = 0x80000000u;
+    for (int i = 1; i < 256; ++i) pow1[i] = gf2_mulmod(pow1[i - 1], x8);
+    for (int i = 1; i < 257; ++i) powL[i] = gf2_mulmod(powL[i - 1], xL);
+    e = cudaMemcpyToSymbol(c_crcTable, tab, sizeof tab); if (e) return e;
+    e = cudaMemcpyToSymbol(c_powL, powL, sizeof powL); if (e) return e;
+    e = cudaMemcpyToSymbol(c_pow1, pow1, sizeof pow1); if (e) return e;
+    return cudaSuccess;
+}
+
+int launch_candidates(const Job& job, cudaStream_t s)
+{
+    k_candidates<<<job.nchunks, 32, 0, s>>>(job);
+    return 1;
+}
+
+int launch_parse(const Job& job, cudaStream_t s)
+{
+    k_parse<<<job.nchunks, kParseThreads, kParseSmem, s>>>(job);
+    return 1;
+}
+
+int launch_huffman(const Job& job, cudaStream_t s)
+{
+    k_huffman<<<(job.nchunks + kHuffThreads - 1) / kHuffThreads, kHuffThreads, 0, s>>>(job);
+    return 1;
+}
+
+int launch_offsets(const Job& job, cudaStream_t s)
+{
+    k_offsets<<<1, 1024, 0, s>>>(job);
+    return 1;
+}
+
+int launch_emit(const Job& job, cudaStream_t s)
+{
+    k_emit<<<job.nchunks, kEmitThreads, kEmitSmem, s>>>(job);
+    return 1;
+}
+
+int launch_checksums(const Job& job, cudaStream_t s)
+{
+    k_checksums<<<job.nchunks, kCkThreads, 0, s>>>(job);
+    return 1;
+}
+
+int launch_fixed(const Job&, cudaStream_t) { return 0; }
+
+uint32_t adler32_combine(uint32_t first, uint32_t second, size_t lenSecond)      // adler.cpp:5-15
+{
+    const uint64_t MOD = 65521;
+    uint64_t a = (first & 0xFFFF) + (second & 0xFFFF);
+    uint64_t b = (first >> 16) + (second >> 16);
+    b += (uint64_t)(lenSecond % MOD) * (first & 0xFFFF);
+    return (uint32_t)(((b % MOD) << 16) | (a % MOD));
+}
+
+uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2)
+{
+    if (len2 == 0) return crc1;
+    uint32_t xp = 0x80000000u, sq = 0x00800000u;
+    for (uint64_t k = len2; k; k >>= 1) {
+        if (k & 1) xp = gf2_mulmod(xp, sq);
+        sq = gf2_mulmod(sq, sq);
+    }
+    return gf2_mulmod(crc1, xp) ^ crc2;
+}
+
+}  // namespace zz
