@@ -14,7 +14,7 @@ def text(n, seed):
 cases = {'text200k': text(200000, 3), 'zeros100k': bytes(100000), 'rand70k': rng.integers(0,256,70000,dtype=np.uint8).tobytes(),
          'small': b'hello hello hello hello', 'one': b'a', 'text64k': text(65536, 5), 'text64k+1': text(65537, 6)}
 for name, data in cases.items():
-    for level in (2, 0):
+    for level in (2, 1, 0):
         try:
             out, a0, crc, st = zz.deflate_raw(data, level=level)
         except Exception as e:

@@ -43,6 +43,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+SYNTH_LIB = PKG_DIR / "libzzsynth.so"
+
+
+def build_synth(force: bool = False) -> Path:
+    src = CSRC / "zz_synth.c"
+    if force or not SYNTH_LIB.exists() or src.stat().st_mtime > SYNTH_LIB.stat().st_mtime:
+        cc = shutil.which("gcc") or "cc"
+        subprocess.check_call([cc, "-O2", "-std=c11", "-fPIC", "-shared", "-o", str(SYNTH_LIB), str(src), "-lpthread"])
+    return SYNTH_LIB
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_synth(force="--force" in sys.argv))

@@ -147,7 +147,7 @@ int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int fina
             launches += launch_huffman(job, c.stream);
         }
         launches += launch_offsets(job, c.stream);
-        launches += launch_emit(job, c.stream);
+        launches += level == 1 ? launch_gather(job, c.stream) : launch_emit(job, c.stream);
         if (wantCk) launches += launch_checksums(job, c.stream);
     }
     CK(cudaGetLastError());
@@ -162,10 +162,11 @@ int foldChecksums(Ctx& c, size_t n, uint32_t chunk, int wantCk, uint32_t* adler0
     CK(cudaMemcpyAsync(c.hCk, c.ck, 2 * nchunks * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
     CK(cudaStreamSynchronize(c.stream));
     uint32_t a = 0, r = 0;
+    const uint32_t shiftFull = crc32_shift_operator(chunk);          // x^(8*chunk): same for every full chunk
     for (uint64_t k = 0; k < nchunks; ++k) {
         const size_t len = (size_t)std::min<uint64_t>(chunk, n - k * chunk);
         a = adler32_combine(a, c.hCk[2 * k], len);
-        r = crc32_combine(r, c.hCk[2 * k + 1], len);
+        r = len == chunk ? crc32_apply_shift(r, shiftFull) ^ c.hCk[2 * k + 1] : crc32_combine(r, c.hCk[2 * k + 1], len);
     }
     if (adler0) *adler0 = a;
     if (crc) *crc = r;

@@ -865,6 +865,114 @@ __global__ void __launch_bounds__(kEmitThreads, 1) k_emit(Job job)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K-FIXED (level 1) : WriteBlockFixedHuff, encoder.cpp:329-373.  The level-1 parse is sequential by
+// construction (only visited positions enter the hash table, and the hash is taken one byte ahead), so one
+// lane walks the chunk; the other lanes prime the table and verify long matches.  Bits go to the chunk's
+// scratch slot; K-OFFS + k_gather place them in the stream.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fixed_lit_code(unsigned v, int& len)     // fixedhuffmanluts.cpp:5 (RFC 1951 3.2.6)
+{
+    if (v < 144) { len = 8; return __brev(0x30u + v) >> 24; }
+    if (v < 256) { len = 9; return __brev(0x190u + (v - 144)) >> 23; }
+    if (v < 280) { len = 7; return __brev(v - 256) >> 25; }
+    len = 8; return __brev(0xC0u + (v - 280)) >> 24;
+}
+
+struct SlotWriter {
+    unsigned long long* out; unsigned long long acc; int used; unsigned words;
+    __device__ __forceinline__ void put(unsigned bits, int n) {
+        acc |= (unsigned long long)bits << used; used += n;
+        if (used >= 64) { out[words++] = acc; used -= 64; acc = used ? ((unsigned long long)bits >> (n - used)) : 0ull; }
+    }
+    __device__ __forceinline__ unsigned long long bitsWritten() const { return (unsigned long long)words * 64 + used; }
+    __device__ __forceinline__ void flush() { if (used) { out[words++] = acc; acc = 0; used = 0; } }
+};
+
+__global__ void __launch_bounds__(32) k_fixed(Job job)
+{
+    __shared__ int table[kHashSize];
+    const unsigned slot = blockIdx.x;
+    const Geom g = chunk_geom(job, slot);
+    const int lane = threadIdx.x;
+    for (int i = lane; i < kHashSize; i += 32) table[i] = kEmptySlot;
+    __syncwarp();
+    const uint8_t* base = job.src + g.off;
+    const long long limit = (long long)job.n - g.off;
+    auto byteAt = [&](int i) -> unsigned { return (i < limit) ? (unsigned)base[i] : 0u; };
+    // level-1 priming convention: table[h(i+1)] = i for every dictionary position
+    for (int i = -g.dict + lane; i < 0; i += 32) {
+        const unsigned v = byteAt(i + 1) | (byteAt(i + 2) << 8) | (byteAt(i + 3) << 16);
+        atomicMax(&table[hash3(v)], i);
+    }
+    __syncwarp();
+    ChunkState& st = job.state[slot];
+    if (lane != 0) return;
+
+    SlotWriter w; w.out = reinterpret_cast<unsigned long long*>(job.cand + (size_t)slot * job.chunk); w.acc = 0; w.used = 0; w.words = 0;
+    const int n = g.body;
+    unsigned matches = 0;
+    if (n > 0) {
+        w.put((g.final ? 1u : 0u) | (1u << 1), 3);                       // StartBlock(FixedHuffman, final)
+        for (int i = 0; i < n; ++i) {
+            const unsigned v = byteAt(i + 1) | (byteAt(i + 2) << 8) | (byteAt(i + 3) << 16);
+            const unsigned h = hash3(v);
+            const int d = i - table[h];
+            table[h] = i;
+            if ((unsigned)d <= (unsigned)kMaxDistance) {
+                int m = 0;
+                while (m < 8 && byteAt(i + m) == (unsigned)base[i - d + m]) ++m;
+                if (m == 8) {                                              // remain(a, b, 8, n - i)
+                    const int maxLen = min(n - i, kMaxMatch);
+                    while (m < maxLen && base[i + m] == base[i - d + m]) ++m;
+                    if (m > maxLen) m = maxLen;
+                } else if (m > n - i) {
+                    m = n - i;                                             // R2: clamp to the block end
+                }
+                if (m > 3) {
+                    int eb, ev, cl;
+                    const int ls = len_symbol(m, eb, ev);
+                    const unsigned lc = fixed_lit_code((unsigned)ls, cl);
+                    w.put(lc | ((unsigned)ev << cl), cl + eb);
+                    const int ds = dist_symbol(d, eb, ev);
+                    w.put((__brev((unsigned)ds) >> 27) | ((unsigned)ev << 5), 5 + eb);
+                    i += m - 1;
+                    ++matches;
+                    continue;
+                }
+            }
+            int cl; const unsigned c = fixed_lit_code(byteAt(i), cl);
+            w.put(c, cl);
+        }
+        int cl; const unsigned c = fixed_lit_code(256u, cl);
+        w.put(c, cl);
+    }
+    unsigned long long q = w.bitsWritten();
+    unsigned bytes = (unsigned)((q + 7) >> 3);
+    if (!g.final) {
+        w.put(0u, 3);                                                    // stored block header, not final
+        const int pad = (int)((8 - ((q + 3) & 7)) & 7);
+        if (pad) w.put(0u, pad);
+        w.put(1u | (0xFFFEu << 16), 32);                                 // LEN = 1, NLEN = 0xFFFE
+        w.put(byteAt(g.n - 1), 8);
+        bytes = (unsigned)(w.bitsWritten() >> 3);
+    }
+    w.flush();
+    st.ntok = matches; st.block_type = 1; st.hdr_bits = 0; st.total_bits = q; st.out_bytes = bytes;
+}
+
+__global__ void __launch_bounds__(256) k_gather(Job job)
+{
+    const unsigned slot = blockIdx.x;
+    const ChunkState st = job.state[slot];
+    if (st.out_off + st.out_bytes > job.cap) {
+        if (threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 1ull);
+        return;
+    }
+    const unsigned* src32 = reinterpret_cast<const unsigned*>(job.cand + (size_t)slot * job.chunk);
+    copy_out(job.dst + st.out_off, src32, st.out_bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K-CKSUM : per-chunk Adler-32 (start 0) and CRC-32
 // ------------------------------------------------------------------------------------------------
 __constant__ uint32_t c_crcTable[256];
@@ -991,7 +1099,17 @@ int launch_checksums(const Job& job, cudaStream_t s)
     return 1;
 }
 
-int launch_fixed(const Job&, cudaStream_t) { return 0; }
+int launch_fixed(const Job& job, cudaStream_t s)
+{
+    k_fixed<<<job.nchunks, 32, 0, s>>>(job);
+    return 1;
+}
+
+int launch_gather(const Job& job, cudaStream_t s)
+{
+    k_gather<<<job.nchunks, 256, 0, s>>>(job);
+    return 1;
+}
 
 uint32_t adler32_combine(uint32_t first, uint32_t second, size_t lenSecond)      // adler.cpp:5-15
 {
@@ -1002,15 +1120,22 @@ uint32_t adler32_combine(uint32_t first, uint32_t second, size_t lenSecond)     
     return (uint32_t)(((b % MOD) << 16) | (a % MOD));
 }
 
-uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2)
+uint32_t crc32_shift_operator(uint64_t len)                        // x^(8*len) mod P, reflected
 {
-    if (len2 == 0) return crc1;
     uint32_t xp = 0x80000000u, sq = 0x00800000u;
-    for (uint64_t k = len2; k; k >>= 1) {
+    for (uint64_t k = len; k; k >>= 1) {
         if (k & 1) xp = gf2_mulmod(xp, sq);
         sq = gf2_mulmod(sq, sq);
     }
-    return gf2_mulmod(crc1, xp) ^ crc2;
+    return xp;
+}
+
+uint32_t crc32_apply_shift(uint32_t crc, uint32_t op) { return gf2_mulmod(crc, op); }
+
+uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2)
+{
+    if (len2 == 0) return crc1;
+    return gf2_mulmod(crc1, crc32_shift_operator(len2)) ^ crc2;
 }
 
 }  // namespace zz

@@ -66,11 +66,14 @@ int launch_huffman(const Job& job, cudaStream_t s);
 int launch_offsets(const Job& job, cudaStream_t s);
 int launch_emit(const Job& job, cudaStream_t s);
 int launch_checksums(const Job& job, cudaStream_t s);
-int launch_fixed(const Job& job, cudaStream_t s);     // level 1
+int launch_fixed(const Job& job, cudaStream_t s);     // level 1: bits into the scratch slot
+int launch_gather(const Job& job, cudaStream_t s);    // level 1: scratch slot -> stream
 cudaError_t configure_kernels();
 
 // host-side checksum folds
 uint32_t adler32_combine(uint32_t first, uint32_t second, size_t lenSecond);
 uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+uint32_t crc32_shift_operator(uint64_t len);
+uint32_t crc32_apply_shift(uint32_t crc, uint32_t op);
 
 }  // namespace zz
