@@ -1,0 +1,223 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (libzzflate_b200.so), against the oracle on
+the same inputs, against the reference's golden vectors, and -- at BASELINE sizes -- through
+size-independent properties (zlib inflate round trip, checksum agreement).  Bit-exact everywhere."""
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle_lib import DEFLATE, GZIP, ZLIB, _padded
+
+pytestmark = pytest.mark.gpu
+
+S, D = 65536, 32768
+
+
+@pytest.fixture(scope="module")
+def zz():
+    import zzflate_b200
+    from zzflate_b200 import build
+    build.build()
+    assert zzflate_b200.device_count() > 0, "no CUDA device: the GPU tests must not fall back to anything"
+    return zzflate_b200
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+def test_golden_cases_identical_to_oracle_and_reference(zz, oracle, golden, level):
+    ref_level = min(level, 2)
+    for case in golden.cases:
+        data = golden.input(case)
+        out, a0, crc, st = zz.deflate_raw(data, level=level)
+        want, _ = oracle.stream_chunked(data, DEFLATE, level)
+        assert out == want, (case, level)
+        assert zlib.decompress(out, -15) == data
+        assert zz.combine(1, a0, len(data)) == zlib.adler32(data) and crc == zlib.crc32(data)
+        # directly against the reference's own per-chunk bytes, no oracle in between
+        chunks, well = golden.chunks(case, ref_level)
+        pos = 0
+        for c, ok in zip(chunks, well):
+            if ok:
+                assert out[pos: pos + len(c)] == c, (case, level)
+            pos += len(c) if ok else 0
+            if not ok:
+                break
+
+
+def test_stage_taps_match_oracle(zz, oracle, golden):
+    for case in ("alice29", "kennedy", "ptt5", "markov", "pattern", "zeros", "mixed", "adinsight", "abc"):
+        data = golden.input(case); buf = _padded(data)
+        for ci, off in enumerate(range(0, len(data), S)):
+            ln = min(S, len(data) - off)
+            tap = zz.debug_chunk(data, ci)
+            want = oracle.chunk_encode(buf, off, ln, min(D, off), 2, off + ln == len(data), want_tokens=True)
+            cand = oracle.chunk_candidates(buf, off, ln, min(D, off))
+            assert np.array_equal(tap["cand"][:ln], cand), (case, ci)
+            assert np.array_equal(tap["matches"], want["matches"]), (case, ci)
+            assert np.array_equal(tap["hist"][:286], want["lit_freq"]) and np.array_equal(tap["hist"][286:], want["dist_freq"])
+            assert np.array_equal(tap["lit_len"], want["lit_len"]) and np.array_equal(tap["dist_len"], want["dist_len"])
+            assert np.array_equal(tap["meta_len"], want["meta_len"])
+            assert tap["block_type"] == want["block_type"] and tap["total_bits"] == want["block_bits"]
+
+
+@pytest.mark.parametrize("fmt,ofmt,wbits", [("Zlib", ZLIB, 15), ("Gzip", GZIP, 31), ("Deflate", DEFLATE, -15)])
+def test_public_api_formats(zz, oracle, golden, fmt, ofmt, wbits):
+    for case in ("alice29", "kennedy", "random", "zeros", "hello", "one", "zero512", "mixed"):
+        data = golden.input(case)
+        for level in (0, 1, 2, 3):
+            for threaded in (False, True):
+                cfg = zz.Config(zz.Format[fmt], level, threaded)
+                out = zz.ZzFlateEncode(data, cfg)
+                assert out is not None
+                assert out == oracle.stream_chunked(data, ofmt, level)[0], (case, level)
+                assert zlib.decompress(out, wbits) == data
+
+
+def test_callback_api(zz, golden):
+    # Test.cpp:207-222: header, data buffers, trailer arrive in order; concatenation is the stream
+    data = golden.input("markov") * 12                      # > 1 000 000 bytes of output pieces
+    for level in (0, 2):
+        cfg = zz.Config(zz.Format.Zlib, level, False)
+        pieces = []
+        zz.ZzFlateEncodeToCallback(data, cfg, lambda b: pieces.append(b) or False)
+        assert b"".join(pieces) == zz.ZzFlateEncode(data, cfg)
+        assert pieces[0] == b"\x78\x01" and len(pieces[-1]) == 4
+        assert all(len(p) <= 1000000 for p in pieces)
+        if level == 0:
+            assert len(pieces) >= 4
+
+
+def test_error_behaviour(zz, golden):
+    data = golden.input("alice29")
+    assert zz.ZzFlateEncode(data, zz.Config(zz.Format.Zlib, 4, False)) is None            # zzflate.cpp:230
+    assert zz.ZzFlateEncode(data, zz.Config(zz.Format.Gzip, 2, False), dest_len=5) is None   # header does not fit
+    assert zz.ZzFlateEncode(data, zz.Config(zz.Format.Zlib, 2, False), dest_len=1000) is None   # explicit, not truncated
+    got = []
+    zz.ZzFlateEncodeToCallback(data, zz.Config(zz.Format.Zlib, 9, False), lambda b: got.append(b) or False)
+    assert got == []                                                                       # zzflate.cpp:201-202
+    with pytest.raises(zz.ZzGpuError):
+        zz.deflate_raw(data, level=2, chunk=1000)
+    empty = zz.ZzFlateEncode(b"", zz.Config(zz.Format.Zlib, 2, False))                     # R7 policy
+    assert zlib.decompress(empty) == b""
+
+
+def test_reference_test_sizing_conventions(zz, golden):
+    # Test.cpp:147 (1.01x), :209 (max(200,n) at level 1), :254 (n, gzip) -- on compressible input these fit
+    data = golden.input("alice29")
+    for cfg, cap in [(zz.Config(zz.Format.Zlib, 2, False), int(len(data) * 1.01)),
+                     (zz.Config(zz.Format.Zlib, 1, False), max(200, len(data))),
+                     (zz.Config(zz.Format.Gzip, 1, False), len(data))]:
+        out = zz.ZzFlateEncode(data, cfg, dest_len=cap)
+        assert out is not None and zlib.decompress(out, 47) == data
+
+
+def test_small_zero_buffers(zz):                          # Test.cpp:330-338
+    for k in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512):
+        for level in (1, 2):
+            out = zz.ZzFlateEncode(bytes(k), zz.Config(zz.Format.Zlib, level, False))
+            assert zlib.decompress(out) == bytes(k)
+
+
+def test_checksums_on_gpu(zz, oracle):
+    rng = np.random.default_rng(9)
+    for n in (0, 1, 255, 256, 257, 65535, 65536, 65537, 1000003):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert zz.adler32x(1, d) == zlib.adler32(d)
+        assert zz.crc32(d) == zlib.crc32(d)
+        assert zz.adler32x(0, d) == oracle.adler32(d, 0)
+        assert zz.crc32(d, 0x1234) == zlib.crc32(d, 0x1234)
+    kat = bytes([0, 1, 23, 30, 4, 69, 145, 32, 216])      # Test.cpp:301-313
+    assert zz.adler32x(1, kat) == zz.combine(zz.adler32x(1, kat[:5]), zz.adler32x(0, kat[5:]), 4)
+    ff = bytes([0xFF]) * (8 << 20)
+    assert zz.adler32x(1, ff) == zlib.adler32(ff)
+
+
+@pytest.mark.parametrize("chunk,dict_size", [(4096, 2048), (1024, 32768), (8192, 0), (32768, 32768), (65536, 1000)])
+def test_other_chunk_and_dictionary_sizes(zz, oracle, golden, chunk, dict_size):
+    for case in ("alice29", "pattern", "mixed"):
+        data = golden.input(case)[:90000]
+        for level in (0, 1, 2):
+            out, *_ = zz.deflate_raw(data, level=level, chunk=chunk, dict_size=dict_size)
+            assert out == oracle.stream_chunked(data, DEFLATE, level, chunk, dict_size)[0], (case, level)
+
+
+def test_shards_with_history_concatenate(zz, oracle, golden):
+    data = golden.input("markov")
+    whole, _ = oracle.stream_chunked(data, DEFLATE, 2)
+    for cut in (S, 2 * S):
+        first, a1, c1, _ = zz.deflate_raw(data[:cut], level=2, final=False)
+        second, a2, c2, _ = zz.deflate_raw(data, level=2, history=cut, final=True)
+        assert first + second == whole
+        assert zz.combine(zz.combine(1, a1, cut), a2, len(data) - cut) == zlib.adler32(data)
+        assert zz.crc32_combine(c1, c2, len(data) - cut) == zlib.crc32(data)
+
+
+def test_encoder_object(zz, golden):
+    import ctypes as C
+    from zzflate_b200 import _lib
+    lib = _lib.load()
+    lib.zz_c_encoder_new.restype = C.c_void_p; lib.zz_c_encoder_new.argtypes = [C.c_int, C.c_void_p, C.c_int64]
+    lib.zz_c_encoder_add_data.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    lib.zz_c_encoder_bytes.restype = C.c_size_t; lib.zz_c_encoder_bytes.argtypes = [C.c_void_p]
+    lib.zz_c_encoder_data.restype = C.c_void_p; lib.zz_c_encoder_data.argtypes = [C.c_void_p]
+    lib.zz_c_encoder_free.argtypes = [C.c_void_p]; lib.zz_c_encoder_set_level.argtypes = [C.c_void_p, C.c_int]
+    data = np.frombuffer(golden.input("alice29"), dtype=np.uint8)
+    e = lib.zz_c_encoder_new(2, None, 0)
+    cut = 70001
+    assert lib.zz_c_encoder_add_data(e, data.ctypes.data, cut, 0) == 1
+    lib.zz_c_encoder_set_level(e, 1)
+    assert lib.zz_c_encoder_add_data(e, data.ctypes.data + cut, data.size - cut, 1) == 1
+    n = lib.zz_c_encoder_bytes(e)
+    out = C.string_at(lib.zz_c_encoder_data(e), n)
+    lib.zz_c_encoder_free(e)
+    assert zlib.decompress(out, -15) == data.tobytes()
+
+
+def test_device_resident_buffers(zz, oracle):
+    import torch
+    from zzflate_b200 import synth
+    data = synth.markov_text(3 * S + 777, seg0=1)
+    src = torch.from_numpy(data.copy()).cuda()
+    dst = torch.empty(zz.bound(data.size), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    n, a0, crc, st = zz.deflate_device(src.data_ptr(), data.size, dst.data_ptr(), dst.numel(), level=2, checksums=3)
+    out = dst[:n].cpu().numpy().tobytes()
+    assert out == oracle.stream_chunked(data, DEFLATE, 2)[0]
+    assert st.kernel_launches >= 5 and st.device_ms > 0
+    # unaligned device pointers take the byte-wise window path
+    src2 = torch.empty(data.size + 64, dtype=torch.uint8, device="cuda")
+    for shift in (1, 7, 13):
+        src2[shift: shift + data.size] = src
+        torch.cuda.synchronize()
+        n2, *_ = zz.deflate_device(src2.data_ptr() + shift, data.size, dst.data_ptr() + 3, dst.numel() - 3, level=2)
+        assert dst[3: 3 + n2].cpu().numpy().tobytes() == out
+
+
+@pytest.mark.parametrize("workload,size_mib", [("text", 1024), ("random", 256), ("zeros", 256), ("pattern", 256)])
+def test_baseline_sizes_round_trip(zz, workload, size_mib):
+    """BASELINE.json configs 2-4 at full size: every output inflates through zlib to the input and the
+    checksums agree with zlib's (size-independent properties; the oracle covers a 32 MiB prefix bit-exactly)."""
+    import torch
+    from oracle_lib import oracle as get_oracle
+    from zzflate_b200 import synth
+    n = size_mib << 20
+    data = synth.workload(workload, n)
+    src = torch.from_numpy(data).cuda()
+    dst = torch.empty(zz.bound(n), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    out_len, a0, crc, st = zz.deflate_device(src.data_ptr(), n, dst.data_ptr(), dst.numel(), level=2, checksums=3)
+    out = dst[:out_len].cpu().numpy()
+    assert zz.combine(1, a0, n) == zlib.adler32(data)
+    assert crc == zlib.crc32(data)
+    d = zlib.decompressobj(-15)
+    pos = 0
+    step = 64 << 20
+    for lo in range(0, out_len, step):
+        piece = d.decompress(out[lo: lo + step].tobytes())
+        assert piece == data[pos: pos + len(piece)].tobytes()
+        pos += len(piece)
+    assert pos == n and d.eof
+    prefix = 32 << 20
+    want, _ = get_oracle().stream_chunked(data[:prefix], DEFLATE, 2, threads=8)
+    # all but the last chunk of the prefix are non-final in both streams
+    keep = len(want) - 70000
+    assert out[:keep].tobytes() == want[:keep]

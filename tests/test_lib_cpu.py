@@ -1,0 +1,84 @@
+"""What can be checked of the product library without a GPU: it builds, loads, exports every symbol
+include/zzgpu.h declares, fails loudly without a device, and its host-only helpers agree with the oracle."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from zzflate_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    from zzflate_b200 import _lib
+    header = (ROOT / "include" / "zzgpu.h").read_text()
+    declared = sorted(set(re.findall(r"ZZGPU_API\s+[\w\s\*]+?\b(zzgpu_\w+)\s*\(", header)))
+    assert declared == sorted(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_cpp_api_symbols_present():
+    import subprocess
+    from zzflate_b200 import _lib
+    out = subprocess.check_output(["nm", "-D", "--defined-only", "-C", str(_lib.LIB_PATH)], text=True)
+    for sym in ("ZzFlateEncode(", "ZzFlateEncodeToCallback(", "adler32x(", "combine(", "crc32(", "Encoder::AddData(",
+                "Encoder::FindDistance(", "Encoder::CreateMergedLengthCodes("):
+        assert sym in out, sym
+
+
+def test_kernels_are_sm100a(lib):
+    import shutil, subprocess
+    from zzflate_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(cuobjdump).exists():
+        pytest.skip("cuobjdump not available")
+    out = subprocess.check_output([cuobjdump, "-lelf", str(_lib.LIB_PATH)], text=True)
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_device(lib):
+    from conftest import has_cuda
+    if has_cuda():
+        pytest.skip("a GPU is present")
+    from zzflate_b200 import Config, Format, ZzFlateEncode, ZzGpuError, deflate_raw, _lib
+    assert lib.zzgpu_init(0) == _lib.E_NO_DEVICE
+    with pytest.raises(ZzGpuError) as e:
+        deflate_raw(b"hello hello hello", level=2)
+    assert e.value.status == _lib.E_NO_DEVICE
+    assert ZzFlateEncode(b"hello", Config(Format.Zlib, 2, False)) is None       # *destLen = ~0
+
+
+def test_bound_matches_oracle(lib, oracle):
+    for n in (0, 1, 65535, 65536, 65537, 10_000_000):
+        for level in (0, 1, 2):
+            assert lib.zzgpu_bound(n, level, 65536) + 18 == oracle.bound(n, level)
+
+
+def test_host_checksum_folds(lib, oracle):
+    import zlib
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, 100001, dtype=np.uint8).tobytes(); b = rng.integers(0, 256, 65536, dtype=np.uint8).tobytes()
+    assert lib.zzgpu_crc32_combine(zlib.crc32(a), zlib.crc32(b), len(b)) == zlib.crc32(a + b)
+    assert lib.zzgpu_adler32_combine(zlib.adler32(a), oracle.adler32(b, 0), len(b)) == zlib.adler32(a + b)
+    kat = bytes([0, 1, 23, 30, 4, 69, 145, 32, 216])                            # Test.cpp:301-313
+    assert lib.zzgpu_adler32_combine(zlib.adler32(kat[:5]), oracle.adler32(kat[5:], 0), 4) == zlib.adler32(kat)
+
+
+def test_static_helpers_match_oracle(lib, oracle):
+    lib.zz_c_find_distance.restype = C.c_int; lib.zz_c_read_lut.restype = C.c_int
+    for d in range(1, 32769):                                                   # TestHuffman.cpp:9-31
+        assert lib.zz_c_find_distance(d) == lib.zz_c_read_lut(d) == oracle.lib.zzo_read_lut(d)
+    assert lib.zz_c_read_lut(0) == 255 and lib.zz_c_find_distance(32769) == -1
+    t = oracle.tables()
+    sym = (C.c_int32 * 572)(*t["codes_f"]); out = (C.c_int32 * 518)()
+    lib.zz_c_merged_length_codes(sym, out)
+    assert list(out) == t["lcodes_f"]                                           # fixedhuffmanluts.cpp:8-46

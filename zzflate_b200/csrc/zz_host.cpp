@@ -86,7 +86,7 @@ int deflateStream(uint8_t* dest, size_t cap, const uint8_t* source, size_t n, in
     for (int g = 0; g < ndev; ++g) {
         Shard& s = shards[(size_t)g];
         const size_t c0 = std::min(nchunks, per * g), c1 = std::min(nchunks, per * (g + 1));
-        s.off = c0 * chunk; s.len = std::min(n, c1 * chunk) - s.off;
+        s.off = std::min(n, c0 * chunk); s.len = std::min(n, c1 * chunk) - s.off;
         s.device = g; s.final = (c1 == nchunks);
     }
     std::vector<std::thread> threads;
