@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- deflate compress throughput (GB/s of input) of the B200 path, BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload text|random|zeros|pattern]
+
+N=1 workload: BASELINE.json configs[1] -- 1 GiB order-2 Markov text, 64 KiB chunks + 32 KiB dictionary,
+level 2 (dynamic Huffman).  For N>1 (torchrun, one rank per GPU) every rank holds its own 1 GiB shard of the
+same stream (weak scaling; shards are independent given the 32 KiB before them, so there is no data-path
+collective -- only the barrier and the max-over-ranks reduction of the timing).
+
+One step = one pass of the whole pipeline over the rank's shard.  `value` is device-timed with CUDA events on
+the library's launching stream, inputs and outputs resident in HBM; `e2e` is the same metric through the public
+ZzFlateEncode call on pinned HOST buffers (H2D and D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+GIB = 1 << 30
+CHUNK, DICT = 65536, 32768
+METRIC = "deflate_compress_input_throughput"
+UNIT = "GB/s"
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_shard(workload: str, rank: int, nbytes: int):
+    """Rank's shard of the stream plus the history (dictionary + backward-extension slack) before it."""
+    import numpy as np
+    from zzflate_b200 import synth
+    hist = 0 if rank == 0 else DICT + 288
+    buf = np.empty(hist + nbytes, dtype=np.uint8)
+    if workload == "text":
+        segs = nbytes >> 20
+        if hist:
+            buf[:hist] = synth.markov_text(1 << 20, seg0=rank * segs - 1)[-hist:]
+        synth.markov_text(nbytes, seg0=rank * segs, out=buf[hist:])
+    else:
+        full = synth.workload(workload, hist + nbytes)        # random/zeros/pattern: each rank an independent stream
+        buf[:] = full
+    return buf, hist
+
+
+def cpu_reference_run(data, steps: int, warmup: int):
+    """The reference's own CPU encoder (oracle/_ref, else the oracle port) on the host cores."""
+    import oracle_lib
+    cores = os.cpu_count() or 1
+    n = data.size
+    if oracle_lib.REF_SO.exists():
+        ref = oracle_lib.reference(); kind = "reference"
+        run = lambda: ref.encode(data, oracle_lib.DEFLATE, 2, threaded=True)       # hardware_concurrency() tasks
+    else:
+        o = oracle_lib.oracle(); kind = "port"
+        run = lambda: o.stream_chunked(data, oracle_lib.DEFLATE, 2, threads=cores)[0]
+    out_len = 0
+    for _ in range(warmup):
+        out_len = len(run())
+    times = []
+    for _ in range(steps):
+        t = time.perf_counter(); out_len = len(run()); times.append(time.perf_counter() - t)
+    return kind, cores, times, out_len
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="text", choices=["text", "random", "zeros", "pattern"])
+    ap.add_argument("--level", type=int, default=2)
+    ap.add_argument("--shard-mib", type=int, default=1024, help="input bytes per GPU per step (MiB)")
+    ap.add_argument("--cpu-sample-mib", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload_name = {"text": "1 GiB order-2 Markov text per GPU (SURVEY 8d.2), 64 KiB chunks + 32 KiB dictionary, level 2 dynamic Huffman",
+                     "random": "splitmix64 random bytes, level 2 (stored fallback)", "zeros": "all-zero input, level 2",
+                     "pattern": "1000-byte pattern repeated, level 2"}[args.workload]
+    config = {"workload": workload_name if args.shard_mib == 1024 else workload_name.replace("1 GiB", f"{args.shard_mib} MiB"),
+              "bytes_per_gpu": args.shard_mib << 20, "chunk": CHUNK, "dict": DICT, "level": args.level,
+              "sharding": f"{world} contiguous shards, no collective" if world > 1 else "single GPU",
+              "l2": "inputs (>= 256 MiB per step) exceed the 126 MB L2; no explicit flush"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from zzflate_b200 import synth
+        n = min(args.cpu_sample_mib, args.shard_mib) << 20
+        data = synth.workload(args.workload, n)
+        kind, cores, times, out_len = cpu_reference_run(data, args.steps, args.warmup)
+        t = sum(times) / len(times)
+        val = n / t / 1e9
+        sample = f"first {n >> 20} MiB of the workload per step, Format=Deflate level 2, threaded=true"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                          "ratio": round(out_len / n, 5),
+                          "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                          "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------------------------------------------------------- B200 arm
+    import numpy as np
+    import torch
+    import zzflate_b200 as zz
+    from zzflate_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _lib.check(_lib.load().zzgpu_init(local_rank))
+
+    nbytes = args.shard_mib << 20
+    host, hist = make_shard(args.workload, rank, nbytes)
+    final = rank == world - 1
+    pinned_src = torch.from_numpy(host).pin_memory()
+    d_src = pinned_src.cuda(non_blocking=False)
+    cap = zz.bound(nbytes, args.level)
+    d_dst = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    pinned_dst = torch.empty(cap + 64, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        return zz.deflate_device(d_src.data_ptr() + hist, nbytes, d_dst.data_ptr(), cap, level=args.level,
+                                 history=hist, final=final, checksums=1)
+
+    for _ in range(args.warmup):
+        out_len, _, _, st = device_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, stage_ms, launches = 0.0, [0.0] * 8, 0
+    stage_n = [0] * 8
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_len, _, _, st = device_step()
+        dev_ms += st.device_ms
+        launches += st.kernel_launches
+        for i in range(8):
+            stage_ms[i] += st.stage_ms[i]; stage_n[i] += st.stage_launches[i]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+
+    # ---- end to end through the public API on pinned host buffers
+    e2e_ms, e2e_out = None, 0
+    if not args.no_e2e:
+        cfg = zz.Config(zz.Format.Deflate, args.level, False)
+        src_ptr = pinned_src.data_ptr() + hist
+        if hist:          # the public single-call API has no history argument: rank>0 encodes its shard as its own stream
+            pass
+        for _ in range(min(args.warmup, 2)):
+            e2e_out = zz.encode_ptr(pinned_dst.data_ptr(), cap, src_ptr, nbytes, cfg)
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_out = zz.encode_ptr(pinned_dst.data_ptr(), cap, src_ptr, nbytes, cfg)
+            assert e2e_out is not None
+        barrier()
+        e2e_ms = (time.perf_counter() - t1) * 1e3
+
+    vals = torch.tensor([dev_ms, wall_ms, e2e_ms or 0.0, float(launches), float(out_len)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, wall_ms, e2e_ms_r = mx[0].item(), mx[1].item(), mx[2].item()
+        launches = int(sm[3].item()); total_out = sm[4].item()
+    else:
+        e2e_ms_r = e2e_ms or 0.0; total_out = float(out_len)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total_in = float(nbytes) * world
+    ms_per_step = dev_ms / args.steps
+    value = total_in / (ms_per_step * 1e-3) / 1e9
+    ratio = total_out / total_in
+    peak, peak_src = measured_peaks()
+    # dominant kernel (rank 0's stage times)
+    names = _lib.STAGES
+    dom = max(range(8), key=lambda i: stage_ms[i])
+    dom_avg_ms = stage_ms[dom] / max(stage_n[dom], 1)
+    chunks_per_launch = min(4096, (nbytes + CHUNK - 1) // CHUNK)
+    alg_bytes = chunks_per_launch * CHUNK * (1.0 + ratio)            # 1 read + r written per input byte
+    achieved = alg_bytes / (dom_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(names[dom])
+        except Exception:
+            traffic = None
+    line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": config, "ratio": round(ratio, 5),
+            "wall_ms_per_step": round(wall_ms / args.steps, 3),
+            "stage_ms_per_step": {names[i]: round(stage_ms[i] / args.steps, 3) for i in range(8) if stage_n[i]},
+            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(dom_avg_ms, 4),
+                         "whole_path_frac": round(value * (1.0 + ratio) / peak, 5)},
+            "gpu_launches": launches, "clocks": clocks}
+    if e2e_ms is not None:
+        e2e_val = total_in / (e2e_ms_r / args.steps * 1e-3) / 1e9
+        line["e2e"] = {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(e2e_out or 0),
+                       "ms_per_step": round(e2e_ms_r / args.steps, 3), "api": "ZzFlateEncode(Format=Deflate, level, threaded=false) on pinned host buffers"}
+    if not args.no_cpu_baseline:
+        n_s = min(args.cpu_sample_mib << 20, nbytes)
+        kind, cores, times, cpu_out = cpu_reference_run(host[hist: hist + n_s], 3, 1)
+        best = min(times)
+        line["cpu_baseline"] = {"value": round(n_s / best / 1e9, 4), "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"first {n_s >> 20} MiB of rank 0's shard, ZzFlateEncode Format=Deflate level 2 threaded=true, best of 3",
+                                "ratio": round(cpu_out / n_s, 5)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,7 +63,13 @@ typedef struct zzgpu_stats {
     float device_ms;          /* CUDA-event time of the device pipeline (kernels only) */
     float total_ms;           /* CUDA-event time including H2D / D2H copies when buffers are on the host */
     uint64_t h2d_bytes, d2h_bytes;
+    /* CUDA-event time per pipeline stage, summed over the call's batches (ZZGPU_STAGE_*) */
+    float stage_ms[8];
+    uint32_t stage_launches[8];
 } zzgpu_stats;
+
+enum { ZZGPU_STAGE_CAND = 0, ZZGPU_STAGE_PARSE = 1, ZZGPU_STAGE_HUFF = 2, ZZGPU_STAGE_OFFS = 3, ZZGPU_STAGE_EMIT = 4,
+       ZZGPU_STAGE_CKSUM = 5, ZZGPU_STAGE_FIXED = 6, ZZGPU_STAGE_GATHER = 7 };
 
 /* Select the device used by the calling thread's subsequent calls (default: current CUDA device).
  * Creates the per-device context (stream, scratch) lazily.  Returns ZZGPU_E_NO_DEVICE without a GPU. */

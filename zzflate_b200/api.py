@@ -153,3 +153,13 @@ def debug_chunk(source, chunk_index: int, level: int = 2, chunk: int = DEFAULT_C
 
 def device_count() -> int:
     return _lib.load().zzgpu_device_count()
+
+
+def encode_ptr(dest_ptr: int, cap: int, src_ptr: int, n: int, config: Config) -> Optional[int]:
+    """ZzFlateEncode on caller-owned HOST buffers given as raw addresses (e.g. pinned torch tensors).
+    Returns bytes written or None on error (*destLen = ~0)."""
+    lib = _lib.load()
+    lib.zz_c_encode.restype = C.c_size_t
+    lib.zz_c_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
+    w = lib.zz_c_encode(dest_ptr, cap, src_ptr, n, int(config.format), int(config.level), int(config.threaded))
+    return None if w == _ERR else w

@@ -37,6 +37,9 @@ struct Ctx {
     uint32_t* hCk = nullptr; size_t hCkCap = 0;
     uint8_t* dIn = nullptr; size_t dInCap = 0;
     uint8_t* dOut = nullptr; size_t dOutCap = 0;
+    std::vector<cudaEvent_t> stageEv;       // pool of events bracketing each stage launch
+    std::vector<int> stageOf;               // stage id of the interval that ENDS at event i (-1: start marker)
+    size_t stageUsed = 0;
 };
 
 Ctx g_ctx[kMaxDevices];
@@ -120,6 +123,29 @@ bool validParams(int level, uint32_t chunk, uint32_t dict)
            dict <= ZZGPU_MAX_DICT;
 }
 
+int markStage(Ctx& c, int stage)
+{
+    if (c.stageUsed == c.stageEv.size()) {
+        cudaEvent_t e; CK(cudaEventCreate(&e));
+        c.stageEv.push_back(e); c.stageOf.push_back(-1);
+    }
+    c.stageOf[c.stageUsed] = stage;
+    CK(cudaEventRecord(c.stageEv[c.stageUsed], c.stream));
+    c.stageUsed++;
+    return ZZGPU_OK;
+}
+
+void collectStages(Ctx& c, zzgpu_stats* stats)
+{
+    if (!stats) return;
+    for (size_t i = 1; i < c.stageUsed; ++i) {
+        const int st = c.stageOf[i];
+        if (st < 0) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c.stageEv[i - 1], c.stageEv[i]) == cudaSuccess) { stats->stage_ms[st] += ms; stats->stage_launches[st]++; }
+    }
+}
+
 // Runs the device pipeline over all chunks of the call.  d_src points at stream position 0 of the call in
 // device memory (history bytes before it), d_dst receives the stream.
 int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap,
@@ -130,6 +156,7 @@ int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int fina
     int rc = ensureScratch(c, slots, chunk); if (rc) return rc;
     if (wantCk) { rc = ensureBuf(c.ck, c.ckCap, 2 * nchunks); if (rc) return rc; }
     CK(cudaMemsetAsync(c.total, 0, 4 * sizeof(uint64_t), c.stream));
+    c.stageUsed = 0;
     for (uint64_t first = 0; first < nchunks; first += slots) {
         Job job{};
         job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
@@ -137,18 +164,20 @@ int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int fina
         job.final_stream = final; job.level = level; job.want_checksums = wantCk;
         job.cand = c.cand; job.tokA = c.tokA; job.tokD = c.tokD; job.hist = c.hist; job.codes = c.codes; job.state = c.state;
         job.dst = d_dst; job.cap = cap; job.total = c.total; job.ck = c.ck;
+        rc = markStage(c, -1); if (rc) return rc;
         if (level >= 2) {
-            launches += launch_candidates(job, c.stream);
-            launches += launch_parse(job, c.stream);
+            launches += launch_candidates(job, c.stream); rc = markStage(c, ZZGPU_STAGE_CAND); if (rc) return rc;
+            launches += launch_parse(job, c.stream); rc = markStage(c, ZZGPU_STAGE_PARSE); if (rc) return rc;
         }
         if (level == 1) {
-            launches += launch_fixed(job, c.stream);
+            launches += launch_fixed(job, c.stream); rc = markStage(c, ZZGPU_STAGE_FIXED); if (rc) return rc;
         } else {
-            launches += launch_huffman(job, c.stream);
+            launches += launch_huffman(job, c.stream); rc = markStage(c, ZZGPU_STAGE_HUFF); if (rc) return rc;
         }
-        launches += launch_offsets(job, c.stream);
-        launches += level == 1 ? launch_gather(job, c.stream) : launch_emit(job, c.stream);
-        if (wantCk) launches += launch_checksums(job, c.stream);
+        launches += launch_offsets(job, c.stream); rc = markStage(c, ZZGPU_STAGE_OFFS); if (rc) return rc;
+        if (level == 1) { launches += launch_gather(job, c.stream); rc = markStage(c, ZZGPU_STAGE_GATHER); if (rc) return rc; }
+        else { launches += launch_emit(job, c.stream); rc = markStage(c, ZZGPU_STAGE_EMIT); if (rc) return rc; }
+        if (wantCk) { launches += launch_checksums(job, c.stream); rc = markStage(c, ZZGPU_STAGE_CKSUM); if (rc) return rc; }
     }
     CK(cudaGetLastError());
     return ZZGPU_OK;
@@ -306,6 +335,7 @@ int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int final, in
         stats->kernel_launches = launches;
         cudaEventElapsedTime(&stats->device_ms, c.ev[1], c.ev[2]);
         cudaEventElapsedTime(&stats->total_ms, c.ev[0], c.ev[3]);
+        collectStages(c, stats);
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
     }
     return ZZGPU_OK;
