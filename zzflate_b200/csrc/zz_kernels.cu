@@ -171,22 +171,29 @@ __device__ __forceinline__ unsigned long long ld8(const uint8_t* win, int o)
     return ((unsigned long long)hi << 32) | lo;
 }
 
-// Parse-independent part of the acceptance rule: need = 4 - min(fwd,4); a position is usable
-// when the candidate supplies `need` bytes backwards.  Returns need (0..4) or 7 when unusable.
-__device__ __forceinline__ int position_info(const uint8_t* win, int wb, int j, int d, int pre)
-{
-    if (d == 0) return 7;
-    const int p = j - d;
-    unsigned x = ld4(win, wb + j) ^ ld4(win, wb + p);
-    int fwd4 = x ? ((__ffs(x) - 1) >> 3) : 4;
-    if (fwd4 == 4) return 0;
-    const int need = 4 - fwd4;
-    unsigned y = ld4(win, wb + j - 4) ^ ld4(win, wb + p - 4);
-    int back4 = y ? (__clz(y) >> 3) : 4;
-    int room = p + pre;                                  // bytes of real history before the candidate (R4 clamp)
-    if (back4 > room) back4 = room;
-    return back4 >= need ? need : 7;
-}
+// ------------------------------------------------------------------------------------------------
+// K-MATCH : one CTA per chunk.
+//
+// The reference's greedy parse (FirstPass, encoder.cpp:375-440) is a sequential walk, but it factors into
+// parse-independent pieces:
+//   * info[j]   = (forward match length, backward match length) of position j against its hash candidate,
+//                 both capped at 32 -- computed for every position in parallel;
+//   * a *state* is b = end of the last emitted match.  From state b the walk probes b+1, b+2, ... and takes the
+//                 first j that is usable (fwd+back >= 4) with j-b >= 4-min(fwd,4).  The next state is
+//                 F(b) = j + fwd (the backward extension only moves the match start) -- again computable for
+//                 every b in parallel;
+//   * the parse is the orbit of F from the batch start.  Orbits are followed tile by tile (32 states): E1[b] is
+//                 the first iterate of F that leaves b's tile (3 rounds of pointer jumping with warp shuffles),
+//                 so one lane hops over 2048 tiles instead of ~10^4 matches; tiles then expand their part of
+//                 the orbit into tokens in parallel.
+// Matches of 32 bytes or more are resolved exactly (up to 258) only where the orbit actually meets them.
+// ------------------------------------------------------------------------------------------------
+constexpr int kParseThreads = 1024;
+constexpr int kBatchCap = kBatch + 128;            // entries of the per-batch arrays (tile-aligned base + slack)
+constexpr int kTilesCap = kBatchCap / 32;
+constexpr int kCapLen = 32;                        // cap of the parallel forward/backward compares
+constexpr unsigned kNone16 = 0xFFFFu;
+constexpr int kParseSmem = kWinBytes + 3 * kBatchCap * 2 /*info,F,E1*/ + (kTilesCap + 4) * (4 + 2 + 2 + 4 + 4);
 
 struct ParseShared {
     int pos;            // start of the next FirstPass batch
@@ -198,6 +205,8 @@ struct ParseShared {
     int patchD[4];
     int fixS;           // excluded position whose successor still has to be found, or -1
     int fixJ;
+    int npre;           // 1 if the batch's first probe (j == backRefEnd) produced a token
+    int total;          // tokens of the batch produced by the tiles
 };
 
 // candidate of j with the never-inserted batch starts removed from the hash chain
@@ -217,11 +226,91 @@ __device__ int effective_cand(const uint16_t* cand, const ParseShared* ps, int j
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K-MATCH : one CTA per chunk
-// ------------------------------------------------------------------------------------------------
-constexpr int kParseThreads = 1024;
-constexpr int kParseSmem = kWinBytes + kMaxChunk /*info*/ + (kMaxChunk / 32) * 4 /*okbits*/;
+__device__ __forceinline__ int patched_cand(const uint16_t* cand, const ParseShared* ps, int j)
+{
+    int d = cand[j];
+    for (int k = 0; k < ps->npatch; ++k) if (ps->patchJ[k] == j) d = ps->patchD[k];
+    return d;
+}
+
+__device__ __forceinline__ int fwd_cap(const uint8_t* win, int oj, int op)
+{
+#pragma unroll
+    for (int k = 0; k < kCapLen / 8; ++k) {
+        const unsigned long long x = ld8(win, oj + 8 * k) ^ ld8(win, op + 8 * k);
+        if (x) return 8 * k + ((__ffsll((long long)x) - 1) >> 3);
+    }
+    return kCapLen;
+}
+
+__device__ __forceinline__ int back_cap(const uint8_t* win, int oj, int op)
+{
+#pragma unroll
+    for (int k = 0; k < kCapLen / 8; ++k) {
+        const unsigned long long x = ld8(win, oj - 8 - 8 * k) ^ ld8(win, op - 8 - 8 * k);
+        if (x) return 8 * k + (__clzll((long long)x) >> 3);
+    }
+    return kCapLen;
+}
+
+// exact forward match length (<= 258), all 32 lanes cooperate (remain(), encoder.cpp:81-90)
+__device__ __forceinline__ int coop_fwd(const uint8_t* win, int oj, int op, int lane)
+{
+    const unsigned long long xa = ld8(win, oj + lane * 8) ^ ld8(win, op + lane * 8);
+    const unsigned mm = __ballot_sync(0xffffffffu, xa != 0);
+    if (mm) {
+        const int src = __ffs(mm) - 1;
+        const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src);
+        return src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
+    }
+    int fwd = 256;
+    if (win[oj + 256] == win[op + 256]) { fwd = 257; if (win[oj + 257] == win[op + 257]) fwd = 258; }
+    return fwd;
+}
+
+// exact backward match length (<= 258), all 32 lanes cooperate (countMatchBackward, encoder.cpp:92-102)
+__device__ __forceinline__ int coop_back(const uint8_t* win, int oj, int op, int lane)
+{
+    const unsigned long long xb = ld8(win, oj - 8 - lane * 8) ^ ld8(win, op - 8 - lane * 8);
+    const unsigned mm = __ballot_sync(0xffffffffu, xb != 0);
+    if (mm) {
+        const int src = __ffs(mm) - 1;
+        const unsigned long long xs = __shfl_sync(0xffffffffu, xb, src);
+        return src * 8 + (__clzll((long long)xs) >> 3);
+    }
+    int lb = 256;
+    if (win[oj - 257] == win[op - 257]) { lb = 257; if (win[oj - 258] == win[op - 258]) lb = 258; }
+    return lb;
+}
+
+// single-thread exact backward length, capped at `limit` (rare path of the token expansion)
+__device__ int slow_back(const uint8_t* win, int oj, int op, int limit)
+{
+    int lb = 0;
+    while (lb < limit && win[oj - 1 - lb] == win[op - 1 - lb]) ++lb;
+    return lb;
+}
+
+// First position the walk would take from state b (b = end of the previous match), or -1.
+// info == 0 marks an unusable position; the low byte of info is min(fwd, 32).
+__device__ __forceinline__ int probe_next(const uint16_t* info, const unsigned* okbits, const uint16_t* nzw,
+                                          int ntiles, int base, int b)
+{
+    const int r = b - base;
+#pragma unroll
+    for (int k = 1; k <= 3; ++k) {
+        const unsigned inf = info[r + k];
+        if (inf != 0 && 4 - (int)(inf & 0xFF) <= k) return b + k;
+    }
+    const int x = r + 4;
+    const int w = x >> 5;
+    if (w >= ntiles) return -1;
+    const unsigned bits = okbits[w] & (~0u << (x & 31));
+    if (bits) return base + w * 32 + __ffs(bits) - 1;
+    const unsigned w2 = nzw[w + 1];
+    if (w2 == kNone16) return -1;
+    return base + (int)w2 * 32 + __ffs(okbits[w2]) - 1;
+}
 
 // Walks positions [a,b) of a chunk against its sorted match list; calls lit(pos) for every literal and
 // match(k, start, len) for every match that starts inside [a,b).
@@ -250,9 +339,16 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* win = smem;
-    uint8_t* info = smem + kWinBytes;
-    unsigned* okbits = reinterpret_cast<unsigned*>(smem + kWinBytes + kMaxChunk);
+    uint16_t* info = reinterpret_cast<uint16_t*>(smem + kWinBytes);
+    uint16_t* F = info + kBatchCap;
+    uint16_t* E1 = F + kBatchCap;
+    unsigned* okbits = reinterpret_cast<unsigned*>(E1 + kBatchCap);
+    unsigned* lazyTok = okbits + (kTilesCap + 4);
+    unsigned* tcnt = lazyTok + (kTilesCap + 4);
+    uint16_t* nzw = reinterpret_cast<uint16_t*>(tcnt + (kTilesCap + 4));
+    uint16_t* entry = nzw + (kTilesCap + 4);
     __shared__ ParseShared ps;
+    __shared__ unsigned wsum[32];
 
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
@@ -264,23 +360,11 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
     uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
 
     load_window(win, wb, chunk0, -g.pre, g.n, g.n + 48);
-    if (tid == 0) { ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npatch = 0; ps.fixS = -1; ps.fixJ = -1; }
+    if (tid == 0) { ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npatch = 0; ps.fixS = -1; ps.fixJ = 0x7fffffff; }
     __syncthreads();
 
-    // ---- phase A: per-position usability (parse independent) ----
     const int t0 = g.t0;
-    const int nsteps = (t0 + 31) >> 5;
-    for (int s = warp; s < nsteps; s += nwarps) {
-        const int j = s * 32 + lane;
-        int inf = 7;
-        if (j >= 1 && j < t0) inf = position_info(win, wb, j, cand[j], g.pre);
-        info[j] = (uint8_t)inf;
-        const unsigned m = __ballot_sync(0xffffffffu, inf != 7);
-        if (lane == 0) okbits[s] = m;
-    }
-    __syncthreads();
-
-    // ---- phase B: greedy acceptance, batch by batch (WriteBlock2Pass loop, encoder.cpp:225-234) ----
+    // ---- batches of the reference's WriteBlock2Pass loop (encoder.cpp:225-234) ----
     for (;;) {
         const int pos = ps.pos;
         if (pos >= t0) break;
@@ -291,106 +375,121 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             int hiJ = fixS + kMaxDistance; if (hiJ > t0) hiJ = t0;
             for (int j = fixS + 1 + tid; j < hiJ; j += kParseThreads)
                 if ((int)cand[j] == j - fixS) atomicMin(&ps.fixJ, j);
+            __syncthreads();
+            if (tid == 0) {
+                const int fj = ps.fixJ;
+                if (fj < 0x7fffffff) { const int k = ps.npatch++; ps.patchJ[k] = fj; ps.patchD[k] = effective_cand(cand, &ps, fj); }
+            }
+            __syncthreads();
+        }
+        int E = pos + kBatch; if (E > t0) E = t0;
+        const int B0 = pos + 1;                          // FirstPass: backRefEnd = j = startPos + 1
+        const int base = B0 & ~31;
+        const int ntiles = (E - base + 31) >> 5;
+
+        // ---- P1: per-position match info (parse independent) ----
+        for (int idx = tid; idx < ntiles * 32 + 64; idx += kParseThreads) {
+            const int j = base + idx;
+            unsigned inf = 0;
+            if (j >= B0 && j < E) {
+                const int d = patched_cand(cand, &ps, j);
+                if (d) {
+                    const int p = j - d;
+                    const int fwd = fwd_cap(win, wb + j, wb + p);
+                    int back = back_cap(win, wb + j, wb + p);
+                    const int room = p + g.pre;          // bytes of real history before the candidate (R4 clamp)
+                    if (back > room) back = room;
+                    if (fwd + back >= 4) inf = (unsigned)fwd | ((unsigned)back << 8);
+                }
+            }
+            info[idx] = (uint16_t)inf;
+            const unsigned m = __ballot_sync(0xffffffffu, inf != 0);
+            if (lane == 0 && (idx >> 5) < kTilesCap + 4) okbits[idx >> 5] = m;
+        }
+        for (int t = tid; t < kTilesCap; t += kParseThreads) entry[t] = (uint16_t)kNone16;
+        __syncthreads();
+        // next non-empty bitmap word at or after w
+        for (int w = tid; w <= ntiles; w += kParseThreads) {
+            int k = w;
+            while (k < ntiles && okbits[k] == 0) ++k;
+            nzw[w] = (uint16_t)(k < ntiles ? k : kNone16);
         }
         __syncthreads();
-        if (warp == 0) {
-            if (fixS >= 0) {
-                const int fj = ps.fixJ;
-                if (fj < 0x7fffffff && lane == 0) {
-                    const int d = effective_cand(cand, &ps, fj);
-                    const int k = ps.npatch++;
-                    ps.patchJ[k] = fj; ps.patchD[k] = d;
-                    const int inf = position_info(win, wb, fj, d, g.pre);
-                    info[fj] = (uint8_t)inf;
-                    unsigned bit = 1u << (fj & 31);
-                    if (inf != 7) okbits[fj >> 5] |= bit; else okbits[fj >> 5] &= ~bit;
+
+        // ---- P2: successor function F over states ----
+        for (int idx = tid; idx < ntiles * 32; idx += kParseThreads) {
+            const int b = base + idx;
+            unsigned f = 0;
+            if (b >= B0 && b < E) {
+                const int j = probe_next(info, okbits, nzw, ntiles, base, b);
+                if (j >= 0) {
+                    const unsigned fwd = info[j - base] & 0xFFu;
+                    f = fwd >= kCapLen ? 1u : (unsigned)j + fwd;      // 1 = long match, resolved where the orbit meets it
                 }
-                __syncwarp();
             }
-            int E = pos + kBatch; if (E > t0) E = t0;
-            int B = pos + 1, jmin = pos + 1;            // FirstPass: backRefEnd = j = startPos + 1
-            int ntok = ps.ntok;
+            F[idx] = (uint16_t)f;
+        }
+        __syncthreads();
+
+        // ---- P3: first iterate leaving the tile (<= 8 hops: every match advances the state by >= 4) ----
+        for (int t = warp; t < ntiles; t += nwarps) {
+            const int tileStart = base + t * 32, tileEnd = tileStart + 32;
+            unsigned e = F[t * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const bool inside = e >= 2 && (int)e < tileEnd;
+                const unsigned e2 = __shfl_sync(0xffffffffu, e, ((int)e - tileStart) & 31);
+                if (inside) e = e2;
+            }
+            E1[t * 32 + lane] = (uint16_t)e;
+        }
+        __syncthreads();
+
+        // ---- P4: follow the orbit tile by tile (warp 0, all lanes redundantly; lanes cooperate on long matches) ----
+        if (warp == 0) {
+            int b = B0, finalB = B0, npre = 0;
+            const int tokBase = ps.ntok;
+            if (B0 < E) {
+                const unsigned inf = info[B0 - base];
+                if ((inf & 0xFFu) >= 4) {                 // first probe of the batch: j == backRefEnd, no backward room
+                    const int d = patched_cand(cand, &ps, B0);
+                    int fwd = (int)(inf & 0xFFu);
+                    if (fwd >= kCapLen) fwd = coop_fwd(win, wb + B0, wb + B0 - d, lane);
+                    if (lane == 0) { tokA[tokBase] = (uint32_t)B0 | ((uint32_t)fwd << 16); tokD[tokBase] = (uint16_t)d; }
+                    b = B0 + fwd; npre = 1;
+                }
+            }
             for (;;) {
-                int j = -1;
-                {
-                    const int x = jmin + lane;
-                    const int inf = (x < E) ? info[x] : 7;
-                    const bool el = (inf != 7) && (x - B >= inf);
-                    const unsigned m = __ballot_sync(0xffffffffu, el);
-                    if (m) {
-                        j = jmin + __ffs(m) - 1;
-                    } else {
-                        // every usable position at distance >= 4 from B is acceptable: scan the bitmap
-                        int start = jmin + 32;
-                        int w0 = start >> 5;
-                        const int wEnd = (E + 31) >> 5;
-                        while (w0 < wEnd) {
-                            const int w = w0 + lane;
-                            unsigned bits = (w < wEnd) ? okbits[w] : 0u;
-                            if (w == (start >> 5)) bits &= ~0u << (start & 31);
-                            const unsigned any = __ballot_sync(0xffffffffu, bits != 0);
-                            if (any) {
-                                const int src = __ffs(any) - 1;
-                                const unsigned b = __shfl_sync(0xffffffffu, bits, src);
-                                j = (w0 + src) * 32 + __ffs(b) - 1;
-                                break;
-                            }
-                            w0 += 32;
-                        }
-                    }
-                }
-                if (j < 0 || j >= E) break;
-                // exact match at j: forward to 258, backward into the pending literals (encoder.cpp:399-416)
-                int d = cand[j];
-                for (int k = 0; k < ps.npatch; ++k) if (ps.patchJ[k] == j) d = ps.patchD[k];
+                finalB = b;
+                if (b >= E) break;
+                const int r = b - base, t = r >> 5;
+                if (lane == 0) entry[t] = (uint16_t)b;
+                const unsigned e = E1[r];
+                if (e >= 2) { b = (int)e; continue; }
+                const int tileEnd = base + (t + 1) * 32;
+                int x = b; unsigned f;
+                for (;;) { f = F[x - base]; if (f >= 2 && (int)f < tileEnd) x = (int)f; else break; }
+                if (f == 0) { finalB = x; break; }        // no further match in this batch
+                // long match at state x: exact lengths
+                const int j = probe_next(info, okbits, nzw, ntiles, base, x);
+                const int d = patched_cand(cand, &ps, j);
                 const int p = j - d;
-                int fwd;
-                {
-                    const unsigned long long xa = ld8(win, wb + j + lane * 8) ^ ld8(win, wb + p + lane * 8);
-                    const unsigned mm = __ballot_sync(0xffffffffu, xa != 0);
-                    if (mm) {
-                        const int src = __ffs(mm) - 1;
-                        const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src);
-                        fwd = src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
-                    } else {
-                        fwd = 256;
-                        if (win[wb + j + 256] == win[wb + p + 256]) { fwd = 257; if (win[wb + j + 257] == win[wb + p + 257]) fwd = 258; }
-                    }
-                }
+                const int fwd = coop_fwd(win, wb + j, wb + p, lane);
+                int maxBack = j - x;
+                { const int room = p + g.pre; if (room < maxBack) maxBack = room; }     // R4: clamp at stream start
+                if (maxBack > kMaxMatch) maxBack = kMaxMatch;                            // R6: cap (reference breaks at 259)
                 int lb = 0;
-                int maxBack = j - B;
-                {
-                    int room = p + g.pre; if (room < maxBack) maxBack = room;       // R4: clamp at stream start
-                    if (maxBack > 258) maxBack = 258;                               // R6: cap (reference breaks at 259)
-                    if (maxBack > 0) {
-                        const unsigned long long xb = ld8(win, wb + j - 8 - lane * 8) ^ ld8(win, wb + p - 8 - lane * 8);
-                        const unsigned mm = __ballot_sync(0xffffffffu, xb != 0);
-                        if (mm) {
-                            const int src = __ffs(mm) - 1;
-                            const unsigned long long xs = __shfl_sync(0xffffffffu, xb, src);
-                            lb = src * 8 + (__clzll((long long)xs) >> 3);
-                        } else {
-                            lb = 256;
-                            if (win[wb + j - 257] == win[wb + p - 257]) { lb = 257; if (win[wb + j - 258] == win[wb + p - 258]) lb = 258; }
-                        }
-                        if (lb > maxBack) lb = maxBack;
-                    }
-                }
+                if (maxBack > 0) { lb = coop_back(win, wb + j, wb + p, lane); if (lb > maxBack) lb = maxBack; }
                 int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
                 const int ms = j - lb;
-                if (lane == 0) {
-                    tokA[ntok] = (uint32_t)ms | ((uint32_t)m << 16);
-                    tokD[ntok] = (uint16_t)d;
-                }
-                ++ntok;
-                B = ms + m;
-                jmin = B + 1;
+                if (lane == 0) lazyTok[t] = (uint32_t)ms | ((uint32_t)m << 16);
+                b = ms + m;
             }
             if (lane == 0) {
-                ps.ntok = ntok;
-                const int newpos = B > E ? B : E;
+                ps.npre = npre;
+                const int newpos = finalB > E ? finalB : E;
                 ps.fixS = -1; ps.fixJ = 0x7fffffff;
-                if (B < E && newpos < t0) {            // next batch start was not covered by a match: never inserted
+                if (finalB < E && newpos < t0 && ps.nexcl < 4) {   // next batch start not covered by a match: never inserted
                     ps.excl[ps.nexcl++] = newpos;
                     ps.fixS = newpos;
                 }
@@ -398,11 +497,73 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             }
         }
         __syncthreads();
+
+        // ---- P5: tiles expand their part of the orbit into tokens ----
+        unsigned cnt = 0;
+        if (tid < ntiles) {
+            const unsigned e = entry[tid];
+            if (e != kNone16) {
+                const int tileEnd = base + (tid + 1) * 32;
+                int x = (int)e;
+                for (;;) {
+                    const unsigned f = F[x - base];
+                    if (f == 0) break;
+                    ++cnt;
+                    if (f == 1 || (int)f >= tileEnd) break;
+                    x = (int)f;
+                }
+            }
+        }
+        unsigned inc = cnt;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned v = wsum[lane];
+            for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+            wsum[lane] = v;
+        }
+        __syncthreads();
+        if (cnt) {
+            int out = ps.ntok + ps.npre + (int)((warp ? wsum[warp - 1] : 0) + inc - cnt);
+            const int tileEnd = base + (tid + 1) * 32;
+            int x = (int)entry[tid];
+            for (;;) {
+                const unsigned f = F[x - base];
+                if (f == 0) break;
+                const int j = probe_next(info, okbits, nzw, ntiles, base, x);
+                const int d = patched_cand(cand, &ps, j);
+                uint32_t tok;
+                if (f == 1) {
+                    tok = lazyTok[tid];
+                } else {
+                    const unsigned inf = info[j - base];
+                    const int fwd = (int)(inf & 0xFFu);
+                    int back = (int)(inf >> 8);
+                    const int gap = j - x;
+                    if (back >= kCapLen && gap > kCapLen) {
+                        int limit = gap; const int room = j - d + g.pre;
+                        if (room < limit) limit = room;
+                        if (limit > kMaxMatch) limit = kMaxMatch;
+                        back = slow_back(win, wb + j, wb + j - d, limit);
+                    }
+                    const int lb = back < gap ? back : gap;
+                    int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
+                    tok = (uint32_t)(j - lb) | ((uint32_t)m << 16);
+                }
+                tokA[out] = tok; tokD[out] = (uint16_t)d; ++out;
+                if (f == 1 || (int)f >= tileEnd) break;
+                x = (int)f;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) ps.ntok += ps.npre + (int)wsum[31];
+        __syncthreads();
     }
     __syncthreads();
 
-    // ---- phase C: histograms (GetFrequencies, encoder.cpp:442-471) ----
-    unsigned* hist = reinterpret_cast<unsigned*>(info);            // per-warp private copies (info is dead)
+    // ---- histograms (GetFrequencies, encoder.cpp:442-471) ----
+    unsigned* hist = reinterpret_cast<unsigned*>(info);            // per-warp private copies (batch arrays are dead)
     for (int i = tid; i < nwarps * kHistStride; i += kParseThreads) hist[i] = 0;
     __syncthreads();
     {
