@@ -15,7 +15,7 @@ namespace {
 
 using namespace zz;
 
-constexpr uint32_t kMaxSlots = 4096;        // chunks per batch (scratch is sized for one batch)
+constexpr uint32_t kMaxSlots = 16384;       // chunks per batch (scratch is sized for one batch)
 constexpr int kMaxDevices = 16;
 
 thread_local std::string t_lastError;

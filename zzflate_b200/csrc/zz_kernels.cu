@@ -83,48 +83,115 @@ __device__ __forceinline__ int len_symbol(int len, int& extraBits, int& extraVal
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-CAND : one warp per chunk, table in shared memory
+// K-CAND : hash heads.  One warp walks a run of consecutive chunks, 32 positions per step:
+//   candidate(j) = nearest earlier inserted position with the same 13-bit hash
+//                = nearest lower lane of the same step with that hash (__match_any_sync), else table[h].
+// Every position is inserted except position 0 of each chunk (never probed nor inserted, encoder.cpp:384);
+// the positions before the first chunk of the run only prime the table (AddHashEntries, encoder.cpp:474).
+//
+// The table holds stream positions modulo 65536 in 16 bits (16 KiB per warp instead of the reference's
+// 32 KiB of ints): distances below 65536 are exact modulo 65536, and every 32768 positions a sweep retires the
+// entries that are 32768 or more behind (invalid from then on, encoder.cpp:392), so nothing ever aliases.
+// With the default geometry (64 KiB chunks, 32 KiB dictionary) the table a fresh reference Encoder would
+// hold after priming chunk c equals, on every entry that can still yield a valid distance, the table after
+// walking chunk c-1 -- so a run of chunks needs one priming pass only.
+// Input is staged through shared memory with cp.async (LDGSTS), double buffered, 1 KiB tiles.
 // ------------------------------------------------------------------------------------------------
+constexpr int kCandTile = 1024;
 constexpr int kEmptySlot = -(1 << 30);
+constexpr int kCandStage = kCandTile + 16;
 
-__global__ void __launch_bounds__(32) k_candidates(Job job)
+__device__ __forceinline__ void cp_async4(void* smemDst, const void* gsrc)
 {
-    __shared__ int table[kHashSize];
-    const unsigned slot = blockIdx.x;
-    const Geom g = chunk_geom(job, slot);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// stages bytes gsrc[0, nbytes) at st + ((uintptr)gsrc & 3); bytes outside [validLo, validHi) read as zero
+__device__ __forceinline__ void stage_tile(uint8_t* st, const uint8_t* gsrc, int nbytes, const uint8_t* validLo,
+                                           const uint8_t* validHi, int lane)
+{
+    const int phase = (int)(reinterpret_cast<uintptr_t>(gsrc) & 3);
+    const uint8_t* g0 = gsrc - phase;
+    const int words = (phase + nbytes + 3) >> 2;
+    for (int w = lane; w < words; w += 32) {
+        const uint8_t* ga = g0 + 4 * w;
+        if (ga >= validLo && ga + 4 <= validHi) {
+            cp_async4(st + 4 * w, ga);
+        } else {
+            unsigned v = 0;
+            for (int k = 0; k < 4; ++k) if (ga + k >= validLo && ga + k < validHi) v |= (unsigned)ga[k] << (8 * k);
+            *reinterpret_cast<unsigned*>(st + 4 * w) = v;
+        }
+    }
+    cp_async_commit();
+}
+
+__global__ void __launch_bounds__(32) k_candidates(Job job, int run)
+{
+    __shared__ uint16_t table[kHashSize];
+    __shared__ __align__(16) uint8_t stage[2][kCandStage];
     const int lane = threadIdx.x;
-    for (int i = lane; i < kHashSize; i += 32) table[i] = kEmptySlot;
-    __syncwarp();
+    const unsigned firstSlot = blockIdx.x * (unsigned)run;
+    unsigned lastSlot = firstSlot + (unsigned)run; if (lastSlot > job.nchunks) lastSlot = job.nchunks;
+    const Geom g0 = chunk_geom(job, firstSlot);
+    const Geom gl = chunk_geom(job, lastSlot - 1);
+    const long long S = job.chunk;
+    const uint8_t* base0 = job.src + g0.off;                                  // position q = 0 of the run
+    const long long qEnd = (long long)(lastSlot - 1 - firstSlot) * S + gl.n;   // positions [-dict, qEnd)
+    const uint8_t* validLo = job.src - job.history;
+    const uint8_t* validHi = job.src + job.n;
 
-    const uint8_t* base = job.src + g.off;
-    const long long limit = (long long)job.n - g.off;          // bytes readable at and after the chunk start
-    uint16_t* cand = job.cand + (size_t)slot * job.chunk;
-
-    for (int j0 = -g.dict; j0 < g.n; j0 += 32) {
-        const int j = j0 + lane;
-        unsigned v = 0;
-        if (j < g.n) {
-            v = (j < limit) ? base[j] : 0u;
-            v |= (j + 1 < limit) ? ((unsigned)base[j + 1] << 8) : 0u;
-            v |= (j + 2 < limit) ? ((unsigned)base[j + 2] << 16) : 0u;
-        }
-        const unsigned h = hash3(v);
-        // position 0 of a block is neither probed nor inserted (encoder.cpp:384); dictionary positions are
-        // inserted only (AddHashEntries, encoder.cpp:474)
-        const bool act = (j != 0) && (j < g.n);
-        const unsigned key = act ? h : (0x10000u + lane);
-        const unsigned grp = __match_any_sync(0xffffffffu, key);
-        const unsigned lower = grp & ((1u << lane) - 1u);
-        const bool last = (grp >> lane) == 1u;
-        const int old = act ? table[h] : kEmptySlot;
+    long long q0 = -(long long)g0.dict;
+    unsigned sweepAt = 0;                    // steps until the next sweep; 0 => sweep now (also the initial fill)
+    int buf = 0;
+    stage_tile(stage[0], base0 + q0, kCandTile + 8, validLo, validHi, lane);
+    for (; q0 < qEnd; q0 += kCandTile) {
+        cp_async_wait_all();
         __syncwarp();
-        if (act && last) table[h] = j;
-        __syncwarp();
-        if (j >= 0 && j < g.n) {
-            const int p = lower ? (j0 + 31 - __clz(lower)) : old;
-            const int d = j - p;
-            cand[j] = (uint16_t)((act && d < kMaxDistance) ? d : 0);
+        if (q0 + kCandTile < qEnd) stage_tile(stage[buf ^ 1], base0 + q0 + kCandTile, kCandTile + 8, validLo, validHi, lane);
+        const unsigned* sw = reinterpret_cast<const unsigned*>(stage[buf]);
+        const int phase = (int)(reinterpret_cast<uintptr_t>(base0 + q0) & 3);
+        long long tileEnd = q0 + kCandTile; if (tileEnd > qEnd) tileEnd = qEnd;
+#pragma unroll 4
+        for (long long qs = q0; qs < tileEnd; qs += 32) {
+            if (sweepAt == 0) {
+                // retire entries 32768 or more behind position qs (and stale markers); marker = qs - 32768
+                const unsigned now = (unsigned)(qs & 0xFFFF);
+                const unsigned marker = (now - 32768u) & 0xFFFFu;
+                for (int i = lane; i < kHashSize; i += 32) {
+                    const unsigned age = (now - table[i]) & 0xFFFFu;
+                    if (age == 0 || age >= 32768u || qs == -(long long)g0.dict) table[i] = (uint16_t)marker;
+                }
+                __syncwarp();
+                sweepAt = 1024;
+            }
+            --sweepAt;
+            const long long q = qs + lane;
+            const int o = phase + (int)(q - q0);
+            const unsigned v = __funnelshift_r(sw[o >> 2], sw[(o >> 2) + 1], (o & 3) * 8) & 0xFFFFFFu;
+            const unsigned h = hash3(v);
+            // chunk of the run and chunk-relative position (runs longer than one chunk only with 64 KiB chunks)
+            const long long k = (run > 1 && q >= 0) ? (q >> 16) : 0;
+            const int j = (int)(q - k * S);
+            const bool inRange = q < qEnd;
+            const bool act = inRange && (j != 0 || q < 0);
+            const unsigned key = act ? h : (0x10000u + lane);
+            const unsigned grp = __match_any_sync(0xffffffffu, key);
+            const unsigned lower = grp & ((1u << lane) - 1u);
+            const bool last = (grp >> lane) == 1u;
+            const unsigned old = table[h];
+            __syncwarp();
+            if (act && last) table[h] = (uint16_t)(q & 0xFFFF);
+            __syncwarp();
+            if (inRange && q >= 0) {
+                const unsigned d = lower ? (unsigned)(lane - (31 - __clz(lower))) : (((unsigned)(q & 0xFFFF) - old) & 0xFFFFu);
+                job.cand[(size_t)(firstSlot + (unsigned)k) * job.chunk + j] = (uint16_t)((act && d < (unsigned)kMaxDistance) ? d : 0);
+            }
         }
+        buf ^= 1;
     }
 }
 
@@ -1226,7 +1293,15 @@ cudaError_t configure_kernels()
 
 int launch_candidates(const Job& job, cudaStream_t s)
 {
-    k_candidates<<<job.nchunks, 32, 0, s>>>(job);
+    // one priming pass per run of chunks is exact only for the default geometry (see K-CAND)
+    int run = 1;
+    if (job.chunk == 65536 && job.dict == 32768) {
+        const unsigned target = 148u * 11u;                       // resident warps: 16 KiB table + staging per CTA
+        run = (int)((job.nchunks + target - 1) / target);
+        if (run < 1) run = 1;
+        if (run > 64) run = 64;
+    }
+    k_candidates<<<(job.nchunks + run - 1) / run, 32, 0, s>>>(job, run);
     return 1;
 }
 
