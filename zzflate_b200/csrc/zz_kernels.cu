@@ -178,13 +178,25 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
             const int j = (int)(q - k * S);
             const bool inRange = q < qEnd;
             const bool act = inRange && (j != 0 || q < 0);
-            const unsigned key = act ? h : (0x10000u + lane);
-            const unsigned grp = __match_any_sync(0xffffffffu, key);
-            const unsigned lower = grp & ((1u << lane) - 1u);
-            const bool last = (grp >> lane) == 1u;
-            const unsigned old = table[h];
+            // Same-hash positions inside one step are found without MATCH.ANY (slow when all 32 keys differ, the
+            // common case): everybody writes, whoever does not read its own value back shares its hash with
+            // another lane; only those groups are then resolved with ballots.
+            const unsigned myv = (unsigned)(q & 0xFFFF);
+            const unsigned old = act ? table[h] : 0u;
             __syncwarp();
-            if (act && last) table[h] = (uint16_t)(q & 0xFFFF);
+            if (act) table[h] = (uint16_t)myv;
+            __syncwarp();
+            const bool loser = act && table[h] != myv;
+            unsigned pending = __ballot_sync(0xffffffffu, loser);
+            unsigned lower = 0;
+            bool fixTable = false;
+            while (pending) {
+                const unsigned hl = __shfl_sync(0xffffffffu, h, __ffs(pending) - 1);
+                const unsigned mem = __ballot_sync(0xffffffffu, act && h == hl);
+                if (act && h == hl) { lower = mem & ((1u << lane) - 1u); fixTable = (mem >> lane) == 1u; }
+                pending &= ~mem;
+            }
+            if (fixTable) table[h] = (uint16_t)myv;          // the highest position of a group owns the slot
             __syncwarp();
             if (inRange && q >= 0) {
                 const unsigned d = lower ? (unsigned)(lane - (31 - __clz(lower))) : (((unsigned)(q & 0xFFFF) - old) & 0xFFFFu);
