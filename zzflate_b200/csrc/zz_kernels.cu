@@ -270,9 +270,11 @@ __device__ __forceinline__ unsigned long long ld8(const uint8_t* win, int o)
 constexpr int kParseThreads = 1024;
 constexpr int kBatchCap = kBatch + 128;            // entries of the per-batch arrays (tile-aligned base + slack)
 constexpr int kTilesCap = kBatchCap / 32;
-constexpr int kCapLen = 32;                        // cap of the parallel forward/backward compares
+constexpr int kSegCap = kTilesCap + 32;
+constexpr int kCapLen = 32;                        // cap of the parallel forward compare
 constexpr unsigned kNone16 = 0xFFFFu;
-constexpr int kParseSmem = kWinBytes + 3 * kBatchCap * 2 /*info,F,E1*/ + (kTilesCap + 4) * (4 + 2 + 2 + 4 + 4);
+constexpr int kParseSmem = kWinBytes + kBatchCap /*info*/ + 3 * kBatchCap * 2 /*F,E1,E2*/ +
+                           (kTilesCap + 4) * (4 + 4 + 2 + 2) + kSegCap * 2;
 
 struct ParseShared {
     int pos;            // start of the next FirstPass batch
@@ -285,7 +287,8 @@ struct ParseShared {
     int fixS;           // excluded position whose successor still has to be found, or -1
     int fixJ;
     int npre;           // 1 if the batch's first probe (j == backRefEnd) produced a token
-    int total;          // tokens of the batch produced by the tiles
+    int nseg;           // orbit segments of the batch (one per super tile entered / long match resolved)
+    int finalB;         // last state of the batch, or -1 while it is still inside a tile
 };
 
 // candidate of j with the never-inserted batch starts removed from the hash chain
@@ -305,10 +308,10 @@ __device__ int effective_cand(const uint16_t* cand, const ParseShared* ps, int j
     }
 }
 
-__device__ __forceinline__ int patched_cand(const uint16_t* cand, const ParseShared* ps, int j)
+__device__ __forceinline__ int patched_cand(const uint16_t* cand, const ParseShared* ps, int npatch, int j)
 {
     int d = cand[j];
-    for (int k = 0; k < ps->npatch; ++k) if (ps->patchJ[k] == j) d = ps->patchD[k];
+    if (npatch) for (int k = 0; k < npatch; ++k) if (ps->patchJ[k] == j) d = ps->patchD[k];
     return d;
 }
 
@@ -318,16 +321,6 @@ __device__ __forceinline__ int fwd_cap(const uint8_t* win, int oj, int op)
     for (int k = 0; k < kCapLen / 8; ++k) {
         const unsigned long long x = ld8(win, oj + 8 * k) ^ ld8(win, op + 8 * k);
         if (x) return 8 * k + ((__ffsll((long long)x) - 1) >> 3);
-    }
-    return kCapLen;
-}
-
-__device__ __forceinline__ int back_cap(const uint8_t* win, int oj, int op)
-{
-#pragma unroll
-    for (int k = 0; k < kCapLen / 8; ++k) {
-        const unsigned long long x = ld8(win, oj - 8 - 8 * k) ^ ld8(win, op - 8 - 8 * k);
-        if (x) return 8 * k + (__clzll((long long)x) >> 3);
     }
     return kCapLen;
 }
@@ -362,25 +355,29 @@ __device__ __forceinline__ int coop_back(const uint8_t* win, int oj, int op, int
     return lb;
 }
 
-// single-thread exact backward length, capped at `limit` (rare path of the token expansion)
-__device__ int slow_back(const uint8_t* win, int oj, int op, int limit)
+// single-thread backward match length, at most `limit` bytes (token expansion: limit is the literal gap, mostly <= 3)
+__device__ __forceinline__ int back_upto(const uint8_t* win, int oj, int op, int limit)
 {
     int lb = 0;
-    while (lb < limit && win[oj - 1 - lb] == win[op - 1 - lb]) ++lb;
-    return lb;
+    while (lb < limit) {
+        const unsigned y = ld4(win, oj - 4 - lb) ^ ld4(win, op - 4 - lb);
+        const int c = y ? (__clz(y) >> 3) : 4;
+        lb += c;
+        if (c < 4) break;
+    }
+    return lb < limit ? lb : limit;
 }
 
 // First position the walk would take from state b (b = end of the previous match), or -1.
-// info == 0 marks an unusable position; the low byte of info is min(fwd, 32).
-__device__ __forceinline__ int probe_next(const uint16_t* info, const unsigned* okbits, const uint16_t* nzw,
+// info == 0 marks an unusable position, otherwise info - 1 = min(forward length, 32); a usable position j is
+// taken when j - b >= 4 - min(fwd, 4).
+__device__ __forceinline__ int probe_next(const uint8_t* info, const unsigned* okbits, const uint16_t* nzw,
                                           int ntiles, int base, int b)
 {
     const int r = b - base;
 #pragma unroll
-    for (int k = 1; k <= 3; ++k) {
-        const unsigned inf = info[r + k];
-        if (inf != 0 && 4 - (int)(inf & 0xFF) <= k) return b + k;
-    }
+    for (int k = 1; k <= 3; ++k)
+        if ((int)info[r + k] >= 5 - k) return b + k;
     const int x = r + 4;
     const int w = x >> 5;
     if (w >= ntiles) return -1;
@@ -418,14 +415,15 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* win = smem;
-    uint16_t* info = reinterpret_cast<uint16_t*>(smem + kWinBytes);
-    uint16_t* F = info + kBatchCap;
+    uint8_t* info = smem + kWinBytes;
+    uint16_t* F = reinterpret_cast<uint16_t*>(info + kBatchCap);
     uint16_t* E1 = F + kBatchCap;
-    unsigned* okbits = reinterpret_cast<unsigned*>(E1 + kBatchCap);
+    uint16_t* E2 = E1 + kBatchCap;
+    unsigned* okbits = reinterpret_cast<unsigned*>(E2 + kBatchCap);
     unsigned* lazyTok = okbits + (kTilesCap + 4);
-    unsigned* tcnt = lazyTok + (kTilesCap + 4);
-    uint16_t* nzw = reinterpret_cast<uint16_t*>(tcnt + (kTilesCap + 4));
+    uint16_t* nzw = reinterpret_cast<uint16_t*>(lazyTok + (kTilesCap + 4));
     uint16_t* entry = nzw + (kTilesCap + 4);
+    uint16_t* seg = entry + (kTilesCap + 4);
     __shared__ ParseShared ps;
     __shared__ unsigned wsum[32];
 
@@ -461,29 +459,41 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             }
             __syncthreads();
         }
+        const int npatch = ps.npatch;
         int E = pos + kBatch; if (E > t0) E = t0;
         const int B0 = pos + 1;                          // FirstPass: backRefEnd = j = startPos + 1
         const int base = B0 & ~31;
         const int ntiles = (E - base + 31) >> 5;
+        const int nsuper = (ntiles + 31) >> 5;
 
         // ---- P1: per-position match info (parse independent) ----
-        for (int idx = tid; idx < ntiles * 32 + 64; idx += kParseThreads) {
-            const int j = base + idx;
-            unsigned inf = 0;
-            if (j >= B0 && j < E) {
-                const int d = patched_cand(cand, &ps, j);
+        {
+            const int lim = ntiles * 32 + 64;
+            int idx = tid;
+            int dNext = (idx < lim && base + idx >= B0 && base + idx < E) ? patched_cand(cand, &ps, npatch, base + idx) : 0;
+            for (; idx < lim; idx += kParseThreads) {
+                const int j = base + idx;
+                const int d = dNext;
+                const int nidx = idx + kParseThreads;
+                dNext = (nidx < lim && base + nidx >= B0 && base + nidx < E) ? patched_cand(cand, &ps, npatch, base + nidx) : 0;
+                unsigned inf = 0;
                 if (d) {
                     const int p = j - d;
                     const int fwd = fwd_cap(win, wb + j, wb + p);
-                    int back = back_cap(win, wb + j, wb + p);
-                    const int room = p + g.pre;          // bytes of real history before the candidate (R4 clamp)
-                    if (back > room) back = room;
-                    if (fwd + back >= 4) inf = (unsigned)fwd | ((unsigned)back << 8);
+                    bool ok = fwd >= 4;
+                    if (!ok) {
+                        const unsigned y = ld4(win, wb + j - 4) ^ ld4(win, wb + p - 4);
+                        int back = y ? (__clz(y) >> 3) : 4;
+                        const int room = p + g.pre;      // bytes of real history before the candidate (R4 clamp)
+                        if (back > room) back = room;
+                        ok = fwd + back >= 4;
+                    }
+                    if (ok) inf = (unsigned)fwd + 1u;
                 }
+                info[idx] = (uint8_t)inf;
+                const unsigned m = __ballot_sync(0xffffffffu, inf != 0);
+                if (lane == 0) okbits[idx >> 5] = m;
             }
-            info[idx] = (uint16_t)inf;
-            const unsigned m = __ballot_sync(0xffffffffu, inf != 0);
-            if (lane == 0 && (idx >> 5) < kTilesCap + 4) okbits[idx >> 5] = m;
         }
         for (int t = tid; t < kTilesCap; t += kParseThreads) entry[t] = (uint16_t)kNone16;
         __syncthreads();
@@ -495,44 +505,54 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         }
         __syncthreads();
 
-        // ---- P2: successor function F over states ----
-        for (int idx = tid; idx < ntiles * 32; idx += kParseThreads) {
-            const int b = base + idx;
+        // ---- P2: successor function F over states, and E1 = where the orbit of b leaves b's tile.
+        //      Values: 0 = no further match in the batch; a state inside the tile = the orbit meets a long match
+        //      there (F == 1 marks such states); otherwise the first iterate beyond the tile.  A match advances
+        //      the state by >= 4, so 3 rounds of pointer jumping (8 hops) cover a 32-state tile.
+        for (int t = warp; t < ntiles; t += nwarps) {
+            const int tileStart = base + t * 32, tileEnd = tileStart + 32;
+            const int b = tileStart + lane;
             unsigned f = 0;
             if (b >= B0 && b < E) {
                 const int j = probe_next(info, okbits, nzw, ntiles, base, b);
                 if (j >= 0) {
-                    const unsigned fwd = info[j - base] & 0xFFu;
-                    f = fwd >= kCapLen ? 1u : (unsigned)j + fwd;      // 1 = long match, resolved where the orbit meets it
+                    const unsigned fwd = (unsigned)info[j - base] - 1u;
+                    f = fwd >= kCapLen ? 1u : (unsigned)j + fwd;
                 }
             }
-            F[idx] = (uint16_t)f;
-        }
-        __syncthreads();
-
-        // ---- P3: first iterate leaving the tile (<= 8 hops: every match advances the state by >= 4) ----
-        for (int t = warp; t < ntiles; t += nwarps) {
-            const int tileStart = base + t * 32, tileEnd = tileStart + 32;
-            unsigned e = F[t * 32 + lane];
+            F[t * 32 + lane] = (uint16_t)f;
+            const bool myLong = f == 1u;
+            unsigned e = myLong ? (unsigned)b : f;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const bool inside = e >= 2 && (int)e < tileEnd;
-                const unsigned e2 = __shfl_sync(0xffffffffu, e, ((int)e - tileStart) & 31);
-                if (inside) e = e2;
+                const int src = ((int)e - tileStart) & 31;
+                const unsigned e2 = __shfl_sync(0xffffffffu, e, src);
+                const bool lz = __shfl_sync(0xffffffffu, myLong ? 1 : 0, src) != 0;
+                if (e >= 2 && (int)e < tileEnd && !lz) e = e2;
             }
             E1[t * 32 + lane] = (uint16_t)e;
+            E2[t * 32 + lane] = (uint16_t)e;
         }
         __syncthreads();
+        // ---- P3: same for super tiles of 32 tiles, by pointer jumping through shared memory (in place) ----
+        for (int r = 0; r < 5; ++r) {
+            for (int idx = tid; idx < ntiles * 32; idx += kParseThreads) {
+                const unsigned e = E2[idx];
+                const int superEnd = base + ((idx >> 10) + 1) * 1024;
+                if (e >= 2 && (int)e < superEnd && (int)e - base < ntiles * 32 && F[(int)e - base] != 1) E2[idx] = E2[(int)e - base];
+            }
+            __syncthreads();
+        }
 
-        // ---- P4: follow the orbit tile by tile (warp 0, all lanes redundantly; lanes cooperate on long matches) ----
+        // ---- P4: follow the orbit super tile by super tile (warp 0; lanes cooperate on long matches) ----
         if (warp == 0) {
-            int b = B0, finalB = B0, npre = 0;
+            int b = B0, finalB = B0, npre = 0, nseg = 0;
             const int tokBase = ps.ntok;
             if (B0 < E) {
                 const unsigned inf = info[B0 - base];
-                if ((inf & 0xFFu) >= 4) {                 // first probe of the batch: j == backRefEnd, no backward room
-                    const int d = patched_cand(cand, &ps, B0);
-                    int fwd = (int)(inf & 0xFFu);
+                if (inf >= 5) {                           // first probe of the batch: j == backRefEnd, no backward room
+                    const int d = patched_cand(cand, &ps, npatch, B0);
+                    int fwd = (int)inf - 1;
                     if (fwd >= kCapLen) fwd = coop_fwd(win, wb + B0, wb + B0 - d, lane);
                     if (lane == 0) { tokA[tokBase] = (uint32_t)B0 | ((uint32_t)fwd << 16); tokD[tokBase] = (uint16_t)d; }
                     b = B0 + fwd; npre = 1;
@@ -541,17 +561,17 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             for (;;) {
                 finalB = b;
                 if (b >= E) break;
-                const int r = b - base, t = r >> 5;
-                if (lane == 0) entry[t] = (uint16_t)b;
-                const unsigned e = E1[r];
-                if (e >= 2) { b = (int)e; continue; }
-                const int tileEnd = base + (t + 1) * 32;
-                int x = b; unsigned f;
-                for (;;) { f = F[x - base]; if (f >= 2 && (int)f < tileEnd) x = (int)f; else break; }
-                if (f == 0) { finalB = x; break; }        // no further match in this batch
-                // long match at state x: exact lengths
+                if (lane == 0) seg[nseg] = (uint16_t)b;
+                ++nseg;
+                const int r = b - base;
+                const unsigned e = E2[r];
+                const int superEnd = base + ((r >> 10) + 1) * 1024;
+                if ((int)e >= superEnd || (int)e >= E) { b = (int)e; continue; }
+                if (e == 0) { finalB = -1; break; }       // ends inside a tile: the tile reports the last state
+                // long match at state x = e: exact lengths
+                const int x = (int)e;
                 const int j = probe_next(info, okbits, nzw, ntiles, base, x);
-                const int d = patched_cand(cand, &ps, j);
+                const int d = patched_cand(cand, &ps, npatch, j);
                 const int p = j - d;
                 const int fwd = coop_fwd(win, wb + j, wb + p, lane);
                 int maxBack = j - x;
@@ -561,18 +581,22 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 if (maxBack > 0) { lb = coop_back(win, wb + j, wb + p, lane); if (lb > maxBack) lb = maxBack; }
                 int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
                 const int ms = j - lb;
-                if (lane == 0) lazyTok[t] = (uint32_t)ms | ((uint32_t)m << 16);
+                if (lane == 0) lazyTok[(x - base) >> 5] = (uint32_t)ms | ((uint32_t)m << 16);
                 b = ms + m;
             }
-            if (lane == 0) {
-                ps.npre = npre;
-                const int newpos = finalB > E ? finalB : E;
-                ps.fixS = -1; ps.fixJ = 0x7fffffff;
-                if (finalB < E && newpos < t0 && ps.nexcl < 4) {   // next batch start not covered by a match: never inserted
-                    ps.excl[ps.nexcl++] = newpos;
-                    ps.fixS = newpos;
-                }
-                ps.pos = newpos;
+            if (lane == 0) { ps.npre = npre; ps.nseg = nseg; ps.finalB = finalB; }
+        }
+        __syncthreads();
+        // ---- P4b: every segment marks the tiles it enters ----
+        if (tid < ps.nseg) {
+            int b = seg[tid];
+            const int superEnd = base + (((b - base) >> 10) + 1) * 1024;
+            for (;;) {
+                const int t = (b - base) >> 5;
+                entry[t] = (uint16_t)b;
+                const unsigned e = E1[b - base];
+                if (e == 0 || (int)e < base + (t + 1) * 32 || (int)e >= superEnd || (int)e >= E) break;
+                b = (int)e;
             }
         }
         __syncthreads();
@@ -586,8 +610,9 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 int x = (int)e;
                 for (;;) {
                     const unsigned f = F[x - base];
-                    if (f == 0) break;
+                    if (f == 0) { ps.finalB = x; break; }
                     ++cnt;
+                    if (f != 1 && (int)f >= E) ps.finalB = (int)f;      // the match that leaves the batch
                     if (f == 1 || (int)f >= tileEnd) break;
                     x = (int)f;
                 }
@@ -611,22 +636,16 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 const unsigned f = F[x - base];
                 if (f == 0) break;
                 const int j = probe_next(info, okbits, nzw, ntiles, base, x);
-                const int d = patched_cand(cand, &ps, j);
+                const int d = patched_cand(cand, &ps, npatch, j);
                 uint32_t tok;
                 if (f == 1) {
                     tok = lazyTok[tid];
                 } else {
-                    const unsigned inf = info[j - base];
-                    const int fwd = (int)(inf & 0xFFu);
-                    int back = (int)(inf >> 8);
-                    const int gap = j - x;
-                    if (back >= kCapLen && gap > kCapLen) {
-                        int limit = gap; const int room = j - d + g.pre;
-                        if (room < limit) limit = room;
-                        if (limit > kMaxMatch) limit = kMaxMatch;
-                        back = slow_back(win, wb + j, wb + j - d, limit);
-                    }
-                    const int lb = back < gap ? back : gap;
+                    const int fwd = (int)info[j - base] - 1;
+                    int limit = j - x;                                     // pending literals (encoder.cpp:404)
+                    { const int room = j - d + g.pre; if (room < limit) limit = room; }
+                    if (limit > kMaxMatch) limit = kMaxMatch;
+                    const int lb = back_upto(win, wb + j, wb + j - d, limit);
                     int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
                     tok = (uint32_t)(j - lb) | ((uint32_t)m << 16);
                 }
@@ -636,7 +655,17 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             }
         }
         __syncthreads();
-        if (tid == 0) ps.ntok += ps.npre + (int)wsum[31];
+        if (tid == 0) {
+            ps.ntok += ps.npre + (int)wsum[31];
+            const int finalB = ps.finalB;
+            const int newpos = finalB > E ? finalB : E;
+            ps.fixS = -1; ps.fixJ = 0x7fffffff;
+            if (finalB < E && newpos < t0 && ps.nexcl < 4) {       // next batch start not covered by a match: never inserted
+                ps.excl[ps.nexcl++] = newpos;
+                ps.fixS = newpos;
+            }
+            ps.pos = newpos;
+        }
         __syncthreads();
     }
     __syncthreads();
