@@ -32,3 +32,13 @@ for f, ln, src, d in sorted(lines, key=lambda l: -int(l[3]["# Samples"]))[:top]:
     s = int(d["# Samples"]); i = int(d["Instructions Executed"])
     st = max(stalls, key=lambda k: int(d.get(k, 0) or 0))
     print(f"{s * 100 / tot_s:5.1f}% smp {i * 100 / tot_i:5.1f}% inst  thr/inst {d['Avg. Threads Executed']:>5} {st.replace('stall_', ''):<10} {f}:{ln:<5} {src.strip()[:105]}")
+
+if len(sys.argv) > 4:      # extra: instruction share by source-line ranges "name:lo-hi,..."
+    print("\ninstruction / sample share by range")
+    for spec in sys.argv[4].split(","):
+        name, rng = spec.split(":"); lo, hi = map(int, rng.split("-"))
+        i = sum(int(l[3]["Instructions Executed"]) for l in lines if l[0].startswith("zz_kernels") and lo <= l[1] <= hi)
+        sm = sum(int(l[3]["# Samples"]) for l in lines if l[0].startswith("zz_kernels") and lo <= l[1] <= hi)
+        print(f"  {name:<12} {i * 100 / tot_i:5.1f}% inst  {sm * 100 / tot_s:5.1f}% samples")
+    i = sum(int(l[3]["Instructions Executed"]) for l in lines if not l[0].startswith("zz_kernels"))
+    print(f"  {'headers':<12} {i * 100 / tot_i:5.1f}% inst")

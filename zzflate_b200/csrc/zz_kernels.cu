@@ -310,19 +310,23 @@ __device__ int effective_cand(const uint16_t* cand, const ParseShared* ps, int j
 
 __device__ __forceinline__ int patched_cand(const uint16_t* cand, const ParseShared* ps, int npatch, int j)
 {
-    int d = cand[j];
+    int d = __ldg(cand + j);
     if (npatch) for (int k = 0; k < npatch; ++k) if (ps->patchJ[k] == j) d = ps->patchD[k];
     return d;
 }
 
 __device__ __forceinline__ int fwd_cap(const uint8_t* win, int oj, int op)
 {
+    // most candidates differ within the first 4 bytes: probe those with a 4-byte compare, then 8 at a time
+    const unsigned x0 = ld4(win, oj) ^ ld4(win, op);
+    if (x0) return (__ffs(x0) - 1) >> 3;
 #pragma unroll
-    for (int k = 0; k < kCapLen / 8; ++k) {
-        const unsigned long long x = ld8(win, oj + 8 * k) ^ ld8(win, op + 8 * k);
-        if (x) return 8 * k + ((__ffsll((long long)x) - 1) >> 3);
+    for (int k = 0; k < 3; ++k) {
+        const unsigned long long x = ld8(win, oj + 4 + 8 * k) ^ ld8(win, op + 4 + 8 * k);
+        if (x) return 4 + 8 * k + ((__ffsll((long long)x) - 1) >> 3);
     }
-    return kCapLen;
+    const unsigned x1 = ld4(win, oj + 28) ^ ld4(win, op + 28);
+    return x1 ? 28 + ((__ffs(x1) - 1) >> 3) : kCapLen;
 }
 
 // exact forward match length (<= 258), all 32 lanes cooperate (remain(), encoder.cpp:81-90)
@@ -531,18 +535,23 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 if (e >= 2 && (int)e < tileEnd && !lz) e = e2;
             }
             E1[t * 32 + lane] = (uint16_t)e;
-            E2[t * 32 + lane] = (uint16_t)e;
         }
         __syncthreads();
-        // ---- P3: same for super tiles of 32 tiles, by pointer jumping through shared memory (in place) ----
-        for (int r = 0; r < 5; ++r) {
-            for (int idx = tid; idx < ntiles * 32; idx += kParseThreads) {
-                const unsigned e = E2[idx];
-                const int superEnd = base + ((idx >> 10) + 1) * 1024;
-                if (e >= 2 && (int)e < superEnd && (int)e - base < ntiles * 32 && F[(int)e - base] != 1) E2[idx] = E2[(int)e - base];
+        // ---- P3: same for super tiles of 32 tiles.  One warp per super tile walks its tiles from the last to the
+        //      first; a state whose tile exit lands on a later tile of the same super tile inherits that state's
+        //      (already final) super-tile exit, so every state is touched once.
+        for (int sp = warp; sp < nsuper; sp += nwarps) {
+            const int superEnd = base + (sp + 1) * 1024;
+            int tLast = sp * 32 + 31; if (tLast >= ntiles) tLast = ntiles - 1;
+            for (int t = tLast; t >= sp * 32; --t) {
+                const unsigned e = E1[t * 32 + lane];
+                unsigned fin = e;
+                if (e >= 2 && (int)e < superEnd && (int)e < E && (int)e >= base + (t + 1) * 32 && F[(int)e - base] != 1) fin = E2[(int)e - base];
+                E2[t * 32 + lane] = (uint16_t)fin;
+                __syncwarp();
             }
-            __syncthreads();
         }
+        __syncthreads();
 
         // ---- P4: follow the orbit super tile by super tile (warp 0; lanes cooperate on long matches) ----
         if (warp == 0) {
@@ -558,16 +567,21 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                     b = B0 + fwd; npre = 1;
                 }
             }
+            bool newSeg = true;
             for (;;) {
                 finalB = b;
                 if (b >= E) break;
-                if (lane == 0) seg[nseg] = (uint16_t)b;
-                ++nseg;
+                if (newSeg) { if (lane == 0) seg[nseg] = (uint16_t)b; ++nseg; newSeg = false; }
                 const int r = b - base;
                 const unsigned e = E2[r];
-                const int superEnd = base + ((r >> 10) + 1) * 1024;
-                if ((int)e >= superEnd || (int)e >= E) { b = (int)e; continue; }
                 if (e == 0) { finalB = -1; break; }       // ends inside a tile: the tile reports the last state
+                if ((int)e >= E) { b = (int)e; continue; }
+                const bool crosses = (((int)e - base) >> 10) != (r >> 10);
+                if (crosses || F[(int)e - base] != 1) {   // plain hop (at least out of b's tile, at best out of its super tile)
+                    newSeg = crosses;
+                    b = (int)e;
+                    continue;
+                }
                 // long match at state x = e: exact lengths
                 const int x = (int)e;
                 const int j = probe_next(info, okbits, nzw, ntiles, base, x);
@@ -583,6 +597,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 const int ms = j - lb;
                 if (lane == 0) lazyTok[(x - base) >> 5] = (uint32_t)ms | ((uint32_t)m << 16);
                 b = ms + m;
+                newSeg = true;
             }
             if (lane == 0) { ps.npre = npre; ps.nseg = nseg; ps.finalB = finalB; }
         }
