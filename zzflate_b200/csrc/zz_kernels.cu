@@ -19,6 +19,7 @@
 // Everything is integer work; nothing here is a dense contraction, so tensor cores are not used.
 #include "zz_kernels.cuh"
 #include <cstdio>
+#include <cstring>
 
 namespace zz {
 
@@ -267,6 +268,12 @@ __device__ __forceinline__ unsigned long long ld8(const uint8_t* win, int o)
 //                 the orbit into tokens in parallel.
 // Matches of 32 bytes or more are resolved exactly (up to 258) only where the orbit actually meets them.
 // ------------------------------------------------------------------------------------------------
+#ifdef ZZ_PHASE_TIMING
+__device__ unsigned long long g_phaseCycles[16];
+#define PHASE_MARK(i) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_phaseCycles[i], (unsigned long long)(now_ - tPhase)); tPhase = now_; } } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
 constexpr int kParseThreads = 1024;
 constexpr int kBatchCap = kBatch + 128;            // entries of the per-batch arrays (tile-aligned base + slack)
 constexpr int kTilesCap = kBatchCap / 32;
@@ -440,9 +447,13 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
     uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
     uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
 
+#ifdef ZZ_PHASE_TIMING
+    long long tPhase = clock64();
+#endif
     load_window(win, wb, chunk0, -g.pre, g.n, g.n + 48);
     if (tid == 0) { ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npatch = 0; ps.fixS = -1; ps.fixJ = 0x7fffffff; }
     __syncthreads();
+    PHASE_MARK(0);
 
     const int t0 = g.t0;
     // ---- batches of the reference's WriteBlock2Pass loop (encoder.cpp:225-234) ----
@@ -501,6 +512,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         }
         for (int t = tid; t < kTilesCap; t += kParseThreads) entry[t] = (uint16_t)kNone16;
         __syncthreads();
+        PHASE_MARK(1);
         // next non-empty bitmap word at or after w
         for (int w = tid; w <= ntiles; w += kParseThreads) {
             int k = w;
@@ -508,6 +520,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             nzw[w] = (uint16_t)(k < ntiles ? k : kNone16);
         }
         __syncthreads();
+        PHASE_MARK(2);
 
         // ---- P2: successor function F over states, and E1 = where the orbit of b leaves b's tile.
         //      Values: 0 = no further match in the batch; a state inside the tile = the orbit meets a long match
@@ -537,6 +550,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             E1[t * 32 + lane] = (uint16_t)e;
         }
         __syncthreads();
+        PHASE_MARK(3);
         // ---- P3: same for super tiles of 32 tiles.  One warp per super tile walks its tiles from the last to the
         //      first; a state whose tile exit lands on a later tile of the same super tile inherits that state's
         //      (already final) super-tile exit, so every state is touched once.
@@ -552,6 +566,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             }
         }
         __syncthreads();
+        PHASE_MARK(4);
 
         // ---- P4: follow the orbit super tile by super tile (warp 0; lanes cooperate on long matches) ----
         if (warp == 0) {
@@ -602,6 +617,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             if (lane == 0) { ps.npre = npre; ps.nseg = nseg; ps.finalB = finalB; }
         }
         __syncthreads();
+        PHASE_MARK(5);
         // ---- P4b: every segment marks the tiles it enters ----
         if (tid < ps.nseg) {
             int b = seg[tid];
@@ -615,6 +631,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             }
         }
         __syncthreads();
+        PHASE_MARK(6);
 
         // ---- P5: tiles expand their part of the orbit into tokens ----
         unsigned cnt = 0;
@@ -682,6 +699,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             ps.pos = newpos;
         }
         __syncthreads();
+        PHASE_MARK(7);
     }
     __syncthreads();
 
@@ -712,6 +730,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         job.hist[(size_t)slot * kHistStride + i] = s;
     }
     if (tid == 0) job.state[slot].ntok = ps.ntok;
+    PHASE_MARK(8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1324,6 +1343,18 @@ __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
 // ------------------------------------------------------------------------------------------------
 // host side: launch wrappers and checksum folds
 // ------------------------------------------------------------------------------------------------
+#ifdef ZZ_PHASE_TIMING
+void dump_phase_cycles()
+{
+    unsigned long long h[16];
+    cudaMemcpyFromSymbol(h, g_phaseCycles, sizeof h);
+    static const char* names[9] = { "window", "P1 info", "nzw", "P2 F+E1", "P3 E2", "P4 chase", "P4b mark", "P5 tokens", "hist" };
+    unsigned long long tot = 0; for (int i = 0; i < 9; ++i) tot += h[i];
+    for (int i = 0; i < 9; ++i) fprintf(stderr, "phase %-10s %6.2f%%  %llu\n", names[i], 100.0 * h[i] / (tot ? tot : 1), h[i]);
+    memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_phaseCycles, h, sizeof h);
+}
+#endif
+
 cudaError_t configure_kernels()
 {
     cudaError_t e;
@@ -1363,6 +1394,9 @@ int launch_candidates(const Job& job, cudaStream_t s)
 
 int launch_parse(const Job& job, cudaStream_t s)
 {
+#ifdef ZZ_PHASE_TIMING
+    cudaStreamSynchronize(s); dump_phase_cycles();
+#endif
     k_parse<<<job.nchunks, kParseThreads, kParseSmem, s>>>(job);
     return 1;
 }
