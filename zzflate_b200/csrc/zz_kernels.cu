@@ -1278,7 +1278,7 @@ __global__ void __launch_bounds__(256) k_gather(Job job)
 // ------------------------------------------------------------------------------------------------
 // K-CKSUM : per-chunk Adler-32 (start 0) and CRC-32
 // ------------------------------------------------------------------------------------------------
-__constant__ uint32_t c_crcTable[256];
+__constant__ uint32_t c_crcTable[4][256];   // slicing-by-4 tables of the reflected polynomial 0xEDB88320 (crc.cpp:5-22 is table 0)
 __constant__ uint32_t c_powL[257];      // x^(8*256*q) mod P, reflected (q <= 256: a full 64 KiB chunk)
 __constant__ uint32_t c_pow1[256];      // x^(8*r) mod P, reflected
 
@@ -1296,15 +1296,18 @@ __host__ __device__ inline uint32_t gf2_mulmod(uint32_t a, uint32_t b)
 constexpr int kCkThreads = 256;
 constexpr int kCkSlice = 256;
 
+// Each thread owns a 256-byte slice: Adler partial sums with dp4a (s1 = sum d, s2 = sum (len-i) d_i), raw CRC
+// with slicing-by-4, then the slice CRC is multiplied by x^(8 * bytes after the slice) and everything is
+// XOR-/sum-reduced.  The chunk's standard CRC adds the propagated 0xFFFFFFFF preset and the final inversion.
 __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
 {
-    __shared__ uint32_t tab[256];
+    __shared__ uint32_t tab[4][256];
     __shared__ unsigned long long redA[8], redB[8];
     __shared__ uint32_t redC[8];
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    tab[tid] = c_crcTable[tid];
+    for (int k = 0; k < 4; ++k) tab[k][tid] = c_crcTable[k][tid];
     __syncthreads();
     const uint8_t* p = job.src + g.off;
     const int lo = tid * kCkSlice;
@@ -1312,13 +1315,32 @@ __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
     unsigned long long s1 = 0, s2 = 0; uint32_t crc = 0;
     if (lo < hi) {
         const int len = hi - lo;
-        for (int i = 0; i < len; ++i) {
-            const unsigned v = p[lo + i];
-            s1 += v; s2 += (unsigned long long)(len - i) * v;
-            crc = (crc >> 8) ^ tab[(crc ^ v) & 0xFF];
+        unsigned a = 0, b = 0;                                       // slice-local: a = sum d, b = sum (len - i) d_i  (< 2^24)
+        int i = 0;
+        auto word = [&](unsigned w, int remaining) {                  // 4 bytes at offset i, `remaining` = len - i
+            // sum_{k<4} (remaining - k) d_k = remaining * sum d_k - (0 d0 + 1 d1 + 2 d2 + 3 d3)
+            const unsigned sum = __dp4a(w, 0x01010101u, 0u);
+            b += (unsigned)remaining * sum - __dp4a(w, 0x03020100u, 0u);
+            a += sum;
+            crc ^= w;
+            crc = tab[3][crc & 0xFF] ^ tab[2][(crc >> 8) & 0xFF] ^ tab[1][(crc >> 16) & 0xFF] ^ tab[0][crc >> 24];
+        };
+        const uint8_t* q = p + lo;
+        if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+            for (; i + 16 <= len; i += 16) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(q + i));
+                word(v.x, len - i); word(v.y, len - i - 4); word(v.z, len - i - 8); word(v.w, len - i - 12);
+            }
+        } else if ((reinterpret_cast<uintptr_t>(q) & 3) == 0) {
+            for (; i + 4 <= len; i += 4) word(__ldg(reinterpret_cast<const unsigned*>(q + i)), len - i);
+        }
+        for (; i < len; ++i) {
+            const unsigned v = q[i];
+            a += v; b += (unsigned)(len - i) * v;
+            crc = (crc >> 8) ^ tab[0][(crc ^ v) & 0xFF];
         }
         const int after = g.n - hi;
-        s2 += (unsigned long long)after * s1;                        // b = sum (n - i) * d[i]
+        s1 = a; s2 = (unsigned long long)b + (unsigned long long)after * a;      // b_chunk = sum (n - i) d[i]
         crc = gf2_mulmod(gf2_mulmod(crc, c_powL[after >> 8]), c_pow1[after & 255]);
     }
     for (int o = 16; o; o >>= 1) {
@@ -1360,12 +1382,15 @@ cudaError_t configure_kernels()
     cudaError_t e;
     e = cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kParseSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem); if (e) return e;
-    uint32_t tab[256], powL[257], pow1[256];
+    static uint32_t tab[4][256];
+    uint32_t powL[257], pow1[256];
     for (uint32_t i = 0; i < 256; ++i) {
         uint32_t c = i;
         for (int j = 0; j < 8; ++j) c = (c >> 1) ^ ((c & 1) * 0xEDB88320u);
-        tab[i] = c;
+        tab[0][i] = c;
     }
+    for (int k = 1; k < 4; ++k)
+        for (uint32_t i = 0; i < 256; ++i) tab[k][i] = (tab[k - 1][i] >> 8) ^ tab[0][tab[k - 1][i] & 0xFF];
     const uint32_t x8 = 0x00800000u;                                  // x^8
     uint32_t xL = 0x80000000u;                                        // x^(8*256) by repeated multiplication
     for (int i = 0; i < 256; ++i) xL = gf2_mulmod(xL, x8);
