@@ -37,6 +37,9 @@ struct Ctx {
     uint32_t* hCk = nullptr; size_t hCkCap = 0;
     uint8_t* dIn = nullptr; size_t dInCap = 0;
     uint8_t* dOut = nullptr; size_t dOutCap = 0;
+    cudaStream_t copyIn = nullptr, copyOut = nullptr;     // host-buffer path: H2D / D2H overlap the kernels
+    std::vector<cudaEvent_t> pieceEv;
+    uint64_t* hPiece = nullptr; size_t hPieceCap = 0;     // pinned: running totals after each piece
     std::vector<cudaEvent_t> stageEv;       // pool of events bracketing each stage launch
     std::vector<int> stageOf;               // stage id of the interval that ENDS at event i (-1: start marker)
     size_t stageUsed = 0;
@@ -148,8 +151,7 @@ void collectStages(Ctx& c, zzgpu_stats* stats)
 
 // Runs the device pipeline over all chunks of the call.  d_src points at stream position 0 of the call in
 // device memory (history bytes before it), d_dst receives the stream.
-int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap,
-                int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t& launches)
+int preparePipeline(Ctx& c, size_t n, uint32_t chunk, int wantCk)
 {
     const uint64_t nchunks = (n + chunk - 1) / chunk;
     const uint32_t slots = (uint32_t)std::min<uint64_t>(nchunks, kMaxSlots);
@@ -157,10 +159,18 @@ int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int fina
     if (wantCk) { rc = ensureBuf(c.ck, c.ckCap, 2 * nchunks); if (rc) return rc; }
     CK(cudaMemsetAsync(c.total, 0, 4 * sizeof(uint64_t), c.stream));
     c.stageUsed = 0;
-    for (uint64_t first = 0; first < nchunks; first += slots) {
+    return ZZGPU_OK;
+}
+
+// Kernel pipeline over chunks [firstChunk, lastChunk) of the call (geometry is always that of the whole call).
+int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap,
+              int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t firstChunk, uint64_t lastChunk, uint64_t& launches)
+{
+    int rc;
+    for (uint64_t first = firstChunk; first < lastChunk; first += c.slots) {
         Job job{};
         job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
-        job.first_chunk = first; job.nchunks = (uint32_t)std::min<uint64_t>(slots, nchunks - first);
+        job.first_chunk = first; job.nchunks = (uint32_t)std::min<uint64_t>(c.slots, lastChunk - first);
         job.final_stream = final; job.level = level; job.want_checksums = wantCk;
         job.cand = c.cand; job.tokA = c.tokA; job.tokD = c.tokD; job.hist = c.hist; job.codes = c.codes; job.state = c.state;
         job.dst = d_dst; job.cap = cap; job.total = c.total; job.ck = c.ck;
@@ -180,6 +190,84 @@ int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int fina
         if (wantCk) { launches += launch_checksums(job, c.stream); rc = markStage(c, ZZGPU_STAGE_CKSUM); if (rc) return rc; }
     }
     CK(cudaGetLastError());
+    return ZZGPU_OK;
+}
+
+// Runs the device pipeline over all chunks of the call.  d_src points at stream position 0 of the call in
+// device memory (history bytes before it), d_dst receives the stream.
+int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap,
+                int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t& launches)
+{
+    int rc = preparePipeline(c, n, chunk, wantCk); if (rc) return rc;
+    return runChunks(c, d_src, n, history, final, d_dst, cap, level, chunk, dict, wantCk, 0, (n + chunk - 1) / chunk, launches);
+}
+
+// Piece schedule of the host-buffer path: small pieces first (the kernels start after one short H2D), large in
+// the middle (full occupancy, one dictionary-priming pass per long run of chunks), small at the end (short drain).
+std::vector<uint64_t> pieceSchedule(uint64_t nchunks)
+{
+    std::vector<uint64_t> ends;
+    const uint64_t big = 4096;
+    uint64_t pos = 0, size = 512;
+    while (nchunks - pos > 2 * big) {
+        pos += size; ends.push_back(pos);
+        if (size < big) size *= 2;
+    }
+    uint64_t rem = nchunks - pos;                       // <= 2 * big: taper
+    while (rem > 1024) { const uint64_t take = rem / 2; pos += take; ends.push_back(pos); rem -= take; }
+    if (rem) { pos += rem; ends.push_back(pos); }
+    return ends;
+}
+
+// Host buffers on both sides: H2D copies, kernels and D2H copies of successive pieces overlap on three streams.
+int runHostPipelined(Ctx& c, const uint8_t* src, size_t n, size_t hist, int final, uint8_t* dst, size_t cap,
+                     int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t& launches, size_t& total, size_t& d2h)
+{
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    int rc = ensureBuf(c.dIn, c.dInCap, hist + n + 64); if (rc) return rc;
+    const size_t d_cap = std::min(cap, zzgpu_bound(n, level, chunk));
+    rc = ensureBuf(c.dOut, c.dOutCap, d_cap + 64); if (rc) return rc;
+    if (!c.copyIn) { CK(cudaStreamCreateWithFlags(&c.copyIn, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c.copyOut, cudaStreamNonBlocking)); }
+    const std::vector<uint64_t> ends = pieceSchedule(nchunks);
+    const size_t np = ends.size();
+    while (c.pieceEv.size() < 2 * np) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.pieceEv.push_back(e); }
+    rc = ensureBuf(c.hPiece, c.hPieceCap, 4 * np, true); if (rc) return rc;
+    rc = preparePipeline(c, n, chunk, wantCk); if (rc) return rc;
+    cudaEvent_t start = c.pieceEv[0];                   // copies must not start before earlier work on the main stream is done
+    CK(cudaEventRecord(c.ev[0], c.stream));
+    CK(cudaStreamWaitEvent(c.copyIn, c.ev[0], 0));
+    CK(cudaStreamWaitEvent(c.copyOut, c.ev[0], 0));
+    (void)start;
+    const uint8_t* d_src = c.dIn + hist;
+    uint64_t firstChunk = 0;
+    for (size_t p = 0; p < np; ++p) {
+        const size_t lo = (size_t)(firstChunk * chunk), hi = (size_t)std::min<uint64_t>(n, ends[p] * chunk);
+        const size_t from = p == 0 ? 0 : hist + lo, to = hist + hi;          // piece 0 also carries the history
+        CK(cudaMemcpyAsync(c.dIn + from, src - hist + from, to - from, cudaMemcpyHostToDevice, c.copyIn));
+        CK(cudaEventRecord(c.pieceEv[2 * p], c.copyIn));
+        CK(cudaStreamWaitEvent(c.stream, c.pieceEv[2 * p], 0));
+        rc = runChunks(c, d_src, n, hist, final, c.dOut, d_cap, level, chunk, dict, wantCk, firstChunk, ends[p], launches);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(c.hPiece + 4 * p, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaEventRecord(c.pieceEv[2 * p + 1], c.stream));
+        firstChunk = ends[p];
+    }
+    CK(cudaEventRecord(c.ev[2], c.stream));
+    size_t done = 0;
+    for (size_t p = 0; p < np; ++p) {
+        CK(cudaEventSynchronize(c.pieceEv[2 * p + 1]));
+        const uint64_t upto = c.hPiece[4 * p], flags = c.hPiece[4 * p + 1];
+        if (flags & 1) return fail(ZZGPU_E_CAPACITY, "destination too small");
+        if (flags & ~1ull) return fail(ZZGPU_E_CUDA, "internal consistency check failed (emit size mismatch)");
+        if (upto > cap) return fail(ZZGPU_E_CAPACITY, "destination too small");
+        if (upto > done) CK(cudaMemcpyAsync(dst + done, c.dOut + done, upto - done, cudaMemcpyDeviceToHost, c.copyOut));
+        done = (size_t)upto;
+    }
+    CK(cudaEventRecord(c.ev[3], c.copyOut));
+    CK(cudaStreamWaitEvent(c.stream, c.ev[3], 0));
+    CK(cudaStreamSynchronize(c.copyOut));
+    for (int i = 0; i < 4; ++i) c.hTotal[i] = c.hPiece[4 * (np - 1) + i];
+    total = done; d2h = done;
     return ZZGPU_OK;
 }
 
@@ -228,6 +316,12 @@ void zzgpu_shutdown(void)
         cudaStreamSynchronize(c.stream);
         freeScratch(c);
         cudaFree(c.total); cudaFreeHost(c.hTotal); cudaFree(c.ck); cudaFreeHost(c.hCk); cudaFree(c.dIn); cudaFree(c.dOut);
+        cudaFreeHost(c.hPiece); c.hPiece = nullptr; c.hPieceCap = 0;
+        for (auto& e : c.pieceEv) cudaEventDestroy(e);
+        c.pieceEv.clear();
+        for (auto& e : c.stageEv) cudaEventDestroy(e);
+        c.stageEv.clear(); c.stageOf.clear(); c.stageUsed = 0;
+        if (c.copyIn) { cudaStreamDestroy(c.copyIn); cudaStreamDestroy(c.copyOut); c.copyIn = nullptr; c.copyOut = nullptr; }
         for (auto& e : c.ev) cudaEventDestroy(e);
         cudaStreamDestroy(c.stream);
         c.total = nullptr; c.hTotal = nullptr; c.ck = nullptr; c.hCk = nullptr; c.dIn = nullptr; c.dOut = nullptr;
@@ -294,37 +388,46 @@ int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int final, in
 
     uint64_t launches = 0;
     const size_t hist = std::min<size_t>(history, (size_t)dict + kPreExtra);    // bytes the kernels may look at
-    CK(cudaEventRecord(c.ev[0], c.stream));
-    const uint8_t* d_src = src;
     size_t h2d = 0, d2h = 0;
-    if (src_mem == ZZGPU_MEM_HOST) {
-        rc = ensureBuf(c.dIn, c.dInCap, hist + n + 64); if (rc) return rc;
-        CK(cudaMemcpyAsync(c.dIn, src - hist, hist + n, cudaMemcpyHostToDevice, c.stream));
-        d_src = c.dIn + hist;
-        h2d = hist + n;
+    uint64_t total = 0;
+    if (src_mem == ZZGPU_MEM_HOST && dst_mem == ZZGPU_MEM_HOST && n >= ((size_t)32 << 20)) {
+        size_t tot = 0;
+        rc = runHostPipelined(c, src, n, hist, final, dst, cap, level, chunk, dict, want_checksums, launches, tot, d2h);
+        if (rc) { cudaStreamSynchronize(c.copyIn); cudaStreamSynchronize(c.stream); cudaStreamSynchronize(c.copyOut); return rc; }
+        total = tot; h2d = hist + n;
+    } else {
+        CK(cudaEventRecord(c.ev[0], c.stream));
+        const uint8_t* d_src = src;
+        if (src_mem == ZZGPU_MEM_HOST) {
+            rc = ensureBuf(c.dIn, c.dInCap, hist + n + 64); if (rc) return rc;
+            CK(cudaMemcpyAsync(c.dIn, src - hist, hist + n, cudaMemcpyHostToDevice, c.stream));
+            d_src = c.dIn + hist;
+            h2d = hist + n;
+        }
+        uint8_t* d_dst = dst;
+        size_t d_cap = cap;
+        if (dst_mem == ZZGPU_MEM_HOST) {
+            d_cap = std::min(cap, zzgpu_bound(n, level, chunk));
+            rc = ensureBuf(c.dOut, c.dOutCap, d_cap + 64); if (rc) return rc;
+            d_dst = c.dOut;
+        }
+        CK(cudaEventRecord(c.ev[1], c.stream));
+        rc = runPipeline(c, d_src, n, hist, final, d_dst, d_cap, level, chunk, dict, want_checksums, launches);
+        if (rc) return rc;
+        CK(cudaEventRecord(c.ev[2], c.stream));
+        CK(cudaMemcpyAsync(c.hTotal, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        total = c.hTotal[0];
+        const uint64_t flags = c.hTotal[1];
+        if (flags & 1) return fail(ZZGPU_E_CAPACITY, "destination too small");
+        if (flags & ~1ull) return fail(ZZGPU_E_CUDA, "internal consistency check failed (emit size mismatch)");
+        if (total > cap) return fail(ZZGPU_E_CAPACITY, "destination too small");
+        if (dst_mem == ZZGPU_MEM_HOST) {
+            CK(cudaMemcpyAsync(dst, c.dOut, total, cudaMemcpyDeviceToHost, c.stream));
+            d2h = total;
+        }
+        CK(cudaEventRecord(c.ev[3], c.stream));
     }
-    uint8_t* d_dst = dst;
-    size_t d_cap = cap;
-    if (dst_mem == ZZGPU_MEM_HOST) {
-        d_cap = std::min(cap, zzgpu_bound(n, level, chunk));
-        rc = ensureBuf(c.dOut, c.dOutCap, d_cap + 64); if (rc) return rc;
-        d_dst = c.dOut;
-    }
-    CK(cudaEventRecord(c.ev[1], c.stream));
-    rc = runPipeline(c, d_src, n, hist, final, d_dst, d_cap, level, chunk, dict, want_checksums, launches);
-    if (rc) return rc;
-    CK(cudaEventRecord(c.ev[2], c.stream));
-    CK(cudaMemcpyAsync(c.hTotal, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
-    CK(cudaStreamSynchronize(c.stream));
-    const uint64_t total = c.hTotal[0], flags = c.hTotal[1];
-    if (flags & 1) return fail(ZZGPU_E_CAPACITY, "destination too small");
-    if (flags & ~1ull) return fail(ZZGPU_E_CUDA, "internal consistency check failed (emit size mismatch)");
-    if (total > cap) return fail(ZZGPU_E_CAPACITY, "destination too small");
-    if (dst_mem == ZZGPU_MEM_HOST) {
-        CK(cudaMemcpyAsync(dst, c.dOut, total, cudaMemcpyDeviceToHost, c.stream));
-        d2h = total;
-    }
-    CK(cudaEventRecord(c.ev[3], c.stream));
     rc = foldChecksums(c, n, chunk, want_checksums, adler0, crc); if (rc) return rc;
     CK(cudaStreamSynchronize(c.stream));
     *out_len = (size_t)total;
@@ -333,9 +436,12 @@ int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int final, in
         stats->matches = c.hTotal[2];
         stats->stored_chunks = c.hTotal[3];
         stats->kernel_launches = launches;
-        cudaEventElapsedTime(&stats->device_ms, c.ev[1], c.ev[2]);
-        cudaEventElapsedTime(&stats->total_ms, c.ev[0], c.ev[3]);
         collectStages(c, stats);
+        cudaEventElapsedTime(&stats->total_ms, c.ev[0], c.ev[3]);
+        if (cudaEventElapsedTime(&stats->device_ms, c.ev[1], c.ev[2]) != cudaSuccess || h2d + d2h > 0) {
+            stats->device_ms = 0;                    // pipelined path: kernels interleave with copies; sum the stages
+            for (int i = 0; i < 8; ++i) stats->device_ms += stats->stage_ms[i];
+        }
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
     }
     return ZZGPU_OK;
