@@ -139,50 +139,53 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
     unsigned lastSlot = firstSlot + (unsigned)run; if (lastSlot > job.nchunks) lastSlot = job.nchunks;
     const Geom g0 = chunk_geom(job, firstSlot);
     const Geom gl = chunk_geom(job, lastSlot - 1);
-    const long long S = job.chunk;
     const uint8_t* base0 = job.src + g0.off;                                  // position q = 0 of the run
-    const long long qEnd = (long long)(lastSlot - 1 - firstSlot) * S + gl.n;   // positions [-dict, qEnd)
+    // positions q in [-dict, qEnd) relative to the run start; runs longer than one chunk only with 64 KiB chunks,
+    // where the chunk-relative position is q & 0xFFFF and the candidate rows of the run are contiguous
+    const int qEnd = (int)(lastSlot - 1 - firstSlot) * (int)job.chunk + gl.n;
+    const int qStart = -g0.dict;
+    const unsigned startMask = run > 1 ? 0xFFFFu : 0xFFFFFFFFu;               // q & startMask == 0 <=> first byte of a chunk
+    uint16_t* candOut = job.cand + (size_t)firstSlot * job.chunk;
     const uint8_t* validLo = job.src - job.history;
     const uint8_t* validHi = job.src + job.n;
+    const unsigned ltMask = (1u << lane) - 1u;
 
-    long long q0 = -(long long)g0.dict;
-    unsigned sweepAt = 0;                    // steps until the next sweep; 0 => sweep now (also the initial fill)
+    int sweepAt = 0;                         // steps until the next sweep; 0 => sweep now (also the initial fill)
     int buf = 0;
-    stage_tile(stage[0], base0 + q0, kCandTile + 8, validLo, validHi, lane);
-    for (; q0 < qEnd; q0 += kCandTile) {
+    stage_tile(stage[0], base0 + qStart, kCandTile + 8, validLo, validHi, lane);
+    for (int q0 = qStart; q0 < qEnd; q0 += kCandTile) {
         cp_async_wait_all();
         __syncwarp();
         if (q0 + kCandTile < qEnd) stage_tile(stage[buf ^ 1], base0 + q0 + kCandTile, kCandTile + 8, validLo, validHi, lane);
         const unsigned* sw = reinterpret_cast<const unsigned*>(stage[buf]);
         const int phase = (int)(reinterpret_cast<uintptr_t>(base0 + q0) & 3);
-        long long tileEnd = q0 + kCandTile; if (tileEnd > qEnd) tileEnd = qEnd;
-#pragma unroll 4
-        for (long long qs = q0; qs < tileEnd; qs += 32) {
+        const int tileEnd = min(q0 + kCandTile, qEnd);
+#pragma unroll 2
+        for (int qs = q0; qs < tileEnd; qs += 32) {
             if (sweepAt == 0) {
                 // retire entries 32768 or more behind position qs (and stale markers); marker = qs - 32768
-                const unsigned now = (unsigned)(qs & 0xFFFF);
+                const unsigned now = (unsigned)qs & 0xFFFFu;
                 const unsigned marker = (now - 32768u) & 0xFFFFu;
                 for (int i = lane; i < kHashSize; i += 32) {
                     const unsigned age = (now - table[i]) & 0xFFFFu;
-                    if (age == 0 || age >= 32768u || qs == -(long long)g0.dict) table[i] = (uint16_t)marker;
+                    if (age == 0 || age >= 32768u || qs == qStart) table[i] = (uint16_t)marker;
                 }
                 __syncwarp();
                 sweepAt = 1024;
             }
             --sweepAt;
-            const long long q = qs + lane;
-            const int o = phase + (int)(q - q0);
+            const int q = qs + lane;
+            const int o = phase + (q - q0);
             const unsigned v = __funnelshift_r(sw[o >> 2], sw[(o >> 2) + 1], (o & 3) * 8) & 0xFFFFFFu;
             const unsigned h = hash3(v);
-            // chunk of the run and chunk-relative position (runs longer than one chunk only with 64 KiB chunks)
-            const long long k = (run > 1 && q >= 0) ? (q >> 16) : 0;
-            const int j = (int)(q - k * S);
             const bool inRange = q < qEnd;
-            const bool act = inRange && (j != 0 || q < 0);
+            // position 0 of a chunk is neither probed nor inserted (encoder.cpp:384); positions before the run
+            // only prime the table (AddHashEntries, encoder.cpp:474)
+            const bool act = inRange && (q < 0 || ((unsigned)q & startMask) != 0);
             // Same-hash positions inside one step are found without MATCH.ANY (slow when all 32 keys differ, the
             // common case): everybody writes, whoever does not read its own value back shares its hash with
             // another lane; only those groups are then resolved with ballots.
-            const unsigned myv = (unsigned)(q & 0xFFFF);
+            const unsigned myv = (unsigned)q & 0xFFFFu;
             const unsigned old = act ? table[h] : 0u;
             __syncwarp();
             if (act) table[h] = (uint16_t)myv;
@@ -194,14 +197,14 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
             while (pending) {
                 const unsigned hl = __shfl_sync(0xffffffffu, h, __ffs(pending) - 1);
                 const unsigned mem = __ballot_sync(0xffffffffu, act && h == hl);
-                if (act && h == hl) { lower = mem & ((1u << lane) - 1u); fixTable = (mem >> lane) == 1u; }
+                if (act && h == hl) { lower = mem & ltMask; fixTable = (mem >> lane) == 1u; }
                 pending &= ~mem;
             }
             if (fixTable) table[h] = (uint16_t)myv;          // the highest position of a group owns the slot
             __syncwarp();
             if (inRange && q >= 0) {
-                const unsigned d = lower ? (unsigned)(lane - (31 - __clz(lower))) : (((unsigned)(q & 0xFFFF) - old) & 0xFFFFu);
-                job.cand[(size_t)(firstSlot + (unsigned)k) * job.chunk + j] = (uint16_t)((act && d < (unsigned)kMaxDistance) ? d : 0);
+                const unsigned d = lower ? (unsigned)(lane - (31 - __clz(lower))) : ((myv - old) & 0xFFFFu);
+                candOut[q] = (uint16_t)((act && d < (unsigned)kMaxDistance) ? d : 0);
             }
         }
         buf ^= 1;
