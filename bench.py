@@ -213,7 +213,6 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
-
     # ---- end to end through the public API on pinned host buffers
     e2e_ms, e2e_out = None, 0
     if not args.no_e2e:
@@ -253,7 +252,7 @@ def main():
     names = _lib.STAGES
     dom = max(range(8), key=lambda i: stage_ms[i])
     dom_avg_ms = stage_ms[dom] / max(stage_n[dom], 1)
-    chunks_per_launch = min(4096, (nbytes + CHUNK - 1) // CHUNK)
+    chunks_per_launch = ((nbytes + CHUNK - 1) // CHUNK) / max(stage_n[dom] / args.steps, 1)
     alg_bytes = chunks_per_launch * CHUNK * (1.0 + ratio)            # 1 read + r written per input byte
     achieved = alg_bytes / (dom_avg_ms * 1e-3) / 1e9
     traffic = None
@@ -268,6 +267,7 @@ def main():
             "dtype": "u8", "data": "synthetic", "config": config, "ratio": round(ratio, 5),
             "wall_ms_per_step": round(wall_ms / args.steps, 3),
             "stage_ms_per_step": {names[i]: round(stage_ms[i] / args.steps, 3) for i in range(8) if stage_n[i]},
+
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(dom_avg_ms, 4),

@@ -38,7 +38,7 @@ STAGES = ["cand", "parse", "huff", "offs", "emit", "cksum", "fixed", "gather"]
 SYMBOLS = [
     "zzgpu_init", "zzgpu_shutdown", "zzgpu_device_count", "zzgpu_strerror", "zzgpu_last_error", "zzgpu_bound",
     "zzgpu_deflate", "zzgpu_deflate_ex", "zzgpu_checksums", "zzgpu_adler32_combine", "zzgpu_crc32_combine",
-    "zzgpu_debug_chunk",
+    "zzgpu_debug_chunk", "zzgpu_set_option",
 ]
 
 _lib = None
@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     lib.zzgpu_adler32_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_size_t]
     lib.zzgpu_crc32_combine.restype = C.c_uint32
     lib.zzgpu_crc32_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+    lib.zzgpu_set_option.restype = C.c_int; lib.zzgpu_set_option.argtypes = [C.c_char_p, C.c_int]
     lib.zzgpu_debug_chunk.restype = C.c_int
     lib.zzgpu_debug_chunk.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64,
                                       C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32),

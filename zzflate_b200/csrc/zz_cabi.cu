@@ -40,6 +40,9 @@ struct Ctx {
     cudaStream_t copyIn = nullptr, copyOut = nullptr;     // host-buffer path: H2D / D2H overlap the kernels
     std::vector<cudaEvent_t> pieceEv;
     uint64_t* hPiece = nullptr; size_t hPieceCap = 0;     // pinned: running totals after each piece
+    cudaStream_t lane[3] = { nullptr, nullptr, nullptr };  // batches of one call rotate over these streams
+    cudaEvent_t laneEv[3] = { nullptr, nullptr, nullptr }; // last kernel of the lane's latest batch
+    std::vector<cudaEvent_t> offsEv;        // offsets scan of batch k (the next batch's scan continues its running total)
     std::vector<cudaEvent_t> stageEv;       // pool of events bracketing each stage launch
     std::vector<int> stageOf;               // stage id of the interval that ENDS at event i (-1: start marker)
     size_t stageUsed = 0;
@@ -126,14 +129,15 @@ bool validParams(int level, uint32_t chunk, uint32_t dict)
            dict <= ZZGPU_MAX_DICT;
 }
 
-int markStage(Ctx& c, int stage)
+int markStage(Ctx& c, int stage, cudaStream_t st = nullptr)
 {
+    if (!st) st = c.stream;
     if (c.stageUsed == c.stageEv.size()) {
         cudaEvent_t e; CK(cudaEventCreate(&e));
         c.stageEv.push_back(e); c.stageOf.push_back(-1);
     }
     c.stageOf[c.stageUsed] = stage;
-    CK(cudaEventRecord(c.stageEv[c.stageUsed], c.stream));
+    CK(cudaEventRecord(c.stageEv[c.stageUsed], st));
     c.stageUsed++;
     return ZZGPU_OK;
 }
@@ -149,8 +153,6 @@ void collectStages(Ctx& c, zzgpu_stats* stats)
     }
 }
 
-// Runs the device pipeline over all chunks of the call.  d_src points at stream position 0 of the call in
-// device memory (history bytes before it), d_dst receives the stream.
 int preparePipeline(Ctx& c, size_t n, uint32_t chunk, int wantCk)
 {
     const uint64_t nchunks = (n + chunk - 1) / chunk;
@@ -162,33 +164,62 @@ int preparePipeline(Ctx& c, size_t n, uint32_t chunk, int wantCk)
     return ZZGPU_OK;
 }
 
+constexpr uint32_t kLaneChunks = 4096;      // chunks per batch when batches overlap
+constexpr int kLanes = 3;
+int g_overlap = 0;                          // zzgpu_set_option("overlap", 0/1); measured slower: K-MATCH needs whole SMs, co-resident
+                                            // small kernels fragment them (40.4 vs 31.6 ms per GiB), so off by default
+
 // Kernel pipeline over chunks [firstChunk, lastChunk) of the call (geometry is always that of the whole call).
+// Large ranges are cut into batches of 4096 chunks that rotate over three streams with their own scratch slices:
+// K-MATCH fills every SM's shared memory, but the candidate, Huffman, emit and checksum kernels of neighbouring
+// batches overlap each other and every kernel's tail.  Only the offsets scan is ordered between batches (it
+// continues the running output size).
 int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap,
               int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t firstChunk, uint64_t lastChunk, uint64_t& launches)
 {
     int rc;
-    for (uint64_t first = firstChunk; first < lastChunk; first += c.slots) {
+    const uint64_t count = lastChunk - firstChunk;
+    const bool overlap = g_overlap && level != 1 && count >= 2 * kLaneChunks && c.slots >= kLanes * kLaneChunks;
+    const uint32_t batch = overlap ? kLaneChunks : c.slots;
+    if (overlap) {
+        for (int i = 0; i < kLanes; ++i)
+            if (!c.lane[i]) { CK(cudaStreamCreateWithFlags(&c.lane[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c.laneEv[i], cudaEventDisableTiming)); }
+        const size_t nb = (size_t)((count + batch - 1) / batch);
+        while (c.offsEv.size() < nb + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.offsEv.push_back(e); }
+        CK(cudaEventRecord(c.offsEv[0], c.stream));                 // everything queued so far on the main stream
+        for (int i = 0; i < kLanes; ++i) CK(cudaStreamWaitEvent(c.lane[i], c.offsEv[0], 0));
+    }
+    size_t k = 0;
+    for (uint64_t first = firstChunk; first < lastChunk; first += batch, ++k) {
+        const int ln = overlap ? (int)(k % kLanes) : 0;
+        cudaStream_t st = overlap ? c.lane[ln] : c.stream;
+        const size_t so = overlap ? (size_t)ln * kLaneChunks : 0;  // scratch slice of the lane
         Job job{};
         job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
-        job.first_chunk = first; job.nchunks = (uint32_t)std::min<uint64_t>(c.slots, lastChunk - first);
+        job.first_chunk = first; job.nchunks = (uint32_t)std::min<uint64_t>(batch, lastChunk - first);
         job.final_stream = final; job.level = level; job.want_checksums = wantCk;
-        job.cand = c.cand; job.tokA = c.tokA; job.tokD = c.tokD; job.hist = c.hist; job.codes = c.codes; job.state = c.state;
+        job.cand = c.cand + so * chunk; job.tokA = c.tokA + so * kMaxTokens; job.tokD = c.tokD + so * kMaxTokens;
+        job.hist = c.hist + so * kHistStride; job.codes = c.codes + so; job.state = c.state + so;
         job.dst = d_dst; job.cap = cap; job.total = c.total; job.ck = c.ck;
-        rc = markStage(c, -1); if (rc) return rc;
+        rc = markStage(c, -1, st); if (rc) return rc;
         if (level >= 2) {
-            launches += launch_candidates(job, c.stream); rc = markStage(c, ZZGPU_STAGE_CAND); if (rc) return rc;
-            launches += launch_parse(job, c.stream); rc = markStage(c, ZZGPU_STAGE_PARSE); if (rc) return rc;
+            launches += launch_candidates(job, st); rc = markStage(c, ZZGPU_STAGE_CAND, st); if (rc) return rc;
+            launches += launch_parse(job, st); rc = markStage(c, ZZGPU_STAGE_PARSE, st); if (rc) return rc;
         }
         if (level == 1) {
-            launches += launch_fixed(job, c.stream); rc = markStage(c, ZZGPU_STAGE_FIXED); if (rc) return rc;
+            launches += launch_fixed(job, st); rc = markStage(c, ZZGPU_STAGE_FIXED, st); if (rc) return rc;
         } else {
-            launches += launch_huffman(job, c.stream); rc = markStage(c, ZZGPU_STAGE_HUFF); if (rc) return rc;
+            launches += launch_huffman(job, st); rc = markStage(c, ZZGPU_STAGE_HUFF, st); if (rc) return rc;
         }
-        launches += launch_offsets(job, c.stream); rc = markStage(c, ZZGPU_STAGE_OFFS); if (rc) return rc;
-        if (level == 1) { launches += launch_gather(job, c.stream); rc = markStage(c, ZZGPU_STAGE_GATHER); if (rc) return rc; }
-        else { launches += launch_emit(job, c.stream); rc = markStage(c, ZZGPU_STAGE_EMIT); if (rc) return rc; }
-        if (wantCk) { launches += launch_checksums(job, c.stream); rc = markStage(c, ZZGPU_STAGE_CKSUM); if (rc) return rc; }
+        if (overlap && k > 0) CK(cudaStreamWaitEvent(st, c.offsEv[k], 0));
+        launches += launch_offsets(job, st); rc = markStage(c, ZZGPU_STAGE_OFFS, st); if (rc) return rc;
+        if (overlap) CK(cudaEventRecord(c.offsEv[k + 1], st));
+        if (level == 1) { launches += launch_gather(job, st); rc = markStage(c, ZZGPU_STAGE_GATHER, st); if (rc) return rc; }
+        else { launches += launch_emit(job, st); rc = markStage(c, ZZGPU_STAGE_EMIT, st); if (rc) return rc; }
+        if (wantCk) { launches += launch_checksums(job, st); rc = markStage(c, ZZGPU_STAGE_CKSUM, st); if (rc) return rc; }
+        if (overlap) CK(cudaEventRecord(c.laneEv[ln], st));
     }
+    if (overlap) for (int i = 0; i < kLanes && i < (int)k; ++i) CK(cudaStreamWaitEvent(c.stream, c.laneEv[i], 0));
     CK(cudaGetLastError());
     return ZZGPU_OK;
 }
@@ -492,6 +523,12 @@ int zzgpu_checksums(const uint8_t* src, size_t n, int src_mem, uint32_t adler_st
     if (adler) *adler = zz::adler32_combine(adler_start, a0, n);
     if (crc) *crc = zz::crc32_combine(crc_start, r, n);
     return ZZGPU_OK;
+}
+
+int zzgpu_set_option(const char* name, int value)
+{
+    if (name && !strcmp(name, "overlap")) { g_overlap = value ? 1 : 0; return ZZGPU_OK; }
+    return fail(ZZGPU_E_ARG, "unknown option");
 }
 
 uint32_t zzgpu_adler32_combine(uint32_t first, uint32_t second_start0, size_t len_second)
