@@ -284,7 +284,7 @@ constexpr int kSegCap = kTilesCap + 32;
 constexpr int kCapLen = 32;                        // cap of the parallel forward compare
 constexpr unsigned kNone16 = 0xFFFFu;
 constexpr int kParseSmem = kWinBytes + kBatchCap /*info*/ + 3 * kBatchCap * 2 /*F,E1,E2*/ +
-                           (kTilesCap + 4) * (4 + 4 + 2 + 2) + kSegCap * 2;
+                           (kTilesCap + 4) * (4 + 4 + 2 + 2 + 12) + kSegCap * 2;
 
 struct ParseShared {
     int pos;            // start of the next FirstPass batch
@@ -438,6 +438,10 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
     uint16_t* nzw = reinterpret_cast<uint16_t*>(lazyTok + (kTilesCap + 4));
     uint16_t* entry = nzw + (kTilesCap + 4);
     uint16_t* seg = entry + (kTilesCap + 4);
+    // bit per position: usable at distance >= 1 / 2 / 3 from the state (info >= 4 / 3 / 2); okbits is distance >= 4
+    unsigned* elig1 = reinterpret_cast<unsigned*>(seg + kSegCap);
+    unsigned* elig2 = elig1 + (kTilesCap + 4);
+    unsigned* elig3 = elig2 + (kTilesCap + 4);
     __shared__ ParseShared ps;
     __shared__ unsigned wsum[32];
 
@@ -484,16 +488,30 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         const int ntiles = (E - base + 31) >> 5;
         const int nsuper = (ntiles + 31) >> 5;
 
+        // ---- P0: candidate distances of the batch, staged through the (still unused) E2 array so that the
+        //      global loads are issued back to back instead of one per loop iteration of P1 ----
+        {
+            const int lim = ntiles * 32 + 64;
+            for (int idx0 = tid; idx0 < lim; idx0 += 4 * kParseThreads) {
+                unsigned short dv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = idx0 + u * kParseThreads, j = base + idx;
+                    dv[u] = (idx < lim && j >= B0 && j < E) ? __ldg(cand + j) : (unsigned short)0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int idx = idx0 + u * kParseThreads; if (idx < lim) E2[idx] = dv[u]; }
+            }
+            __syncthreads();
+            if (tid < npatch) { const int pj = ps.patchJ[tid]; if (pj >= B0 && pj < E) E2[pj - base] = (uint16_t)ps.patchD[tid]; }
+            __syncthreads();
+        }
         // ---- P1: per-position match info (parse independent) ----
         {
             const int lim = ntiles * 32 + 64;
-            int idx = tid;
-            int dNext = (idx < lim && base + idx >= B0 && base + idx < E) ? patched_cand(cand, &ps, npatch, base + idx) : 0;
-            for (; idx < lim; idx += kParseThreads) {
+            for (int idx = tid; idx < lim; idx += kParseThreads) {
                 const int j = base + idx;
-                const int d = dNext;
-                const int nidx = idx + kParseThreads;
-                dNext = (nidx < lim && base + nidx >= B0 && base + nidx < E) ? patched_cand(cand, &ps, npatch, base + nidx) : 0;
+                const int d = E2[idx];
                 unsigned inf = 0;
                 if (d) {
                     const int p = j - d;
@@ -509,8 +527,11 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                     if (ok) inf = (unsigned)fwd + 1u;
                 }
                 info[idx] = (uint8_t)inf;
-                const unsigned m = __ballot_sync(0xffffffffu, inf != 0);
-                if (lane == 0) okbits[idx >> 5] = m;
+                const unsigned m4 = __ballot_sync(0xffffffffu, inf != 0);
+                const unsigned m1 = __ballot_sync(0xffffffffu, inf >= 4);
+                const unsigned m2 = __ballot_sync(0xffffffffu, inf >= 3);
+                const unsigned m3 = __ballot_sync(0xffffffffu, inf >= 2);
+                if (lane == 0) { okbits[idx >> 5] = m4; elig1[idx >> 5] = m1; elig2[idx >> 5] = m2; elig3[idx >> 5] = m3; }
             }
         }
         for (int t = tid; t < kTilesCap; t += kParseThreads) entry[t] = (uint16_t)kNone16;
@@ -533,9 +554,25 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             const int tileStart = base + t * 32, tileEnd = tileStart + 32;
             const int b = tileStart + lane;
             unsigned f = 0;
-            if (b >= B0 && b < E) {
-                const int j = probe_next(info, okbits, nzw, ntiles, base, b);
-                if (j >= 0) {
+            {
+                // probe_next for the 32 states of the tile from the (warp-uniform) eligibility bitmaps
+                const unsigned long long a1 = elig1[t] | ((unsigned long long)elig1[t + 1] << 32);
+                const unsigned long long a2 = elig2[t] | ((unsigned long long)elig2[t + 1] << 32);
+                const unsigned long long a3 = elig3[t] | ((unsigned long long)elig3[t + 1] << 32);
+                const unsigned long long a4 = okbits[t] | ((unsigned long long)okbits[t + 1] << 32);
+                int j = -1;
+                if ((a1 >> (lane + 1)) & 1ull) j = b + 1;
+                else if ((a2 >> (lane + 2)) & 1ull) j = b + 2;
+                else if ((a3 >> (lane + 3)) & 1ull) j = b + 3;
+                else {
+                    const unsigned long long rest = a4 >> (lane + 4);
+                    if (rest) j = b + 4 + __ffsll((long long)rest) - 1;
+                    else if (t + 2 <= ntiles) {
+                        const unsigned w2 = nzw[t + 2];
+                        if (w2 != kNone16) j = base + (int)w2 * 32 + __ffs(okbits[w2]) - 1;
+                    }
+                }
+                if (b >= B0 && b < E && j >= 0) {
                     const unsigned fwd = (unsigned)info[j - base] - 1u;
                     f = fwd >= kCapLen ? 1u : (unsigned)j + fwd;
                 }
@@ -587,6 +624,9 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             }
             bool newSeg = true;
             for (;;) {
+#ifdef ZZ_PHASE_TIMING
+                if (lane == 0) atomicAdd(&g_phaseCycles[15], 1ull);
+#endif
                 finalB = b;
                 if (b >= E) break;
                 if (newSeg) { if (lane == 0) seg[nseg] = (uint16_t)b; ++nseg; newSeg = false; }
@@ -1376,6 +1416,7 @@ void dump_phase_cycles()
     static const char* names[9] = { "window", "P1 info", "nzw", "P2 F+E1", "P3 E2", "P4 chase", "P4b mark", "P5 tokens", "hist" };
     unsigned long long tot = 0; for (int i = 0; i < 9; ++i) tot += h[i];
     for (int i = 0; i < 9; ++i) fprintf(stderr, "phase %-10s %6.2f%%  %llu\n", names[i], 100.0 * h[i] / (tot ? tot : 1), h[i]);
+    fprintf(stderr, "orbit hops %llu\n", h[15]);
     memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_phaseCycles, h, sizeof h);
 }
 #endif
