@@ -1224,86 +1224,157 @@ __device__ __forceinline__ unsigned fixed_lit_code(unsigned v, int& len)     // 
     len = 8; return __brev(0xC0u + (v - 280)) >> 24;
 }
 
-struct SlotWriter {
-    unsigned long long* out; unsigned long long acc; int used; unsigned words;
-    __device__ __forceinline__ void put(unsigned bits, int n) {
-        acc |= (unsigned long long)bits << used; used += n;
-        if (used >= 64) { out[words++] = acc; used -= 64; acc = used ? ((unsigned long long)bits >> (n - used)) : 0ull; }
+// unaligned 8-byte little-endian load from global memory; bytes outside [lo, hi) read as zero
+__device__ __forceinline__ unsigned long long gload8(const uint8_t* p, const uint8_t* lo, const uint8_t* hi)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint8_t* al = reinterpret_cast<const uint8_t*>(a & ~(uintptr_t)7);
+    if (al >= lo && al + 16 <= hi) {
+        const unsigned long long x = __ldg(reinterpret_cast<const unsigned long long*>(al));
+        const unsigned long long y = __ldg(reinterpret_cast<const unsigned long long*>(al) + 1);
+        const int sh = (int)(a & 7) * 8;
+        return sh ? ((x >> sh) | (y << (64 - sh))) : x;
     }
-    __device__ __forceinline__ unsigned long long bitsWritten() const { return (unsigned long long)words * 64 + used; }
-    __device__ __forceinline__ void flush() { if (used) { out[words++] = acc; acc = 0; used = 0; } }
-};
+    unsigned long long v = 0;
+    for (int k = 0; k < 8; ++k) if (p + k >= lo && p + k < hi) v |= (unsigned long long)p[k] << (8 * k);
+    return v;
+}
 
+// One warp per chunk.  The level-1 walk inserts only the positions it visits, so candidates depend on the parse;
+// the warp speculates that the next 32 positions are all visited (true up to and including the first match of the
+// step), finds candidates like K-CAND (same-hash lower lane, else the table), verifies them, commits the lanes up
+// to the first match and jumps behind it.  Bits of a step are assembled in a small shared-memory window and
+// written to the chunk's scratch slot word by word.
 __global__ void __launch_bounds__(32) k_fixed(Job job)
 {
     __shared__ int table[kHashSize];
+    __shared__ unsigned obuf[16];
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
     const int lane = threadIdx.x;
+    const unsigned ltMask = (1u << lane) - 1u;
     for (int i = lane; i < kHashSize; i += 32) table[i] = kEmptySlot;
+    if (lane < 16) obuf[lane] = 0;
     __syncwarp();
     const uint8_t* base = job.src + g.off;
-    const long long limit = (long long)job.n - g.off;
-    auto byteAt = [&](int i) -> unsigned { return (i < limit) ? (unsigned)base[i] : 0u; };
+    const uint8_t* lo = job.src - job.history;
+    const uint8_t* hi = job.src + job.n;
     // level-1 priming convention: table[h(i+1)] = i for every dictionary position
     for (int i = -g.dict + lane; i < 0; i += 32) {
-        const unsigned v = byteAt(i + 1) | (byteAt(i + 2) << 8) | (byteAt(i + 3) << 16);
+        const unsigned v = (unsigned)(gload8(base + i, lo, hi) >> 8) & 0xFFFFFFu;
         atomicMax(&table[hash3(v)], i);
     }
     __syncwarp();
     ChunkState& st = job.state[slot];
-    if (lane != 0) return;
-
-    SlotWriter w; w.out = reinterpret_cast<unsigned long long*>(job.cand + (size_t)slot * job.chunk); w.acc = 0; w.used = 0; w.words = 0;
+    unsigned* out32 = reinterpret_cast<unsigned*>(job.cand + (size_t)slot * job.chunk);
     const int n = g.body;
+    unsigned long long bitpos = 0;           // bits of the chunk emitted so far (warp-uniform)
     unsigned matches = 0;
+
+    // appends `nbits` (<= 31, lane-private) at step-relative offset `off`; all lanes call it
+    auto stepFlush = [&](unsigned stepBits) {
+        __syncwarp();
+        const unsigned startBit = (unsigned)(bitpos & 31);
+        const unsigned full = (startBit + stepBits) >> 5;
+        const unsigned wbase = (unsigned)(bitpos >> 5);
+        const unsigned mine = lane < 16 ? obuf[lane] : 0u;
+        if ((unsigned)lane < full) out32[wbase + lane] = mine;
+        const unsigned carry = __shfl_sync(0xffffffffu, mine, full & 15);
+        __syncwarp();
+        if (lane < 16) obuf[lane] = lane == 0 ? carry : 0u;
+        bitpos += stepBits;
+        __syncwarp();
+    };
+    auto putAt = [&](unsigned off, unsigned bits, int nb) {          // off relative to bitpos, nb <= 31
+        const unsigned o = (unsigned)(bitpos & 31) + off;
+        const unsigned long long v = (unsigned long long)bits << (o & 31);
+        atomicOr(&obuf[o >> 5], (unsigned)v);
+        if ((o & 31) + nb > 32) atomicOr(&obuf[(o >> 5) + 1], (unsigned)(v >> 32));
+    };
+
     if (n > 0) {
-        w.put((g.final ? 1u : 0u) | (1u << 1), 3);                       // StartBlock(FixedHuffman, final)
-        for (int i = 0; i < n; ++i) {
-            const unsigned v = byteAt(i + 1) | (byteAt(i + 2) << 8) | (byteAt(i + 3) << 16);
-            const unsigned h = hash3(v);
-            const int d = i - table[h];
-            table[h] = i;
-            if ((unsigned)d <= (unsigned)kMaxDistance) {
-                int m = 0;
-                while (m < 8 && byteAt(i + m) == (unsigned)base[i - d + m]) ++m;
-                if (m == 8) {                                              // remain(a, b, 8, n - i)
-                    const int maxLen = min(n - i, kMaxMatch);
-                    while (m < maxLen && base[i + m] == base[i - d + m]) ++m;
-                    if (m > maxLen) m = maxLen;
-                } else if (m > n - i) {
-                    m = n - i;                                             // R2: clamp to the block end
-                }
-                if (m > 3) {
-                    int eb, ev, cl;
-                    const int ls = len_symbol(m, eb, ev);
-                    const unsigned lc = fixed_lit_code((unsigned)ls, cl);
-                    w.put(lc | ((unsigned)ev << cl), cl + eb);
-                    const int ds = dist_symbol(d, eb, ev);
-                    w.put((__brev((unsigned)ds) >> 27) | ((unsigned)ev << 5), 5 + eb);
-                    i += m - 1;
-                    ++matches;
-                    continue;
+        if (lane == 0) putAt(0, (g.final ? 1u : 0u) | (1u << 1), 3);     // StartBlock(FixedHuffman, final)
+        stepFlush(3);
+        int i0 = 0;
+        while (i0 < n) {
+            const int i = i0 + lane;
+            const bool valid = i < n;
+            const unsigned long long v8 = valid ? gload8(base + i, lo, hi) : 0ull;
+            const unsigned h = hash3((unsigned)(v8 >> 8) & 0xFFFFFFu);
+            const unsigned grp = __match_any_sync(0xffffffffu, valid ? h : (0x10000u + lane));
+            const unsigned lower = grp & ltMask;
+            const int old = valid ? table[h] : kEmptySlot;
+            const int cand = lower ? (i0 + 31 - __clz(lower)) : old;
+            const int d = i - cand;
+            int m = 0;
+            const int remaining = n - i;
+            if (valid && (unsigned)d <= (unsigned)kMaxDistance) {
+                const unsigned long long x = v8 ^ gload8(base + cand, lo, hi);
+                m = x ? ((__ffsll((long long)x) - 1) >> 3) : 8;
+                if (m > remaining) m = remaining;                     // R2 clamp (short) / remain() clamp (long)
+            }
+            const unsigned accMask = __ballot_sync(0xffffffffu, m > 3);
+            const int first = accMask ? __ffs(accMask) - 1 : 32;
+            // commit: lanes <= first were visited; the highest visited lane of a hash group owns the slot
+            const unsigned visited = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
+            __syncwarp();
+            if (valid && ((visited >> lane) & 1u) && (grp & ~ltMask & ~(1u << lane) & visited) == 0) table[h] = i;
+            // exact length of the winning match (remain(a, b, 8, n - i), encoder.cpp:352)
+            int mlen = 0, mdist = 0;
+            if (first < 32) {
+                mlen = __shfl_sync(0xffffffffu, m, first);
+                mdist = __shfl_sync(0xffffffffu, d, first);
+                if (mlen == 8) {
+                    const int fi = i0 + first;
+                    const int maxLen = min(n - fi, kMaxMatch);
+                    const unsigned long long xa = gload8(base + fi + 8 + lane * 8, lo, hi) ^ gload8(base + fi - mdist + 8 + lane * 8, lo, hi);
+                    const unsigned mm = __ballot_sync(0xffffffffu, xa != 0);
+                    int ext = 256;
+                    if (mm) { const int src = __ffs(mm) - 1; const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src); ext = src * 8 + ((__ffsll((long long)xs) - 1) >> 3); }
+                    mlen = 8 + ext; if (mlen > maxLen) mlen = maxLen;
                 }
             }
-            int cl; const unsigned c = fixed_lit_code(byteAt(i), cl);
-            w.put(c, cl);
+            // emission: literals of the lanes before the match, then the match
+            unsigned bits1 = 0, bits2 = 0; int n1 = 0, n2 = 0;
+            if (valid && lane < first) {
+                bits1 = fixed_lit_code((unsigned)(v8 & 0xFF), n1);
+            } else if (lane == first) {
+                int eb, ev, cl;
+                const int ls = len_symbol(mlen, eb, ev);
+                const unsigned lc = fixed_lit_code((unsigned)ls, cl);
+                bits1 = lc | ((unsigned)ev << cl); n1 = cl + eb;
+                const int ds = dist_symbol(mdist, eb, ev);
+                bits2 = (__brev((unsigned)ds) >> 27) | ((unsigned)ev << 5); n2 = 5 + eb;
+            }
+            unsigned incl = (unsigned)(n1 + n2);
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const unsigned off = incl - (unsigned)(n1 + n2);
+            const unsigned stepBits = __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            if (n1) putAt(off, bits1, n1);
+            if (n2) putAt(off + n1, bits2, n2);
+            stepFlush(stepBits);
+            if (first < 32) { i0 += first + mlen; ++matches; } else i0 += 32;
         }
-        int cl; const unsigned c = fixed_lit_code(256u, cl);
-        w.put(c, cl);
+        { int cl; const unsigned c = fixed_lit_code(256u, cl); if (lane == 0) putAt(0, c, cl); stepFlush((unsigned)cl); }
     }
-    unsigned long long q = w.bitsWritten();
+    const unsigned long long q = bitpos;
     unsigned bytes = (unsigned)((q + 7) >> 3);
     if (!g.final) {
-        w.put(0u, 3);                                                    // stored block header, not final
-        const int pad = (int)((8 - ((q + 3) & 7)) & 7);
-        if (pad) w.put(0u, pad);
-        w.put(1u | (0xFFFEu << 16), 32);                                 // LEN = 1, NLEN = 0xFFFE
-        w.put(byteAt(g.n - 1), 8);
-        bytes = (unsigned)(w.bitsWritten() >> 3);
+        const unsigned pad = (unsigned)((8 - ((q + 3) & 7)) & 7);
+        stepFlush(3 + pad);                                              // stored block header (not final) + padding: zeros
+        if (lane == 0) putAt(0, 0xFFFE0001u, 32);                        // LEN = 1, NLEN = 0xFFFE
+        stepFlush(32);
+        const unsigned lastByte = (unsigned)(gload8(base + g.n - 1, lo, hi) & 0xFF);
+        if (lane == 0) putAt(0, lastByte, 8);
+        stepFlush(8);
+        bytes = (unsigned)(bitpos >> 3);
     }
-    w.flush();
-    st.ntok = matches; st.block_type = 1; st.hdr_bits = 0; st.total_bits = q; st.out_bytes = bytes;
+    {   // final partial word
+        __syncwarp();
+        if (lane == 0 && (bitpos & 31)) out32[bitpos >> 5] = obuf[0];
+    }
+    if (lane == 0) { st.ntok = matches; st.block_type = 1; st.hdr_bits = 0; st.total_bits = q; st.out_bytes = bytes; }
 }
 
 __global__ void __launch_bounds__(256) k_gather(Job job)
