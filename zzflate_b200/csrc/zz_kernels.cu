@@ -779,40 +779,48 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
 // ------------------------------------------------------------------------------------------------
 // K-HUFF : one thread per chunk (tie-breaks follow the libstdc++ heap layout, so the tree build is serial)
 // ------------------------------------------------------------------------------------------------
-struct HRec { int f; int id; };
+// Heap entries are packed as frequency << 10 | id and live in shared memory, interleaved by lane
+// ([index][lane], 32 chunks per CTA) so that 32 independent heaps never conflict on a bank.  Comparisons look
+// at the frequency only: ties are decided by the heap layout alone, as in the reference (huffman.cpp:55-63).
+constexpr int kHuffLanes = 32;
+#define HF(v) ((v) >> 10)
+#define HS(i) ((i) * kHuffLanes)
 
-__device__ void heap_push_(HRec* h, int hole, int top, HRec v)
+__device__ __forceinline__ void heap_push_(unsigned* h, int hole, int top, unsigned v)
 {
     int parent = (hole - 1) / 2;
-    while (hole > top && h[parent].f > v.f) {
-        h[hole] = h[parent];
+    while (hole > top && HF(h[HS(parent)]) > HF(v)) {
+        h[HS(hole)] = h[HS(parent)];
         hole = parent;
         parent = (hole - 1) / 2;
     }
-    h[hole] = v;
+    h[HS(hole)] = v;
 }
 
-__device__ void heap_adjust(HRec* h, int hole, int len, HRec v)
+__device__ __forceinline__ void heap_adjust(unsigned* h, int hole, int len, unsigned v)
 {
     const int top = hole;
     int child = hole;
     while (child < (len - 1) / 2) {
         child = 2 * (child + 1);
-        if (h[child].f > h[child - 1].f) child--;
-        h[hole] = h[child];
+        const unsigned cr = h[HS(child)], cl = h[HS(child - 1)];
+        unsigned pick = cr;
+        if (HF(cr) > HF(cl)) { child--; pick = cl; }
+        h[HS(hole)] = pick;
         hole = child;
     }
     if ((len & 1) == 0 && child == (len - 2) / 2) {
         child = 2 * (child + 1);
-        h[hole] = h[child - 1];
+        h[HS(hole)] = h[HS(child - 1)];
         hole = child - 1;
     }
     heap_push_(h, hole, top, v);
 }
 
-// CalcLengths (huffman.cpp:122-154).  n <= 286.  Work arrays are caller-provided.
+// CalcLengths (huffman.cpp:122-154).  n <= 286.  heap points at this lane's shared-memory column (the hot, latency-
+// critical structure); the tree links and depths are thread-local (touched once per merge / once at the end).
 __device__ __noinline__ void calc_lengths(const int* freqs, int n, int maxLength, uint8_t* lens,
-                             HRec* heap, unsigned short* left, unsigned short* right, uint8_t* depth)
+                                          unsigned* heap, unsigned short* left, unsigned short* right, uint8_t* depth)
 {
     int total = 0;
     for (int i = 0; i < n; ++i) total += freqs[i];
@@ -821,33 +829,33 @@ __device__ __noinline__ void calc_lengths(const int* freqs, int n, int maxLength
         int rn = 0;
         for (int i = 0; i < n; ++i) {
             if (freqs[i] == 0) continue;
-            HRec r; r.f = freqs[i] > minFreq ? freqs[i] : minFreq; r.id = i;
-            heap[rn++] = r;
+            const unsigned f = (unsigned)(freqs[i] > minFreq ? freqs[i] : minFreq);
+            heap[HS(rn++)] = (f << 10) | (unsigned)i;
         }
         if (rn >= 2)
-            for (int parent = (rn - 2) / 2; ; --parent) { heap_adjust(heap, parent, rn, heap[parent]); if (parent == 0) break; }
+            for (int parent = (rn - 2) / 2; ; --parent) { heap_adjust(heap, parent, rn, heap[HS(parent)]); if (parent == 0) break; }
         int tn = n;                                              // tree index of the next internal node
         while (rn >= 2) {
-            HRec a, b;
-            if (rn > 1) { HRec v = heap[rn - 1]; heap[rn - 1] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
-            a = heap[--rn];
-            if (rn > 1) { HRec v = heap[rn - 1]; heap[rn - 1] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
-            b = heap[--rn];
-            left[tn - n] = (unsigned short)a.id; right[tn - n] = (unsigned short)b.id;
-            HRec r; r.f = a.f + b.f; r.id = tn;
-            heap[rn++] = r;
+            unsigned a, b;
+            if (rn > 1) { const unsigned v = heap[HS(rn - 1)]; heap[HS(rn - 1)] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
+            a = heap[HS(--rn)];
+            if (rn > 1) { const unsigned v = heap[HS(rn - 1)]; heap[HS(rn - 1)] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
+            b = heap[HS(--rn)];
+            left[tn - n] = (unsigned short)(a & 1023u); right[tn - n] = (unsigned short)(b & 1023u);
+            const unsigned r = ((HF(a) + HF(b)) << 10) | (unsigned)tn;
+            heap[HS(rn++)] = r;
             heap_push_(heap, rn - 1, 0, r);
             ++tn;
         }
         for (int i = 0; i < tn; ++i) depth[i] = 0;
         int maxDepth = 0;
-        for (int i = tn - 1; i != 0 && i > 0; --i) {                // index 0 is not visited (huffman.cpp:108)
-            if (i < n) { if (depth[i] > maxDepth) maxDepth = depth[i]; continue; }
-            const uint8_t dd = (uint8_t)(depth[i] + 1);
-            depth[left[i - n]] = dd; depth[right[i - n]] = dd;
+        for (int i = tn - 1; i > 0; --i) {                          // index 0 is not visited (huffman.cpp:108)
+            const int di = depth[i];
+            if (i < n) { if (di > maxDepth) maxDepth = di; continue; }
+            depth[left[i - n]] = (uint8_t)(di + 1); depth[right[i - n]] = (uint8_t)(di + 1);
         }
         if (maxDepth <= maxLength) {
-            for (int i = 0; i < n; ++i) lens[i] = freqs[i] == 0 ? 0 : (depth[i] > 1 ? depth[i] : 1);
+            for (int i = 0; i < n; ++i) { const int di = depth[i]; lens[i] = freqs[i] == 0 ? 0 : (di > 1 ? di : 1); }
             return;
         }
         int step = total / (1 << maxLength);
@@ -920,6 +928,7 @@ __device__ __forceinline__ uint32_t stored_size(int body)           // WriteUnco
 }
 
 constexpr int kHuffThreads = 32;
+constexpr int kHuffSmem = 286 * kHuffLanes * 4;
 
 __global__ void __launch_bounds__(kHuffThreads) k_huffman(Job job)
 {
@@ -937,7 +946,8 @@ __global__ void __launch_bounds__(kHuffThreads) k_huffman(Job job)
         return;
     }
 
-    HRec heap[286];
+    extern __shared__ __align__(16) uint8_t hsm[];
+    unsigned* heap = reinterpret_cast<unsigned*>(hsm) + threadIdx.x;
     unsigned short left[286], right[286];
     uint8_t depth[572];
     int freq[286];
@@ -945,26 +955,30 @@ __global__ void __launch_bounds__(kHuffThreads) k_huffman(Job job)
     unsigned short symRec[288], distRec[32];
     uint32_t metaCodes[19];
     uint8_t metaL[19];
+    uint8_t lens[336];                  // thread-local while the trees are built; copied to cc.lens at the end
 
     const uint32_t* hist = job.hist + (size_t)slot * kHistStride;
     long long bits = 0;
 
     for (int i = 0; i < 19; ++i) metaF[i] = 0;
     for (int i = 0; i < 286; ++i) freq[i] = (int)hist[i];
-    calc_lengths(freq, 286, 15, cc.lens, heap, left, right, depth);
-    generate_codes(cc.lens, 286, cc.lit);
-    const int nSym = rle_lengths(cc.lens, 286, symRec, metaF);
-    for (int i = 0; i < 286; ++i) bits += (long long)freq[i] * (cc.lens[i] + len_extra_bits(i));
+    calc_lengths(freq, 286, 15, lens, heap, left, right, depth);
+    generate_codes(lens, 286, cc.lit);
+    const int nSym = rle_lengths(lens, 286, symRec, metaF);
+    for (int i = 0; i < 286; ++i) bits += (long long)freq[i] * (lens[i] + len_extra_bits(i));
 
     for (int i = 0; i < 30; ++i) freq[i] = (int)hist[286 + i];
-    calc_lengths(freq, 30, 15, cc.lens + 286, heap, left, right, depth);
-    generate_codes(cc.lens + 286, 30, cc.dist);
-    const int nDist = rle_lengths(cc.lens + 286, 30, distRec, metaF);
-    for (int i = 0; i < 30; ++i) bits += (long long)freq[i] * (cc.lens[286 + i] + dist_extra_bits(i));
+    calc_lengths(freq, 30, 15, lens + 286, heap, left, right, depth);
+    generate_codes(lens + 286, 30, cc.dist);
+    const int nDist = rle_lengths(lens + 286, 30, distRec, metaF);
+    for (int i = 0; i < 30; ++i) bits += (long long)freq[i] * (lens[286 + i] + dist_extra_bits(i));
 
     calc_lengths(metaF, 19, 7, metaL, heap, left, right, depth);
     generate_codes(metaL, 19, metaCodes);
-    for (int i = 0; i < 19; ++i) cc.lens[316 + i] = metaL[i];
+    for (int i = 0; i < 19; ++i) lens[316 + i] = metaL[i];
+    lens[335] = 0;
+    for (int i = 0; i < 336 / 4; ++i)
+        reinterpret_cast<uint32_t*>(cc.lens)[i] = lens[4 * i] | (lens[4 * i + 1] << 8) | (lens[4 * i + 2] << 16) | ((uint32_t)lens[4 * i + 3] << 24);
 
     long long total = 3 + 5 + 5 + 4 + 3 * 19 + bits;
     for (int pass = 0; pass < 2; ++pass) {
@@ -1497,6 +1511,7 @@ cudaError_t configure_kernels()
     cudaError_t e;
     e = cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kParseSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem); if (e) return e;
+    e = cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffSmem); if (e) return e;
     static uint32_t tab[4][256];
     uint32_t powL[257], pow1[256];
     for (uint32_t i = 0; i < 256; ++i) {
@@ -1543,7 +1558,7 @@ int launch_parse(const Job& job, cudaStream_t s)
 
 int launch_huffman(const Job& job, cudaStream_t s)
 {
-    k_huffman<<<(job.nchunks + kHuffThreads - 1) / kHuffThreads, kHuffThreads, 0, s>>>(job);
+    k_huffman<<<(job.nchunks + kHuffThreads - 1) / kHuffThreads, kHuffThreads, kHuffSmem, s>>>(job);
     return 1;
 }
 
