@@ -237,16 +237,19 @@ int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int fina
 // the middle (full occupancy, one dictionary-priming pass per long run of chunks), small at the end (short drain).
 std::vector<uint64_t> pieceSchedule(uint64_t nchunks)
 {
+    // Every piece costs one launch of each kernel, and the Huffman kernel is ~1 ms however few chunks it gets
+    // (one serial thread per chunk), so pieces are few: 1024, 2048, then 4096 chunks, and the last <= 6144 chunks in
+    // two pieces (60/40) so that the final D2H is short.
     std::vector<uint64_t> ends;
     const uint64_t big = 4096;
-    uint64_t pos = 0, size = 512;
-    while (nchunks - pos > 2 * big) {
+    uint64_t pos = 0, size = 1024;
+    while (nchunks - pos > big + big / 2) {
         pos += size; ends.push_back(pos);
         if (size < big) size *= 2;
     }
-    uint64_t rem = nchunks - pos;                       // <= 2 * big: taper
-    while (rem > 1024) { const uint64_t take = rem / 2; pos += take; ends.push_back(pos); rem -= take; }
-    if (rem) { pos += rem; ends.push_back(pos); }
+    const uint64_t rem = nchunks - pos;
+    if (rem > 1024) { const uint64_t take = rem * 3 / 5; pos += take; ends.push_back(pos); }
+    if (pos < nchunks) ends.push_back(nchunks);
     return ends;
 }
 
@@ -469,10 +472,13 @@ int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int final, in
         stats->kernel_launches = launches;
         collectStages(c, stats);
         cudaEventElapsedTime(&stats->total_ms, c.ev[0], c.ev[3]);
-        if (cudaEventElapsedTime(&stats->device_ms, c.ev[1], c.ev[2]) != cudaSuccess || h2d + d2h > 0) {
-            stats->device_ms = 0;                    // pipelined path: kernels interleave with copies; sum the stages
+        if (h2d + d2h > 0) {
+            stats->device_ms = 0;                    // host buffers: kernels interleave with copies; sum the stages
             for (int i = 0; i < 8; ++i) stats->device_ms += stats->stage_ms[i];
+        } else {
+            cudaEventElapsedTime(&stats->device_ms, c.ev[1], c.ev[2]);
         }
+        (void)cudaGetLastError();                    // timing queries must never poison the next call
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
     }
     return ZZGPU_OK;

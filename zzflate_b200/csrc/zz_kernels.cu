@@ -817,10 +817,11 @@ __device__ __forceinline__ void heap_adjust(unsigned* h, int hole, int len, unsi
     heap_push_(h, hole, top, v);
 }
 
-// CalcLengths (huffman.cpp:122-154).  n <= 286.  heap points at this lane's shared-memory column (the hot, latency-
-// critical structure); the tree links and depths are thread-local (touched once per merge / once at the end).
-__device__ __noinline__ void calc_lengths(const int* freqs, int n, int maxLength, uint8_t* lens,
-                                          unsigned* heap, unsigned short* left, unsigned short* right, uint8_t* depth)
+// CalcLengths (huffman.cpp:122-154).  n <= 286.  `heap` points at this lane's shared-memory column.  The heap
+// shrinks by one entry per merge while the tree grows by one node, so node t (tree id n + t) is stored in the slot the
+// heap has just vacated (slot nsym-1-t) as left | right << 10 | depth << 20: heap, tree links and depths share one
+// 286-word column and the latency-critical chain never leaves shared memory.  Leaf depths go straight to `lens`.
+__device__ __noinline__ void calc_lengths(const int* freqs, int n, int maxLength, uint8_t* lens, unsigned* heap)
 {
     int total = 0;
     for (int i = 0; i < n; ++i) total += freqs[i];
@@ -828,36 +829,41 @@ __device__ __noinline__ void calc_lengths(const int* freqs, int n, int maxLength
     for (;;) {
         int rn = 0;
         for (int i = 0; i < n; ++i) {
+            lens[i] = freqs[i] == 0 ? 0 : 1;                        // a used symbol that stays at depth 0 gets length 1
             if (freqs[i] == 0) continue;
             const unsigned f = (unsigned)(freqs[i] > minFreq ? freqs[i] : minFreq);
             heap[HS(rn++)] = (f << 10) | (unsigned)i;
         }
+        const int nsym = rn;
         if (rn >= 2)
             for (int parent = (rn - 2) / 2; ; --parent) { heap_adjust(heap, parent, rn, heap[HS(parent)]); if (parent == 0) break; }
-        int tn = n;                                              // tree index of the next internal node
+        int tn = n;                                              // tree id of the next internal node
         while (rn >= 2) {
             unsigned a, b;
             if (rn > 1) { const unsigned v = heap[HS(rn - 1)]; heap[HS(rn - 1)] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
             a = heap[HS(--rn)];
             if (rn > 1) { const unsigned v = heap[HS(rn - 1)]; heap[HS(rn - 1)] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
             b = heap[HS(--rn)];
-            left[tn - n] = (unsigned short)(a & 1023u); right[tn - n] = (unsigned short)(b & 1023u);
             const unsigned r = ((HF(a) + HF(b)) << 10) | (unsigned)tn;
             heap[HS(rn++)] = r;
             heap_push_(heap, rn - 1, 0, r);
+            heap[HS(rn)] = (a & 1023u) | ((b & 1023u) << 10);       // node tn lives in the slot just vacated (depth 0 for now)
             ++tn;
         }
-        for (int i = 0; i < tn; ++i) depth[i] = 0;
+        // depths, root first: the root is the last node created = slot 1, node t sits in slot nsym-1-t
         int maxDepth = 0;
-        for (int i = tn - 1; i > 0; --i) {                          // index 0 is not visited (huffman.cpp:108)
-            const int di = depth[i];
-            if (i < n) { if (di > maxDepth) maxDepth = di; continue; }
-            depth[left[i - n]] = (uint8_t)(di + 1); depth[right[i - n]] = (uint8_t)(di + 1);
+        for (int sl = 1; sl < nsym; ++sl) {
+            const unsigned nd = heap[HS(sl)];
+            const int dd = (int)(nd >> 20) + 1;
+            const int ids[2] = { (int)(nd & 1023u), (int)((nd >> 10) & 1023u) };
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int id = ids[c];
+                if (id < n) { lens[id] = (uint8_t)dd; if (id != 0 && dd > maxDepth) maxDepth = dd; }   // leaf 0 is not looked at (huffman.cpp:108)
+                else { const int cs = nsym - 1 - (id - n); heap[HS(cs)] = (heap[HS(cs)] & 0xFFFFFu) | ((unsigned)dd << 20); }
+            }
         }
-        if (maxDepth <= maxLength) {
-            for (int i = 0; i < n; ++i) { const int di = depth[i]; lens[i] = freqs[i] == 0 ? 0 : (di > 1 ? di : 1); }
-            return;
-        }
+        if (maxDepth <= maxLength) return;
         int step = total / (1 << maxLength);
         minFreq += step > 1 ? step : 1;
     }
@@ -948,8 +954,6 @@ __global__ void __launch_bounds__(kHuffThreads) k_huffman(Job job)
 
     extern __shared__ __align__(16) uint8_t hsm[];
     unsigned* heap = reinterpret_cast<unsigned*>(hsm) + threadIdx.x;
-    unsigned short left[286], right[286];
-    uint8_t depth[572];
     int freq[286];
     int metaF[19];
     unsigned short symRec[288], distRec[32];
@@ -962,18 +966,18 @@ __global__ void __launch_bounds__(kHuffThreads) k_huffman(Job job)
 
     for (int i = 0; i < 19; ++i) metaF[i] = 0;
     for (int i = 0; i < 286; ++i) freq[i] = (int)hist[i];
-    calc_lengths(freq, 286, 15, lens, heap, left, right, depth);
+    calc_lengths(freq, 286, 15, lens, heap);
     generate_codes(lens, 286, cc.lit);
     const int nSym = rle_lengths(lens, 286, symRec, metaF);
     for (int i = 0; i < 286; ++i) bits += (long long)freq[i] * (lens[i] + len_extra_bits(i));
 
     for (int i = 0; i < 30; ++i) freq[i] = (int)hist[286 + i];
-    calc_lengths(freq, 30, 15, lens + 286, heap, left, right, depth);
+    calc_lengths(freq, 30, 15, lens + 286, heap);
     generate_codes(lens + 286, 30, cc.dist);
     const int nDist = rle_lengths(lens + 286, 30, distRec, metaF);
     for (int i = 0; i < 30; ++i) bits += (long long)freq[i] * (lens[286 + i] + dist_extra_bits(i));
 
-    calc_lengths(metaF, 19, 7, metaL, heap, left, right, depth);
+    calc_lengths(metaF, 19, 7, metaL, heap);
     generate_codes(metaL, 19, metaCodes);
     for (int i = 0; i < 19; ++i) lens[316 + i] = metaL[i];
     lens[335] = 0;
