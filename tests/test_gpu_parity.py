@@ -192,6 +192,32 @@ def test_device_resident_buffers(zz, oracle):
         assert dst[3: 3 + n2].cpu().numpy().tobytes() == out
 
 
+def test_host_buffers_pipelined_path(zz, oracle):
+    """Inputs >= 32 MiB on host buffers go through the piece-wise path (H2D / kernels / D2H overlapped on three
+    streams); the bytes must not depend on how the call was cut into pieces, nor on the batch-overlap option."""
+    import ctypes as C
+    from zzflate_b200 import synth, _lib
+    n = (96 << 20) + 12345
+    data = synth.markov_text(n, seg0=7)
+    data[40 << 20: 41 << 20] = 0                                 # a stretch of zeros and of noise inside the text
+    data[41 << 20: 42 << 20] = synth.random_bytes(1 << 20)
+    want, _ = oracle.stream_chunked(data, ZLIB, 2, threads=8)
+    for threaded in (False, True):
+        got = zz.ZzFlateEncode(data, zz.Config(zz.Format.Zlib, 2, threaded))
+        assert got == want
+    lib = _lib.load()
+    assert lib.zzgpu_set_option(b"overlap", 1) == 0
+    try:
+        out, a0, crc, st = zz.deflate_raw(data, level=2)
+    finally:
+        lib.zzgpu_set_option(b"overlap", 0)
+    assert out == want[2:-4]
+    assert zz.combine(1, a0, n) == zlib.adler32(data) and crc == zlib.crc32(data)
+    assert lib.zzgpu_set_option(b"no-such-option", 1) == _lib.E_ARG
+    g1 = zz.ZzFlateEncode(data[: 40 << 20], zz.Config(zz.Format.Gzip, 1, False))
+    assert zlib.decompress(g1, 31) == data[: 40 << 20].tobytes()
+
+
 @pytest.mark.parametrize("workload,size_mib", [("text", 1024), ("random", 256), ("zeros", 256), ("pattern", 256)])
 def test_baseline_sizes_round_trip(zz, workload, size_mib):
     """BASELINE.json configs 2-4 at full size: every output inflates through zlib to the input and the
