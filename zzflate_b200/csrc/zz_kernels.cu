@@ -747,23 +747,31 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
     __syncthreads();
 
     // ---- histograms (GetFrequencies, encoder.cpp:442-471) ----
+    // Matches are counted token-parallel and mark the positions they cover in a bitmap; literals are then counted
+    // position-parallel (coalesced window reads) into per-warp private histograms.
     unsigned* hist = reinterpret_cast<unsigned*>(info);            // per-warp private copies (batch arrays are dead)
-    for (int i = tid; i < nwarps * kHistStride; i += kParseThreads) hist[i] = 0;
+    unsigned* cov = hist + nwarps * kHistStride;                   // bit per position: covered by a match
+    for (int i = tid; i < nwarps * kHistStride + kMaxChunk / 32; i += kParseThreads) hist[i] = 0;
     __syncthreads();
     {
         const int ntok = ps.ntok;
         unsigned* myh = hist + warp * kHistStride;
-        const int per = (g.body + kParseThreads - 1) / kParseThreads;
-        int a = tid * per, b = a + per; if (b > g.body) b = g.body;
-        if (a < b) {
-            walk_positions(tokA, ntok, a, b,
-                [&](int pos) { atomicAdd(&myh[win[wb + pos]], 1u); },
-                [&](int k, int, int ln) {
-                    int eb, ev;
-                    atomicAdd(&myh[len_symbol(ln, eb, ev)], 1u);
-                    atomicAdd(&myh[286 + dist_symbol(tokD[k], eb, ev)], 1u);
-                });
+        for (int k = tid; k < ntok; k += kParseThreads) {
+            const uint32_t t = tokA[k];
+            const int ms = (int)(t & 0xFFFF), ln = (int)(t >> 16), me = ms + ln - 1;
+            int eb, ev;
+            atomicAdd(&myh[len_symbol(ln, eb, ev)], 1u);
+            atomicAdd(&myh[286 + dist_symbol(tokD[k], eb, ev)], 1u);
+            for (int w = ms >> 5; w <= (me >> 5); ++w) {
+                unsigned m = 0xffffffffu;
+                if (w == (ms >> 5)) m &= 0xffffffffu << (ms & 31);
+                if (w == (me >> 5)) m &= 0xffffffffu >> (31 - (me & 31));
+                atomicOr(&cov[w], m);
+            }
         }
+        __syncthreads();
+        for (int pos = tid; pos < g.body; pos += kParseThreads)
+            if (!((cov[pos >> 5] >> (pos & 31)) & 1u)) atomicAdd(&myh[win[wb + pos]], 1u);
     }
     __syncthreads();
     for (int i = tid; i < 316; i += kParseThreads) {
