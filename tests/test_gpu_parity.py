@@ -218,10 +218,11 @@ def test_host_buffers_pipelined_path(zz, oracle):
     assert zlib.decompress(g1, 31) == data[: 40 << 20].tobytes()
 
 
-@pytest.mark.parametrize("workload,size_mib", [("text", 1024), ("random", 256), ("zeros", 256), ("pattern", 256)])
+@pytest.mark.parametrize("workload,size_mib", [("text", 1024), ("text", 1088), ("random", 256), ("zeros", 256), ("pattern", 256)])
 def test_baseline_sizes_round_trip(zz, workload, size_mib):
     """BASELINE.json configs 2-4 at full size: every output inflates through zlib to the input and the
-    checksums agree with zlib's (size-independent properties; the oracle covers a 32 MiB prefix bit-exactly)."""
+    checksums agree with zlib's (size-independent properties; the oracle covers a 32 MiB prefix bit-exactly).
+    1088 MiB = 17 408 chunks crosses the 16 384-chunk scratch batch."""
     import torch
     from oracle_lib import oracle as get_oracle
     from zzflate_b200 import synth
