@@ -325,18 +325,18 @@ __device__ __forceinline__ int patched_cand(const uint16_t* cand, const ParseSha
     return d;
 }
 
-__device__ __forceinline__ int fwd_cap(const uint8_t* win, int oj, int op)
+// forward match length beyond the first 4 bytes, capped at kCapLen - 4 (oj, op already advanced by 4)
+__device__ __forceinline__ int fwd_more(const uint8_t* win, int oj, int op)
 {
-    // most candidates differ within the first 4 bytes: probe those with a 4-byte compare, then 8 at a time
-    const unsigned x0 = ld4(win, oj) ^ ld4(win, op);
-    if (x0) return (__ffs(x0) - 1) >> 3;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const unsigned long long x = ld8(win, oj + 4 + 8 * k) ^ ld8(win, op + 4 + 8 * k);
-        if (x) return 4 + 8 * k + ((__ffsll((long long)x) - 1) >> 3);
+        const unsigned long long x = ld8(win, oj + 8 * k) ^ ld8(win, op + 8 * k);
+        const unsigned xl = (unsigned)x, xh = (unsigned)(x >> 32);
+        if (xl) return 8 * k + ((__ffs(xl) - 1) >> 3);
+        if (xh) return 8 * k + 4 + ((__ffs(xh) - 1) >> 3);
     }
-    const unsigned x1 = ld4(win, oj + 28) ^ ld4(win, op + 28);
-    return x1 ? 28 + ((__ffs(x1) - 1) >> 3) : kCapLen;
+    const unsigned x1 = ld4(win, oj + 24) ^ ld4(win, op + 24);
+    return x1 ? 24 + ((__ffs(x1) - 1) >> 3) : kCapLen - 4;
 }
 
 // exact forward match length (<= 258), all 32 lanes cooperate (remain(), encoder.cpp:81-90)
@@ -509,18 +509,26 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         // ---- P1: per-position match info (parse independent) ----
         {
             const int lim = ntiles * 32 + 64;
+            const unsigned* w32 = reinterpret_cast<const unsigned*>(win);
             for (int idx = tid; idx < lim; idx += kParseThreads) {
                 const int j = base + idx;
                 const int d = E2[idx];
                 unsigned inf = 0;
                 if (d) {
-                    const int p = j - d;
-                    const int fwd = fwd_cap(win, wb + j, wb + p);
+                    // bytes [j-4, j+4) and [p-4, p+4) from three aligned words each: one funnel shift gives the
+                    // 4 bytes after the position, one the 4 bytes before it
+                    const int oj = wb + j, op = oj - d;
+                    const unsigned* wj = w32 + (oj >> 2);
+                    const unsigned* wp = w32 + (op >> 2);
+                    const int sj = (oj & 3) * 8, sp = (op & 3) * 8;
+                    const unsigned j0 = wj[0], p0 = wp[0];
+                    const unsigned x = __funnelshift_r(j0, wj[1], sj) ^ __funnelshift_r(p0, wp[1], sp);
+                    int fwd = x ? ((__ffs(x) - 1) >> 3) : 4 + fwd_more(win, oj + 4, op + 4);
                     bool ok = fwd >= 4;
                     if (!ok) {
-                        const unsigned y = ld4(win, wb + j - 4) ^ ld4(win, wb + p - 4);
+                        const unsigned y = __funnelshift_r(wj[-1], j0, sj) ^ __funnelshift_r(wp[-1], p0, sp);
                         int back = y ? (__clz(y) >> 3) : 4;
-                        const int room = p + g.pre;      // bytes of real history before the candidate (R4 clamp)
+                        const int room = j - d + g.pre;  // bytes of real history before the candidate (R4 clamp)
                         if (back > room) back = room;
                         ok = fwd + back >= 4;
                     }
@@ -555,18 +563,20 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             const int b = tileStart + lane;
             unsigned f = 0;
             {
-                // probe_next for the 32 states of the tile from the (warp-uniform) eligibility bitmaps
-                const unsigned long long a1 = elig1[t] | ((unsigned long long)elig1[t + 1] << 32);
-                const unsigned long long a2 = elig2[t] | ((unsigned long long)elig2[t + 1] << 32);
-                const unsigned long long a3 = elig3[t] | ((unsigned long long)elig3[t + 1] << 32);
-                const unsigned long long a4 = okbits[t] | ((unsigned long long)okbits[t + 1] << 32);
+                // probe_next for the 32 states of the tile from the (warp-uniform) eligibility bitmaps:
+                // funnel shifts line bit b+k of the two words covering [tile, tile+64) up with lane b
                 int j = -1;
-                if ((a1 >> (lane + 1)) & 1ull) j = b + 1;
-                else if ((a2 >> (lane + 2)) & 1ull) j = b + 2;
-                else if ((a3 >> (lane + 3)) & 1ull) j = b + 3;
+                auto bitAt = [](unsigned lo, unsigned hi, int i) { return (((i & 32) ? hi : lo) >> (i & 31)) & 1u; };
+                if (bitAt(elig1[t], elig1[t + 1], lane + 1)) j = b + 1;
+                else if (bitAt(elig2[t], elig2[t + 1], lane + 2)) j = b + 2;
+                else if (bitAt(elig3[t], elig3[t + 1], lane + 3)) j = b + 3;
                 else {
-                    const unsigned long long rest = a4 >> (lane + 4);
-                    if (rest) j = b + 4 + __ffsll((long long)rest) - 1;
+                    const unsigned low = okbits[t], hiw = okbits[t + 1];
+                    const int sh = lane + 4;                                           // first position that needs nothing backwards
+                    const unsigned near = sh < 32 ? __funnelshift_r(low, hiw, sh) : hiw >> (sh - 32);   // from position b+4
+                    const unsigned far = sh < 32 ? hiw >> sh : 0u;                    // from position b+36
+                    if (near) j = b + 4 + __ffs(near) - 1;
+                    else if (far) j = b + 36 + __ffs(far) - 1;
                     else if (t + 2 <= ntiles) {
                         const unsigned w2 = nzw[t + 2];
                         if (w2 != kNone16) j = base + (int)w2 * 32 + __ffs(okbits[w2]) - 1;
