@@ -642,14 +642,10 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 if (newSeg) { if (lane == 0) seg[nseg] = (uint16_t)b; ++nseg; newSeg = false; }
                 const int r = b - base;
                 const unsigned e = E2[r];
+                // E2 is complete for every state (P3), so: beyond the super tile (or the batch) = plain hop,
+                // 0 = the orbit ends inside a tile, anything else = the state where it meets a long match
+                if ((int)e >= base + ((r >> 10) + 1) * 1024 || (int)e >= E) { b = (int)e; newSeg = true; continue; }
                 if (e == 0) { finalB = -1; break; }       // ends inside a tile: the tile reports the last state
-                if ((int)e >= E) { b = (int)e; continue; }
-                const bool crosses = (((int)e - base) >> 10) != (r >> 10);
-                if (crosses || F[(int)e - base] != 1) {   // plain hop (at least out of b's tile, at best out of its super tile)
-                    newSeg = crosses;
-                    b = (int)e;
-                    continue;
-                }
                 // long match at state x = e: exact lengths
                 const int x = (int)e;
                 const int j = probe_next(info, okbits, nzw, ntiles, base, x);
