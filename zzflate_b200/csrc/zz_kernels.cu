@@ -132,7 +132,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* st, const uint8_t* gsrc, int
 
 __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
 {
-    __shared__ uint16_t table[kHashSize];
+    __shared__ int table[kHashSize];
     __shared__ __align__(16) uint8_t stage[2][kCandStage];
     const int lane = threadIdx.x;
     const unsigned firstSlot = blockIdx.x * (unsigned)run;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
     const uint8_t* validHi = job.src + job.n;
     const unsigned ltMask = (1u << lane) - 1u;
 
-    int sweepAt = 0;                         // steps until the next sweep; 0 => sweep now (also the initial fill)
+    for (int i = lane; i < kHashSize; i += 32) table[i] = kEmptySlot;
     int buf = 0;
     stage_tile(stage[0], base0 + qStart, kCandTile + 8, validLo, validHi, lane);
     for (int q0 = qStart; q0 < qEnd; q0 += kCandTile) {
@@ -162,18 +162,6 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
         const int tileEnd = min(q0 + kCandTile, qEnd);
 #pragma unroll 2
         for (int qs = q0; qs < tileEnd; qs += 32) {
-            if (sweepAt == 0) {
-                // retire entries 32768 or more behind position qs (and stale markers); marker = qs - 32768
-                const unsigned now = (unsigned)qs & 0xFFFFu;
-                const unsigned marker = (now - 32768u) & 0xFFFFu;
-                for (int i = lane; i < kHashSize; i += 32) {
-                    const unsigned age = (now - table[i]) & 0xFFFFu;
-                    if (age == 0 || age >= 32768u || qs == qStart) table[i] = (uint16_t)marker;
-                }
-                __syncwarp();
-                sweepAt = 1024;
-            }
-            --sweepAt;
             const int q = qs + lane;
             const int o = phase + (q - q0);
             const unsigned v = __funnelshift_r(sw[o >> 2], sw[(o >> 2) + 1], (o & 3) * 8) & 0xFFFFFFu;
@@ -182,29 +170,25 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
             // position 0 of a chunk is neither probed nor inserted (encoder.cpp:384); positions before the run
             // only prime the table (AddHashEntries, encoder.cpp:474)
             const bool act = inRange && (q < 0 || ((unsigned)q & startMask) != 0);
-            // Same-hash positions inside one step are found without MATCH.ANY (slow when all 32 keys differ, the
-            // common case): everybody writes, whoever does not read its own value back shares its hash with
-            // another lane; only those groups are then resolved with ballots.
-            const unsigned myv = (unsigned)q & 0xFFFFu;
-            const unsigned old = act ? table[h] : 0u;
-            __syncwarp();
-            if (act) table[h] = (uint16_t)myv;
-            __syncwarp();
-            const bool loser = act && table[h] != myv;
-            unsigned pending = __ballot_sync(0xffffffffu, loser);
-            unsigned lower = 0;
-            bool fixTable = false;
-            while (pending) {
-                const unsigned hl = __shfl_sync(0xffffffffu, h, __ffs(pending) - 1);
-                const unsigned mem = __ballot_sync(0xffffffffu, act && h == hl);
-                if (act && h == hl) { lower = mem & ltMask; fixTable = (mem >> lane) == 1u; }
-                pending &= ~mem;
+            // One shared-memory exchange per position does probe and insert at once.  Lanes of a step that share a
+            // hash are serialised by the hardware; if that happens in ascending lane order each lane receives the
+            // position of the nearest lower lane with its hash (or the slot's previous content) -- exactly the
+            // candidate -- and the highest lane's position stays in the slot.  Any other order hands some lane a
+            // position above its own, which is detected and the step is redone with explicit group resolution.
+            int old = act ? atomicExch(&table[h], q) : kEmptySlot;
+            if (__ballot_sync(0xffffffffu, act && old > q)) {
+                const unsigned grp = __match_any_sync(0xffffffffu, act ? h : (0x10000u + lane));
+                const unsigned fromBefore = __ballot_sync(0xffffffffu, act && old < qs) & grp;   // exactly one lane per group
+                const int pre = __shfl_sync(0xffffffffu, old, fromBefore ? __ffs(fromBefore) - 1 : lane);
+                const unsigned lower = grp & ltMask;
+                old = lower ? qs + 31 - __clz(lower) : pre;
+                __syncwarp();
+                if (act && (grp >> lane) == 1u) table[h] = q;       // the highest position of a group owns the slot
+                __syncwarp();
             }
-            if (fixTable) table[h] = (uint16_t)myv;          // the highest position of a group owns the slot
-            __syncwarp();
             if (inRange && q >= 0) {
-                const unsigned d = lower ? (unsigned)(lane - (31 - __clz(lower))) : ((myv - old) & 0xFFFFu);
-                candOut[q] = (uint16_t)((act && d < (unsigned)kMaxDistance) ? d : 0);
+                const int d = q - old;
+                candOut[q] = (uint16_t)((act && d < kMaxDistance) ? d : 0);
             }
         }
         buf ^= 1;
@@ -1556,7 +1540,7 @@ int launch_candidates(const Job& job, cudaStream_t s)
     // one priming pass per run of chunks is exact only for the default geometry (see K-CAND)
     int run = 1;
     if (job.chunk == 65536 && job.dict == 32768) {
-        const unsigned target = 148u * 11u;                       // resident warps: 16 KiB table + staging per CTA
+        const unsigned target = 148u * 6u;                        // resident warps: 32 KiB table + staging per CTA
         run = (int)((job.nchunks + target - 1) / target);
         if (run < 1) run = 1;
         if (run > 64) run = 64;
