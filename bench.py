@@ -45,18 +45,21 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up; the summary uses the samples
+    whose timestamps fall inside the timed region (and, if the region was shorter than the sampling jitter, the
+    load-carrying warm-up right before it)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -64,24 +67,40 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
+
+        def summarise(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[2])); mx.append(float(r[3]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[6:10]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                except Exception:
+                    continue
+            return sm, mx, reasons
+
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 - 0.02 <= x[0] <= (self.t1 or x[0]) + 0.02]
+        window = "timed region"
+        if len(inside) < 3:
+            inside = [x for x in self.rows if self.t0 is None or x[0] >= self.t0 - 1.0]
+            window = "timed region and the warm-up second before it"
+        sm, mx, reasons = summarise(inside)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def make_shard(workload: str, rank: int, nbytes: int):
@@ -196,11 +215,12 @@ def main():
         return zz.deflate_device(d_src.data_ptr() + hist, nbytes, d_dst.data_ptr(), cap, level=args.level,
                                  history=hist, final=final, checksums=1)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         out_len, _, _, st = device_step()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     dev_ms, stage_ms, launches = 0.0, [0.0] * 8, 0
     stage_n = [0] * 8
     t0 = time.perf_counter()
@@ -212,6 +232,7 @@ def main():
             stage_ms[i] += st.stage_ms[i]; stage_n[i] += st.stage_launches[i]
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.mark_end()
     clocks = sampler.stop()
     # ---- end to end through the public API on pinned host buffers
     e2e_ms, e2e_out = None, 0
