@@ -4,8 +4,12 @@
 #include "../../include/zzgpu.h"
 #include "zz_kernels.cuh"
 
+#include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include <cstring>
 #include <cstdio>
@@ -38,6 +42,9 @@ struct Ctx {
     uint8_t* dIn = nullptr; size_t dInCap = 0;
     uint8_t* dOut = nullptr; size_t dOutCap = 0;
     cudaStream_t copyIn = nullptr, copyOut = nullptr;     // host-buffer path: H2D / D2H overlap the kernels
+    uint8_t* stageIn[2] = { nullptr, nullptr };           // pinned blocks between pageable caller memory and the device
+    uint8_t* stageOut[2] = { nullptr, nullptr };
+    cudaEvent_t stageInEv[2] = { nullptr, nullptr }, stageOutEv[2] = { nullptr, nullptr };
     std::vector<cudaEvent_t> pieceEv;
     uint64_t* hPiece = nullptr; size_t hPieceCap = 0;     // pinned: running totals after each piece
     cudaStream_t lane[3] = { nullptr, nullptr, nullptr };  // batches of one call rotate over these streams
@@ -153,6 +160,72 @@ void collectStages(Ctx& c, zzgpu_stats* stats)
     }
 }
 
+// Parallel memcpy between pageable caller memory and the pinned staging blocks (a single host thread moves
+// ~10 GB/s, less than the PCIe link).  Workers are shared by all contexts of the process.
+class CopyPool {
+public:
+    static CopyPool& get() { static CopyPool p; return p; }
+    void copy(void* dst, const void* src, size_t n)
+    {
+        const size_t part = (size_t)2 << 20;
+        if (n <= 2 * part || workers.empty()) { memcpy(dst, src, n); return; }
+        std::atomic<size_t> left{ (n + part - 1) / part };
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t off = 0; off < n; off += part)
+                q.push_back(Task{ (char*)dst + off, (const char*)src + off, std::min(part, n - off), &left });
+        }
+        cv.notify_all();
+        for (;;) {                                   // the caller helps, then waits for stragglers
+            Task t;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (q.empty()) break;
+                t = q.front(); q.pop_front();
+            }
+            memcpy(t.d, t.s, t.n); t.left->fetch_sub(1);
+        }
+        while (left.load() != 0) std::this_thread::yield();
+    }
+private:
+    struct Task { char* d; const char* s; size_t n; std::atomic<size_t>* left; };
+    CopyPool()
+    {
+        unsigned k = std::thread::hardware_concurrency();
+        k = k > 16 ? 7 : (k > 3 ? k / 2 - 1 : 0);
+        for (unsigned i = 0; i < k; ++i) workers.emplace_back([this] { run(); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& w : workers) w.join();
+    }
+    void run()
+    {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [this] { return stop || !q.empty(); });
+                if (stop && q.empty()) return;
+                t = q.front(); q.pop_front();
+            }
+            memcpy(t.d, t.s, t.n); t.left->fetch_sub(1);
+        }
+    }
+    std::vector<std::thread> workers; std::mutex mu; std::condition_variable cv; std::deque<Task> q; bool stop = false;
+};
+
+bool isPinnedHost(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+constexpr size_t kStageBlock = (size_t)32 << 20;    // pinned staging block for pageable caller buffers
+
 int preparePipeline(Ctx& c, size_t n, uint32_t chunk, int wantCk)
 {
     const uint64_t nchunks = (n + chunk - 1) / chunk;
@@ -262,6 +335,14 @@ int runHostPipelined(Ctx& c, const uint8_t* src, size_t n, size_t hist, int fina
     const size_t d_cap = std::min(cap, zzgpu_bound(n, level, chunk));
     rc = ensureBuf(c.dOut, c.dOutCap, d_cap + 64); if (rc) return rc;
     if (!c.copyIn) { CK(cudaStreamCreateWithFlags(&c.copyIn, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c.copyOut, cudaStreamNonBlocking)); }
+    const bool srcPinned = isPinnedHost(src), dstPinned = isPinnedHost(dst);
+    if (!srcPinned || !dstPinned) {
+        for (int i = 0; i < 2; ++i) {
+            if (!c.stageIn[i]) { CK(cudaMallocHost(&c.stageIn[i], kStageBlock)); CK(cudaMallocHost(&c.stageOut[i], kStageBlock));
+                                 CK(cudaEventCreateWithFlags(&c.stageInEv[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c.stageOutEv[i], cudaEventDisableTiming)); }
+        }
+    }
+    size_t inBlocks = 0, outBlocks = 0;
     const std::vector<uint64_t> ends = pieceSchedule(nchunks);
     const size_t np = ends.size();
     while (c.pieceEv.size() < 2 * np) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.pieceEv.push_back(e); }
@@ -277,7 +358,18 @@ int runHostPipelined(Ctx& c, const uint8_t* src, size_t n, size_t hist, int fina
     for (size_t p = 0; p < np; ++p) {
         const size_t lo = (size_t)(firstChunk * chunk), hi = (size_t)std::min<uint64_t>(n, ends[p] * chunk);
         const size_t from = p == 0 ? 0 : hist + lo, to = hist + hi;          // piece 0 also carries the history
-        CK(cudaMemcpyAsync(c.dIn + from, src - hist + from, to - from, cudaMemcpyHostToDevice, c.copyIn));
+        if (srcPinned) {
+            CK(cudaMemcpyAsync(c.dIn + from, src - hist + from, to - from, cudaMemcpyHostToDevice, c.copyIn));
+        } else {
+            for (size_t off = from; off < to; off += kStageBlock, ++inBlocks) {
+                const size_t len = std::min(kStageBlock, to - off);
+                const int sb = (int)(inBlocks & 1);
+                CK(cudaEventSynchronize(c.stageInEv[sb]));                   // the block's previous H2D has drained
+                CopyPool::get().copy(c.stageIn[sb], src - hist + off, len);
+                CK(cudaMemcpyAsync(c.dIn + off, c.stageIn[sb], len, cudaMemcpyHostToDevice, c.copyIn));
+                CK(cudaEventRecord(c.stageInEv[sb], c.copyIn));
+            }
+        }
         CK(cudaEventRecord(c.pieceEv[2 * p], c.copyIn));
         CK(cudaStreamWaitEvent(c.stream, c.pieceEv[2 * p], 0));
         rc = runChunks(c, d_src, n, hist, final, c.dOut, d_cap, level, chunk, dict, wantCk, firstChunk, ends[p], launches);
@@ -294,7 +386,25 @@ int runHostPipelined(Ctx& c, const uint8_t* src, size_t n, size_t hist, int fina
         if (flags & 1) return fail(ZZGPU_E_CAPACITY, "destination too small");
         if (flags & ~1ull) return fail(ZZGPU_E_CUDA, "internal consistency check failed (emit size mismatch)");
         if (upto > cap) return fail(ZZGPU_E_CAPACITY, "destination too small");
-        if (upto > done) CK(cudaMemcpyAsync(dst + done, c.dOut + done, upto - done, cudaMemcpyDeviceToHost, c.copyOut));
+        if (upto > done) {
+            if (dstPinned) {
+                CK(cudaMemcpyAsync(dst + done, c.dOut + done, upto - done, cudaMemcpyDeviceToHost, c.copyOut));
+            } else {
+                // D2H of block k+1 runs while block k is copied out of its pinned stage
+                size_t pendOff = 0, pendLen = 0; int pendSb = 0;
+                for (size_t off = done; off < upto || pendLen; ) {
+                    size_t len = 0; int sb = 0;
+                    if (off < upto) {
+                        len = std::min(kStageBlock, (size_t)upto - off); sb = (int)(outBlocks++ & 1);
+                        CK(cudaMemcpyAsync(c.stageOut[sb], c.dOut + off, len, cudaMemcpyDeviceToHost, c.copyOut));
+                        CK(cudaEventRecord(c.stageOutEv[sb], c.copyOut));
+                    }
+                    if (pendLen) { CK(cudaEventSynchronize(c.stageOutEv[pendSb])); CopyPool::get().copy(dst + pendOff, c.stageOut[pendSb], pendLen); }
+                    pendOff = off; pendLen = len; pendSb = sb;
+                    off += len;
+                }
+            }
+        }
         done = (size_t)upto;
     }
     CK(cudaEventRecord(c.ev[3], c.copyOut));
@@ -356,6 +466,7 @@ void zzgpu_shutdown(void)
         for (auto& e : c.stageEv) cudaEventDestroy(e);
         c.stageEv.clear(); c.stageOf.clear(); c.stageUsed = 0;
         if (c.copyIn) { cudaStreamDestroy(c.copyIn); cudaStreamDestroy(c.copyOut); c.copyIn = nullptr; c.copyOut = nullptr; }
+        for (int i = 0; i < 2; ++i) if (c.stageIn[i]) { cudaFreeHost(c.stageIn[i]); cudaFreeHost(c.stageOut[i]); cudaEventDestroy(c.stageInEv[i]); cudaEventDestroy(c.stageOutEv[i]); c.stageIn[i] = c.stageOut[i] = nullptr; }
         for (auto& e : c.ev) cudaEventDestroy(e);
         cudaStreamDestroy(c.stream);
         c.total = nullptr; c.hTotal = nullptr; c.ck = nullptr; c.hCk = nullptr; c.dIn = nullptr; c.dOut = nullptr;
