@@ -47,8 +47,8 @@ struct Ctx {
     cudaEvent_t stageInEv[2] = { nullptr, nullptr }, stageOutEv[2] = { nullptr, nullptr };
     std::vector<cudaEvent_t> pieceEv;
     uint64_t* hPiece = nullptr; size_t hPieceCap = 0;     // pinned: running totals after each piece
-    cudaStream_t lane[3] = { nullptr, nullptr, nullptr };  // batches of one call rotate over these streams
-    cudaEvent_t laneEv[3] = { nullptr, nullptr, nullptr }; // last kernel of the lane's latest batch
+    cudaStream_t lane[3] = { nullptr, nullptr, nullptr };  // overlap option: front-end and back-end streams
+    cudaEvent_t laneEv[3] = { nullptr, nullptr, nullptr };
     std::vector<cudaEvent_t> offsEv;        // offsets scan of batch k (the next batch's scan continues its running total)
     std::vector<cudaEvent_t> stageEv;       // pool of events bracketing each stage launch
     std::vector<int> stageOf;               // stage id of the interval that ENDS at event i (-1: start marker)
@@ -238,61 +238,91 @@ int preparePipeline(Ctx& c, size_t n, uint32_t chunk, int wantCk)
 }
 
 constexpr uint32_t kLaneChunks = 4096;      // chunks per batch when batches overlap
-constexpr int kLanes = 3;
-int g_overlap = 0;                          // zzgpu_set_option("overlap", 0/1); measured slower: K-MATCH needs whole SMs, co-resident
-                                            // small kernels fragment them (40.4 vs 31.6 ms per GiB), so off by default
+int g_overlap = 0;                          // zzgpu_set_option("overlap", 0/1)
+
+Job makeJob(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap, int level,
+            uint32_t chunk, uint32_t dict, int wantCk, uint64_t first, uint32_t count, size_t so)
+{
+    Job job{};
+    job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
+    job.first_chunk = first; job.nchunks = count;
+    job.final_stream = final; job.level = level; job.want_checksums = wantCk;
+    job.cand = c.cand + so * chunk; job.tokA = c.tokA + so * kMaxTokens; job.tokD = c.tokD + so * kMaxTokens;
+    job.hist = c.hist + so * kHistStride; job.codes = c.codes + so; job.state = c.state + so;
+    job.dst = d_dst; job.cap = cap; job.total = c.total; job.ck = c.ck;
+    return job;
+}
 
 // Kernel pipeline over chunks [firstChunk, lastChunk) of the call (geometry is always that of the whole call).
-// Large ranges are cut into batches of 4096 chunks that rotate over three streams with their own scratch slices:
-// K-MATCH fills every SM's shared memory, but the candidate, Huffman, emit and checksum kernels of neighbouring
-// batches overlap each other and every kernel's tail.  Only the offsets scan is ordered between batches (it
-// continues the running output size).
+//
+// Default: batches of up to 16 384 chunks, kernels back to back on one stream.
+// "overlap" option: batches of 4096 chunks on two streams with two scratch slices.  Stream A runs K-CAND and K-MATCH,
+// stream B runs K-HUFF, K-OFFS, K-EMIT, K-CKSUM.  K-MATCH needs whole SMs (its CTA takes all shared memory), so it
+// is ordered after the previous batch's K-EMIT; what overlaps is K-CAND of batch k+1 (one warp + 34 KiB per CTA) with
+// the back end of batch k.
 int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap,
               int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t firstChunk, uint64_t lastChunk, uint64_t& launches)
 {
     int rc;
     const uint64_t count = lastChunk - firstChunk;
-    const bool overlap = g_overlap && level != 1 && count >= 2 * kLaneChunks && c.slots >= kLanes * kLaneChunks;
-    const uint32_t batch = overlap ? kLaneChunks : c.slots;
-    if (overlap) {
-        for (int i = 0; i < kLanes; ++i)
-            if (!c.lane[i]) { CK(cudaStreamCreateWithFlags(&c.lane[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c.laneEv[i], cudaEventDisableTiming)); }
-        const size_t nb = (size_t)((count + batch - 1) / batch);
-        while (c.offsEv.size() < nb + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.offsEv.push_back(e); }
-        CK(cudaEventRecord(c.offsEv[0], c.stream));                 // everything queued so far on the main stream
-        for (int i = 0; i < kLanes; ++i) CK(cudaStreamWaitEvent(c.lane[i], c.offsEv[0], 0));
+    const bool overlap = g_overlap && level >= 2 && count >= 2 * kLaneChunks && c.slots >= 2 * kLaneChunks;
+    if (!overlap) {
+        for (uint64_t first = firstChunk; first < lastChunk; first += c.slots) {
+            const Job job = makeJob(c, d_src, n, history, final, d_dst, cap, level, chunk, dict, wantCk, first,
+                                    (uint32_t)std::min<uint64_t>(c.slots, lastChunk - first), 0);
+            cudaStream_t st = c.stream;
+            rc = markStage(c, -1, st); if (rc) return rc;
+            if (level >= 2) {
+                launches += launch_candidates(job, st); rc = markStage(c, ZZGPU_STAGE_CAND, st); if (rc) return rc;
+                launches += launch_parse(job, st); rc = markStage(c, ZZGPU_STAGE_PARSE, st); if (rc) return rc;
+            }
+            if (level == 1) {
+                launches += launch_fixed(job, st); rc = markStage(c, ZZGPU_STAGE_FIXED, st); if (rc) return rc;
+            } else {
+                launches += launch_huffman(job, st); rc = markStage(c, ZZGPU_STAGE_HUFF, st); if (rc) return rc;
+            }
+            launches += launch_offsets(job, st); rc = markStage(c, ZZGPU_STAGE_OFFS, st); if (rc) return rc;
+            if (level == 1) { launches += launch_gather(job, st); rc = markStage(c, ZZGPU_STAGE_GATHER, st); if (rc) return rc; }
+            else { launches += launch_emit(job, st); rc = markStage(c, ZZGPU_STAGE_EMIT, st); if (rc) return rc; }
+            if (wantCk) { launches += launch_checksums(job, st); rc = markStage(c, ZZGPU_STAGE_CKSUM, st); if (rc) return rc; }
+        }
+        CK(cudaGetLastError());
+        return ZZGPU_OK;
     }
+
+    for (int i = 0; i < 2; ++i)
+        if (!c.lane[i]) { CK(cudaStreamCreateWithFlags(&c.lane[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c.laneEv[i], cudaEventDisableTiming)); }
+    const size_t nb = (size_t)((count + kLaneChunks - 1) / kLaneChunks);
+    while (c.offsEv.size() < 2 * nb + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.offsEv.push_back(e); }
+    cudaStream_t sA = c.lane[0], sB = c.lane[1];
+    CK(cudaEventRecord(c.offsEv[2 * nb], c.stream));               // everything queued so far on the main stream
+    CK(cudaStreamWaitEvent(sA, c.offsEv[2 * nb], 0));
+    CK(cudaStreamWaitEvent(sB, c.offsEv[2 * nb], 0));
+    auto evParse = [&](size_t k) { return c.offsEv[2 * k]; };
+    auto evEmit = [&](size_t k) { return c.offsEv[2 * k + 1]; };
     size_t k = 0;
-    for (uint64_t first = firstChunk; first < lastChunk; first += batch, ++k) {
-        const int ln = overlap ? (int)(k % kLanes) : 0;
-        cudaStream_t st = overlap ? c.lane[ln] : c.stream;
-        const size_t so = overlap ? (size_t)ln * kLaneChunks : 0;  // scratch slice of the lane
-        Job job{};
-        job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
-        job.first_chunk = first; job.nchunks = (uint32_t)std::min<uint64_t>(batch, lastChunk - first);
-        job.final_stream = final; job.level = level; job.want_checksums = wantCk;
-        job.cand = c.cand + so * chunk; job.tokA = c.tokA + so * kMaxTokens; job.tokD = c.tokD + so * kMaxTokens;
-        job.hist = c.hist + so * kHistStride; job.codes = c.codes + so; job.state = c.state + so;
-        job.dst = d_dst; job.cap = cap; job.total = c.total; job.ck = c.ck;
-        rc = markStage(c, -1, st); if (rc) return rc;
-        if (level >= 2) {
-            launches += launch_candidates(job, st); rc = markStage(c, ZZGPU_STAGE_CAND, st); if (rc) return rc;
-            launches += launch_parse(job, st); rc = markStage(c, ZZGPU_STAGE_PARSE, st); if (rc) return rc;
-        }
-        if (level == 1) {
-            launches += launch_fixed(job, st); rc = markStage(c, ZZGPU_STAGE_FIXED, st); if (rc) return rc;
-        } else {
-            launches += launch_huffman(job, st); rc = markStage(c, ZZGPU_STAGE_HUFF, st); if (rc) return rc;
-        }
-        if (overlap && k > 0) CK(cudaStreamWaitEvent(st, c.offsEv[k], 0));
-        launches += launch_offsets(job, st); rc = markStage(c, ZZGPU_STAGE_OFFS, st); if (rc) return rc;
-        if (overlap) CK(cudaEventRecord(c.offsEv[k + 1], st));
-        if (level == 1) { launches += launch_gather(job, st); rc = markStage(c, ZZGPU_STAGE_GATHER, st); if (rc) return rc; }
-        else { launches += launch_emit(job, st); rc = markStage(c, ZZGPU_STAGE_EMIT, st); if (rc) return rc; }
-        if (wantCk) { launches += launch_checksums(job, st); rc = markStage(c, ZZGPU_STAGE_CKSUM, st); if (rc) return rc; }
-        if (overlap) CK(cudaEventRecord(c.laneEv[ln], st));
+    for (uint64_t first = firstChunk; first < lastChunk; first += kLaneChunks, ++k) {
+        const Job job = makeJob(c, d_src, n, history, final, d_dst, cap, level, chunk, dict, wantCk, first,
+                                (uint32_t)std::min<uint64_t>(kLaneChunks, lastChunk - first), (k & 1) * (size_t)kLaneChunks);
+        // stream A: candidates as soon as the scratch slice is free, the match kernel once the SMs are
+        if (k >= 2) CK(cudaStreamWaitEvent(sA, evEmit(k - 2), 0));
+        rc = markStage(c, -1, sA); if (rc) return rc;
+        launches += launch_candidates(job, sA); rc = markStage(c, ZZGPU_STAGE_CAND, sA); if (rc) return rc;
+        if (k >= 1) CK(cudaStreamWaitEvent(sA, evEmit(k - 1), 0));
+        rc = markStage(c, -1, sA); if (rc) return rc;
+        launches += launch_parse(job, sA); rc = markStage(c, ZZGPU_STAGE_PARSE, sA); if (rc) return rc;
+        CK(cudaEventRecord(evParse(k), sA));
+        // stream B: back end of the batch
+        CK(cudaStreamWaitEvent(sB, evParse(k), 0));
+        rc = markStage(c, -1, sB); if (rc) return rc;
+        launches += launch_huffman(job, sB); rc = markStage(c, ZZGPU_STAGE_HUFF, sB); if (rc) return rc;
+        launches += launch_offsets(job, sB); rc = markStage(c, ZZGPU_STAGE_OFFS, sB); if (rc) return rc;
+        launches += launch_emit(job, sB); rc = markStage(c, ZZGPU_STAGE_EMIT, sB); if (rc) return rc;
+        if (wantCk) { launches += launch_checksums(job, sB); rc = markStage(c, ZZGPU_STAGE_CKSUM, sB); if (rc) return rc; }
+        CK(cudaEventRecord(evEmit(k), sB));
     }
-    if (overlap) for (int i = 0; i < kLanes && i < (int)k; ++i) CK(cudaStreamWaitEvent(c.stream, c.laneEv[i], 0));
+    CK(cudaStreamWaitEvent(c.stream, evEmit(k - 1), 0));
+    CK(cudaStreamWaitEvent(c.stream, evParse(k - 1), 0));
     CK(cudaGetLastError());
     return ZZGPU_OK;
 }
