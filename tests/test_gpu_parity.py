@@ -192,6 +192,36 @@ def test_device_resident_buffers(zz, oracle):
         assert dst[3: 3 + n2].cpu().numpy().tobytes() == out
 
 
+def test_regressions_found_by_fuzzing(zz, oracle):
+    """tests/golden/regress/*.bin: inputs on which tools/gpu_fuzz.py once found a mismatch (file name carries level,
+    chunk and dictionary size).  fuzz_1_3613: a match of >= 32 bytes whose backward extension is so long that it ends
+    inside the tile of the state it was taken from (R6 territory, lb = 258)."""
+    import re
+    from pathlib import Path
+    files = sorted((Path(__file__).parent / "golden" / "regress").glob("*.bin"))
+    assert files
+    for f in files:
+        m = re.search(r"_l(\d)_c(\d+)_d(\d+)", f.name)
+        level, chunk, dict_size = int(m.group(1)), int(m.group(2)), int(m.group(3))
+        data = f.read_bytes()
+        got, *_ = zz.deflate_raw(data, level=level, chunk=chunk, dict_size=dict_size)
+        assert got == oracle.stream_chunked(data, DEFLATE, level, chunk, dict_size)[0], f.name
+        assert zlib.decompress(got, -15) == data
+        got2, *_ = zz.deflate_raw(data, level=level)
+        assert got2 == oracle.stream_chunked(data, DEFLATE, level)[0], f.name
+
+
+def test_short_fuzz_run(zz):
+    """20 s of tools/gpu_fuzz.py (structured random inputs, both levels, default and odd geometries) against the oracle;
+    longer runs (3 x 240 s, 118 000 cases) were clean after the fix recorded in tests/golden/regress."""
+    import subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "tools" / "gpu_fuzz.py"), "20", "12345"], capture_output=True, text=True, cwd=str(root))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "0 failures" in r.stdout
+
+
 def test_host_buffers_pipelined_path(zz, oracle):
     """Inputs >= 32 MiB on host buffers go through the piece-wise path (H2D / kernels / D2H overlapped on three
     streams); the bytes must not depend on how the call was cut into pieces, nor on the batch-overlap option."""

@@ -266,6 +266,12 @@ constexpr int kBatchCap = kBatch + 128;            // entries of the per-batch a
 constexpr int kTilesCap = kBatchCap / 32;
 constexpr int kSegCap = kTilesCap + 32;
 constexpr int kCapLen = 32;                        // cap of the parallel forward compare
+constexpr int kLongGap = kMaxMatch - kCapLen + 1;   // literal gap from which fwd + backward extension can exceed 258
+
+// F(b) = j + fwd holds while the match length fwd + lb stays below the 258 cap.  A match is resolved exactly (by the
+// orbit chase) when its forward part reached the 32-byte compare cap, or when the pending literal run is so long that the
+// backward extension alone could push fwd + lb over 258 (then the next state is j - lb + 258 < j + fwd).
+__device__ __forceinline__ bool needs_exact(int fwd, int gap) { return fwd >= kCapLen || gap >= kLongGap; }
 constexpr unsigned kNone16 = 0xFFFFu;
 constexpr int kParseSmem = kWinBytes + kBatchCap /*info*/ + 3 * kBatchCap * 2 /*F,E1,E2*/ +
                            (kTilesCap + 4) * (4 + 4 + 2 + 2 + 12) + kSegCap * 2;
@@ -418,10 +424,9 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
     uint16_t* E1 = F + kBatchCap;
     uint16_t* E2 = E1 + kBatchCap;
     unsigned* okbits = reinterpret_cast<unsigned*>(E2 + kBatchCap);
-    unsigned* lazyTok = okbits + (kTilesCap + 4);
-    uint16_t* nzw = reinterpret_cast<uint16_t*>(lazyTok + (kTilesCap + 4));
-    uint16_t* entry = nzw + (kTilesCap + 4);
-    uint16_t* seg = entry + (kTilesCap + 4);
+    unsigned* entry = okbits + (kTilesCap + 4);      // first orbit state inside each tile (atomicMin: a tile can be entered twice)
+    uint16_t* nzw = reinterpret_cast<uint16_t*>(entry + (kTilesCap + 4));
+    uint16_t* seg = nzw + 2 * (kTilesCap + 4);
     // bit per position: usable at distance >= 1 / 2 / 3 from the state (info >= 4 / 3 / 2); okbits is distance >= 4
     unsigned* elig1 = reinterpret_cast<unsigned*>(seg + kSegCap);
     unsigned* elig2 = elig1 + (kTilesCap + 4);
@@ -526,7 +531,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 if (lane == 0) { okbits[idx >> 5] = m4; elig1[idx >> 5] = m1; elig2[idx >> 5] = m2; elig3[idx >> 5] = m3; }
             }
         }
-        for (int t = tid; t < kTilesCap; t += kParseThreads) entry[t] = (uint16_t)kNone16;
+        for (int t = tid; t < kTilesCap; t += kParseThreads) entry[t] = kNone16;
         __syncthreads();
         PHASE_MARK(1);
         // next non-empty bitmap word at or after w
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 }
                 if (b >= B0 && b < E && j >= 0) {
                     const unsigned fwd = (unsigned)info[j - base] - 1u;
-                    f = fwd >= kCapLen ? 1u : (unsigned)j + fwd;
+                    f = needs_exact((int)fwd, j - b) ? 1u : (unsigned)j + fwd;
                 }
             }
             F[t * 32 + lane] = (uint16_t)f;
@@ -643,8 +648,10 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 if (maxBack > 0) { lb = coop_back(win, wb + j, wb + p, lane); if (lb > maxBack) lb = maxBack; }
                 int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
                 const int ms = j - lb;
-                if (lane == 0) lazyTok[(x - base) >> 5] = (uint32_t)ms | ((uint32_t)m << 16);
                 b = ms + m;
+                // F becomes exact for this state.  With a long backward part the match can end inside x's own tile
+                // (b = j - lb + 258 may be as small as j): the tile's expansion then simply walks on from b.
+                if (lane == 0) F[x - base] = (uint16_t)(b < 65535 ? b : 65535);
                 newSeg = true;
             }
             if (lane == 0) { ps.npre = npre; ps.nseg = nseg; ps.finalB = finalB; }
@@ -657,7 +664,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             const int superEnd = base + (((b - base) >> 10) + 1) * 1024;
             for (;;) {
                 const int t = (b - base) >> 5;
-                entry[t] = (uint16_t)b;
+                atomicMin(&entry[t], (unsigned)b);
                 const unsigned e = E1[b - base];
                 if (e == 0 || (int)e < base + (t + 1) * 32 || (int)e >= superEnd || (int)e >= E) break;
                 b = (int)e;
@@ -703,16 +710,18 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 const int j = probe_next(info, okbits, nzw, ntiles, base, x);
                 const int d = patched_cand(cand, &ps, npatch, j);
                 uint32_t tok;
-                if (f == 1) {
-                    tok = lazyTok[tid];
-                } else {
+                {
                     const int fwd = (int)info[j - base] - 1;
                     int limit = j - x;                                     // pending literals (encoder.cpp:404)
                     { const int room = j - d + g.pre; if (room < limit) limit = room; }
                     if (limit > kMaxMatch) limit = kMaxMatch;
                     const int lb = back_upto(win, wb + j, wb + j - d, limit);
-                    int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
-                    tok = (uint32_t)(j - lb) | ((uint32_t)m << 16);
+                    const int ms = j - lb;
+                    // matches of 32 bytes or more were measured exactly by the orbit chase, which left the exact next
+                    // state in F: their length is the distance from the match start to that state
+                    int m = needs_exact(fwd, j - x) ? (int)f - ms : fwd + lb;
+                    if (m > kMaxMatch) m = kMaxMatch;
+                    tok = (uint32_t)ms | ((uint32_t)m << 16);
                 }
                 tokA[out] = tok; tokD[out] = (uint16_t)d; ++out;
                 if (f == 1 || (int)f >= tileEnd) break;
