@@ -6,10 +6,12 @@ compute entry point returns ZZGPU_E_NO_DEVICE (raised here as ZzGpuError) withou
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libzzflate_b200.so"
+# ZZFLATE_B200_LIB selects a diagnostic build of the same library (e.g. -DZZ_PHASE_TIMING); never a fallback
+LIB_PATH = Path(os.environ.get("ZZFLATE_B200_LIB") or (PKG_DIR / "libzzflate_b200.so"))
 
 OK, E_NO_DEVICE, E_CUDA, E_ARG, E_CAPACITY, E_NOMEM = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1

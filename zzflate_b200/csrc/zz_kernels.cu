@@ -160,6 +160,53 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
         const unsigned* sw = reinterpret_cast<const unsigned*>(stage[buf]);
         const int phase = (int)(reinterpret_cast<uintptr_t>(base0 + q0) & 3);
         const int tileEnd = min(q0 + kCandTile, qEnd);
+        // Fast path: a full tile of positions that are all probed and inserted (no priming, no chunk start, no tail).
+        // Four steps (128 positions) are in flight at once: their hashes are independent, the four exchanges are issued
+        // back to back (shared-memory operations of one warp complete in program order, so step u+1 sees the slots as
+        // step u left them) and the ascending-order check is made once for the group.  If any lane received a position
+        // above its own, the slots the group touched are restored from the pre-group values the lanes hold (exactly one
+        // lane per touched slot received a position below the group) and the group is redone step by step with explicit
+        // same-hash group resolution.
+        if (q0 > 0 && q0 + kCandTile <= qEnd && ((unsigned)q0 & startMask) != 0) {
+            const int ob = phase + lane;
+            const unsigned* swl = sw + (ob >> 2);
+            const int sh = (ob & 3) * 8;
+            uint16_t* outp = candOut + q0 + lane;
+            for (int g4 = 0; g4 < kCandTile / 128; ++g4) {
+                const int qs = q0 + g4 * 128;
+                unsigned h[4]; int old[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned v = __funnelshift_r(swl[g4 * 32 + u * 8], swl[g4 * 32 + u * 8 + 1], sh) & 0xFFFFFFu;
+                    h[u] = hash3(v);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) old[u] = atomicExch(&table[h[u]], qs + u * 32 + lane);
+                const bool bad = old[0] > qs + lane || old[1] > qs + 32 + lane || old[2] > qs + 64 + lane || old[3] > qs + 96 + lane;
+                if (__ballot_sync(0xffffffffu, bad)) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (old[u] < qs) table[h[u]] = old[u];
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int pre = table[h[u]];
+                        const unsigned grp = __match_any_sync(0xffffffffu, h[u]);
+                        const unsigned lower = grp & ltMask;
+                        old[u] = lower ? qs + u * 32 + 31 - __clz(lower) : pre;
+                        __syncwarp();
+                        if ((grp >> lane) == 1u) table[h[u]] = qs + u * 32 + lane;
+                        __syncwarp();
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int d = qs + u * 32 + lane - old[u];
+                    outp[g4 * 128 + u * 32] = (uint16_t)(d < kMaxDistance ? d : 0);
+                }
+            }
+            buf ^= 1;
+            continue;
+        }
 #pragma unroll 2
         for (int qs = q0; qs < tileEnd; qs += 32) {
             const int q = qs + lane;
@@ -611,6 +658,12 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         if (warp == 0) {
             int b = B0, finalB = B0, npre = 0, nseg = 0;
             const int tokBase = ps.ntok;
+#ifdef ZZ_PHASE_TIMING
+            long long tSub = clock64();
+#define SUB_MARK(i) do { if (lane == 0) { const long long n_ = clock64(); atomicAdd(&g_phaseCycles[i], (unsigned long long)(n_ - tSub)); tSub = n_; } } while (0)
+#else
+#define SUB_MARK(i) do { } while (0)
+#endif
             if (B0 < E) {
                 const unsigned inf = info[B0 - base];
                 if (inf >= 5) {                           // first probe of the batch: j == backRefEnd, no backward room
@@ -622,6 +675,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 }
             }
             bool newSeg = true;
+            SUB_MARK(9);
             for (;;) {
 #ifdef ZZ_PHASE_TIMING
                 if (lane == 0) atomicAdd(&g_phaseCycles[15], 1ull);
@@ -633,8 +687,11 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 const unsigned e = E2[r];
                 // E2 is complete for every state (P3), so: beyond the super tile (or the batch) = plain hop,
                 // 0 = the orbit ends inside a tile, anything else = the state where it meets a long match
-                if ((int)e >= base + ((r >> 10) + 1) * 1024 || (int)e >= E) { b = (int)e; newSeg = true; continue; }
+                if ((int)e >= base + ((r >> 10) + 1) * 1024 || (int)e >= E) { b = (int)e; newSeg = true; SUB_MARK(10); continue; }
                 if (e == 0) { finalB = -1; break; }       // ends inside a tile: the tile reports the last state
+#ifdef ZZ_PHASE_TIMING
+                if (lane == 0) atomicAdd(&g_phaseCycles[12], 1ull);
+#endif
                 // long match at state x = e: exact lengths
                 const int x = (int)e;
                 const int j = probe_next(info, okbits, nzw, ntiles, base, x);
@@ -653,6 +710,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 // (b = j - lb + 258 may be as small as j): the tile's expansion then simply walks on from b.
                 if (lane == 0) F[x - base] = (uint16_t)(b < 65535 ? b : 65535);
                 newSeg = true;
+                SUB_MARK(11);
             }
             if (lane == 0) { ps.npre = npre; ps.nseg = nseg; ps.finalB = finalB; }
         }
@@ -673,7 +731,8 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         __syncthreads();
         PHASE_MARK(6);
 
-        // ---- P5: tiles expand their part of the orbit into tokens ----
+        // ---- P5: tiles list the orbit states they hold (each state yields one token), then the tokens of the batch are
+        //      expanded token-parallel: the candidate loads overlap and the token stores are coalesced ----
         unsigned cnt = 0;
         if (tid < ntiles) {
             const unsigned e = entry[tid];
@@ -700,32 +759,40 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             wsum[lane] = v;
         }
         __syncthreads();
+        uint16_t* stateList = E2;                                    // E2 is dead after the chase
         if (cnt) {
-            int out = ps.ntok + ps.npre + (int)((warp ? wsum[warp - 1] : 0) + inc - cnt);
+            int out = (int)((warp ? wsum[warp - 1] : 0) + inc - cnt);
             const int tileEnd = base + (tid + 1) * 32;
             int x = (int)entry[tid];
             for (;;) {
                 const unsigned f = F[x - base];
                 if (f == 0) break;
-                const int j = probe_next(info, okbits, nzw, ntiles, base, x);
-                const int d = patched_cand(cand, &ps, npatch, j);
-                uint32_t tok;
-                {
-                    const int fwd = (int)info[j - base] - 1;
-                    int limit = j - x;                                     // pending literals (encoder.cpp:404)
-                    { const int room = j - d + g.pre; if (room < limit) limit = room; }
-                    if (limit > kMaxMatch) limit = kMaxMatch;
-                    const int lb = back_upto(win, wb + j, wb + j - d, limit);
-                    const int ms = j - lb;
-                    // matches of 32 bytes or more were measured exactly by the orbit chase, which left the exact next
-                    // state in F: their length is the distance from the match start to that state
-                    int m = needs_exact(fwd, j - x) ? (int)f - ms : fwd + lb;
-                    if (m > kMaxMatch) m = kMaxMatch;
-                    tok = (uint32_t)ms | ((uint32_t)m << 16);
-                }
-                tokA[out] = tok; tokD[out] = (uint16_t)d; ++out;
+                stateList[out++] = (uint16_t)x;
                 if (f == 1 || (int)f >= tileEnd) break;
                 x = (int)f;
+            }
+        }
+        __syncthreads();
+        {
+            const int nbt = (int)wsum[31];
+            const int outBase = ps.ntok + ps.npre;
+            for (int t = tid; t < nbt; t += kParseThreads) {
+                const int x = stateList[t];
+                const unsigned f = F[x - base];
+                const int j = probe_next(info, okbits, nzw, ntiles, base, x);
+                const int d = patched_cand(cand, &ps, npatch, j);
+                const int fwd = (int)info[j - base] - 1;
+                int limit = j - x;                                     // pending literals (encoder.cpp:404)
+                { const int room = j - d + g.pre; if (room < limit) limit = room; }
+                if (limit > kMaxMatch) limit = kMaxMatch;
+                const int lb = back_upto(win, wb + j, wb + j - d, limit);
+                const int ms = j - lb;
+                // matches of 32 bytes or more were measured exactly by the orbit chase, which left the exact next
+                // state in F: their length is the distance from the match start to that state
+                int m = needs_exact(fwd, j - x) ? (int)f - ms : fwd + lb;
+                if (m > kMaxMatch) m = kMaxMatch;
+                tokA[outBase + t] = (uint32_t)ms | ((uint32_t)m << 16);
+                tokD[outBase + t] = (uint16_t)d;
             }
         }
         __syncthreads();
@@ -1512,7 +1579,7 @@ void dump_phase_cycles()
     static const char* names[9] = { "window", "P1 info", "nzw", "P2 F+E1", "P3 E2", "P4 chase", "P4b mark", "P5 tokens", "hist" };
     unsigned long long tot = 0; for (int i = 0; i < 9; ++i) tot += h[i];
     for (int i = 0; i < 9; ++i) fprintf(stderr, "phase %-10s %6.2f%%  %llu\n", names[i], 100.0 * h[i] / (tot ? tot : 1), h[i]);
-    fprintf(stderr, "orbit hops %llu\n", h[15]);
+    fprintf(stderr, "orbit hops %llu; chase cycles: first probe %llu, plain hops %llu, long matches %llu (%llu of them)\n", h[15], h[9], h[10], h[11], h[12]);
     memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_phaseCycles, h, sizeof h);
 }
 #endif
