@@ -312,6 +312,9 @@ constexpr int kParseThreads = 1024;
 constexpr int kBatchCap = kBatch + 128;            // entries of the per-batch arrays (tile-aligned base + slack)
 constexpr int kTilesCap = kBatchCap / 32;
 constexpr int kSegCap = kTilesCap + 32;
+constexpr int kSuperShift = 9;                     // super tile = 16 tiles = 512 states: one per warp and batch
+constexpr int kSuperStates = 1 << kSuperShift;
+constexpr int kSuperTiles = kSuperStates / 32;
 constexpr int kCapLen = 32;                        // cap of the parallel forward compare
 constexpr int kLongGap = kMaxMatch - kCapLen + 1;   // literal gap from which fwd + backward extension can exceed 258
 
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         const int B0 = pos + 1;                          // FirstPass: backRefEnd = j = startPos + 1
         const int base = B0 & ~31;
         const int ntiles = (E - base + 31) >> 5;
-        const int nsuper = (ntiles + 31) >> 5;
+        const int nsuper = (ntiles + kSuperTiles - 1) / kSuperTiles;
 
         // ---- P0: candidate distances of the batch, staged through the (still unused) E2 array so that the
         //      global loads are issued back to back instead of one per loop iteration of P1 ----
@@ -594,7 +597,10 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         //      Values: 0 = no further match in the batch; a state inside the tile = the orbit meets a long match
         //      there (F == 1 marks such states); otherwise the first iterate beyond the tile.  A match advances
         //      the state by >= 4, so 3 rounds of pointer jumping (8 hops) cover a 32-state tile.
-        for (int t = warp; t < ntiles; t += nwarps) {
+        for (int sp = warp; sp < nsuper; sp += nwarps) {
+          const int superEnd = base + (sp + 1) * kSuperStates;
+          int tLast = sp * kSuperTiles + kSuperTiles - 1; if (tLast >= ntiles) tLast = ntiles - 1;
+          for (int t = tLast; t >= sp * kSuperTiles; --t) {
             const int tileStart = base + t * 32, tileEnd = tileStart + 32;
             const int b = tileStart + lane;
             unsigned f = 0;
@@ -634,24 +640,17 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 if (e >= 2 && (int)e < tileEnd && !lz) e = e2;
             }
             E1[t * 32 + lane] = (uint16_t)e;
+            // E2 = where the orbit leaves the super tile (kSuperTiles tiles).  The warp walks the super tile's tiles from the
+            // last to the first: a state whose tile exit lands on a later tile of the same super tile inherits that state's
+            // (already final) super-tile exit, so every state is touched once and no separate pass is needed.
+            unsigned fin = e;
+            if (e >= 2 && (int)e < superEnd && (int)e < E && (int)e >= tileEnd && F[(int)e - base] != 1) fin = E2[(int)e - base];
+            E2[t * 32 + lane] = (uint16_t)fin;
+            __syncwarp();
+          }
         }
         __syncthreads();
         PHASE_MARK(3);
-        // ---- P3: same for super tiles of 32 tiles.  One warp per super tile walks its tiles from the last to the
-        //      first; a state whose tile exit lands on a later tile of the same super tile inherits that state's
-        //      (already final) super-tile exit, so every state is touched once.
-        for (int sp = warp; sp < nsuper; sp += nwarps) {
-            const int superEnd = base + (sp + 1) * 1024;
-            int tLast = sp * 32 + 31; if (tLast >= ntiles) tLast = ntiles - 1;
-            for (int t = tLast; t >= sp * 32; --t) {
-                const unsigned e = E1[t * 32 + lane];
-                unsigned fin = e;
-                if (e >= 2 && (int)e < superEnd && (int)e < E && (int)e >= base + (t + 1) * 32 && F[(int)e - base] != 1) fin = E2[(int)e - base];
-                E2[t * 32 + lane] = (uint16_t)fin;
-                __syncwarp();
-            }
-        }
-        __syncthreads();
         PHASE_MARK(4);
 
         // ---- P4: follow the orbit super tile by super tile (warp 0; lanes cooperate on long matches) ----
@@ -687,7 +686,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 const unsigned e = E2[r];
                 // E2 is complete for every state (P3), so: beyond the super tile (or the batch) = plain hop,
                 // 0 = the orbit ends inside a tile, anything else = the state where it meets a long match
-                if ((int)e >= base + ((r >> 10) + 1) * 1024 || (int)e >= E) { b = (int)e; newSeg = true; SUB_MARK(10); continue; }
+                if ((int)e >= base + ((r >> kSuperShift) + 1) * kSuperStates || (int)e >= E) { b = (int)e; newSeg = true; SUB_MARK(10); continue; }
                 if (e == 0) { finalB = -1; break; }       // ends inside a tile: the tile reports the last state
 #ifdef ZZ_PHASE_TIMING
                 if (lane == 0) atomicAdd(&g_phaseCycles[12], 1ull);
@@ -719,7 +718,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         // ---- P4b: every segment marks the tiles it enters ----
         if (tid < ps.nseg) {
             int b = seg[tid];
-            const int superEnd = base + (((b - base) >> 10) + 1) * 1024;
+            const int superEnd = base + (((b - base) >> kSuperShift) + 1) * kSuperStates;
             for (;;) {
                 const int t = (b - base) >> 5;
                 atomicMin(&entry[t], (unsigned)b);
