@@ -657,12 +657,6 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         if (warp == 0) {
             int b = B0, finalB = B0, npre = 0, nseg = 0;
             const int tokBase = ps.ntok;
-#ifdef ZZ_PHASE_TIMING
-            long long tSub = clock64();
-#define SUB_MARK(i) do { if (lane == 0) { const long long n_ = clock64(); atomicAdd(&g_phaseCycles[i], (unsigned long long)(n_ - tSub)); tSub = n_; } } while (0)
-#else
-#define SUB_MARK(i) do { } while (0)
-#endif
             if (B0 < E) {
                 const unsigned inf = info[B0 - base];
                 if (inf >= 5) {                           // first probe of the batch: j == backRefEnd, no backward room
@@ -673,24 +667,31 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                     b = B0 + fwd; npre = 1;
                 }
             }
-            bool newSeg = true;
-            SUB_MARK(9);
+            // The hop is a dependent shared-memory load per super tile and sits on the kernel's critical path (every other
+            // warp waits), so it is written with explicit shared addresses: ld.shared, compare, branch.
+            const unsigned aE2 = (unsigned)__cvta_generic_to_shared(E2) - 2u * (unsigned)base;   // &E2[b - base] = aE2 + 2 b
+            const unsigned aSeg = (unsigned)__cvta_generic_to_shared(seg);
             for (;;) {
-#ifdef ZZ_PHASE_TIMING
-                if (lane == 0) atomicAdd(&g_phaseCycles[15], 1ull);
-#endif
-                finalB = b;
-                if (b >= E) break;
-                if (newSeg) { if (lane == 0) seg[nseg] = (uint16_t)b; ++nseg; newSeg = false; }
-                const int r = b - base;
-                const unsigned e = E2[r];
-                // E2 is complete for every state (P3), so: beyond the super tile (or the batch) = plain hop,
-                // 0 = the orbit ends inside a tile, anything else = the state where it meets a long match
-                if ((int)e >= base + ((r >> kSuperShift) + 1) * kSuperStates || (int)e >= E) { b = (int)e; newSeg = true; SUB_MARK(10); continue; }
+                // every iteration starts a new segment (a super tile is entered / a long match was resolved)
+                unsigned e = 0;
+                bool done = false;
+                for (;;) {
+                    finalB = b;
+                    if (b >= E) { done = true; break; }
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(aSeg + 2u * (unsigned)nseg), "h"((unsigned short)b) : "memory");
+                    ++nseg;
+                    unsigned short ev;
+                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ev) : "r"(aE2 + 2u * (unsigned)b) : "memory");
+                    e = ev;
+                    // E2 is complete for every state, so: beyond the super tile (or the batch) = plain hop,
+                    // 0 = the orbit ends inside a tile, anything else = the state where it meets a long match
+                    int lim = base + (((b - base) | (kSuperStates - 1)) + 1); if (lim > E) lim = E;
+                    if ((int)e < lim) break;
+                    b = (int)e;
+                }
+                if (done) break;
                 if (e == 0) { finalB = -1; break; }       // ends inside a tile: the tile reports the last state
-#ifdef ZZ_PHASE_TIMING
-                if (lane == 0) atomicAdd(&g_phaseCycles[12], 1ull);
-#endif
+
                 // long match at state x = e: exact lengths
                 const int x = (int)e;
                 const int j = probe_next(info, okbits, nzw, ntiles, base, x);
@@ -708,8 +709,6 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 // F becomes exact for this state.  With a long backward part the match can end inside x's own tile
                 // (b = j - lb + 258 may be as small as j): the tile's expansion then simply walks on from b.
                 if (lane == 0) F[x - base] = (uint16_t)(b < 65535 ? b : 65535);
-                newSeg = true;
-                SUB_MARK(11);
             }
             if (lane == 0) { ps.npre = npre; ps.nseg = nseg; ps.finalB = finalB; }
         }
@@ -1578,7 +1577,7 @@ void dump_phase_cycles()
     static const char* names[9] = { "window", "P1 info", "nzw", "P2 F+E1", "P3 E2", "P4 chase", "P4b mark", "P5 tokens", "hist" };
     unsigned long long tot = 0; for (int i = 0; i < 9; ++i) tot += h[i];
     for (int i = 0; i < 9; ++i) fprintf(stderr, "phase %-10s %6.2f%%  %llu\n", names[i], 100.0 * h[i] / (tot ? tot : 1), h[i]);
-    fprintf(stderr, "orbit hops %llu; chase cycles: first probe %llu, plain hops %llu, long matches %llu (%llu of them)\n", h[15], h[9], h[10], h[11], h[12]);
+
     memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_phaseCycles, h, sizeof h);
 }
 #endif
