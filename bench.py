@@ -221,14 +221,14 @@ def main():
         out_len, _, _, st = device_step()
     barrier()
     sampler.mark_begin()
-    dev_ms, stage_ms, launches = 0.0, [0.0] * 8, 0
-    stage_n = [0] * 8
+    dev_ms, stage_ms, launches = 0.0, [0.0] * len(_lib.STAGES), 0
+    stage_n = [0] * len(_lib.STAGES)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         out_len, _, _, st = device_step()
         dev_ms += st.device_ms
         launches += st.kernel_launches
-        for i in range(8):
+        for i in range(len(_lib.STAGES)):
             stage_ms[i] += st.stage_ms[i]; stage_n[i] += st.stage_launches[i]
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -271,7 +271,7 @@ def main():
     peak, peak_src = measured_peaks()
     # dominant kernel (rank 0's stage times)
     names = _lib.STAGES
-    dom = max(range(8), key=lambda i: stage_ms[i])
+    dom = max(range(len(_lib.STAGES)), key=lambda i: stage_ms[i])
     dom_avg_ms = stage_ms[dom] / max(stage_n[dom], 1)
     chunks_per_launch = ((nbytes + CHUNK - 1) // CHUNK) / max(stage_n[dom] / args.steps, 1)
     alg_bytes = chunks_per_launch * CHUNK * (1.0 + ratio)            # 1 read + r written per input byte
@@ -287,7 +287,7 @@ def main():
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": config, "ratio": round(ratio, 5),
             "wall_ms_per_step": round(wall_ms / args.steps, 3),
-            "stage_ms_per_step": {names[i]: round(stage_ms[i] / args.steps, 3) for i in range(8) if stage_n[i]},
+            "stage_ms_per_step": {names[i]: round(stage_ms[i] / args.steps, 3) for i in range(len(_lib.STAGES)) if stage_n[i]},
 
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,

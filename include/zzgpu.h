@@ -54,6 +54,8 @@ enum { ZZGPU_MEM_HOST = 0, ZZGPU_MEM_DEVICE = 1 };
 #define ZZGPU_MAX_CHUNK     65536u
 #define ZZGPU_MAX_DICT      32768u
 
+#define ZZGPU_NSTAGES 10
+
 /* Per-call statistics (all optional outputs). */
 typedef struct zzgpu_stats {
     uint64_t chunks;          /* chunks encoded */
@@ -64,12 +66,12 @@ typedef struct zzgpu_stats {
     float total_ms;           /* CUDA-event time including H2D / D2H copies when buffers are on the host */
     uint64_t h2d_bytes, d2h_bytes;
     /* CUDA-event time per pipeline stage, summed over the call's batches (ZZGPU_STAGE_*) */
-    float stage_ms[8];
-    uint32_t stage_launches[8];
+    float stage_ms[ZZGPU_NSTAGES];
+    uint32_t stage_launches[ZZGPU_NSTAGES];
 } zzgpu_stats;
 
 enum { ZZGPU_STAGE_CAND = 0, ZZGPU_STAGE_PARSE = 1, ZZGPU_STAGE_HUFF = 2, ZZGPU_STAGE_OFFS = 3, ZZGPU_STAGE_EMIT = 4,
-       ZZGPU_STAGE_CKSUM = 5, ZZGPU_STAGE_FIXED = 6, ZZGPU_STAGE_GATHER = 7 };
+       ZZGPU_STAGE_CKSUM = 5, ZZGPU_STAGE_FIXED = 6, ZZGPU_STAGE_GATHER = 7, ZZGPU_STAGE_INFO = 8 };
 
 /* Select the device used by the calling thread's subsequent calls (default: current CUDA device).
  * Creates the per-device context (stream, scratch) lazily.  Returns ZZGPU_E_NO_DEVICE without a GPU. */

@@ -30,10 +30,10 @@ class Stats(C.Structure):
         ("chunks", C.c_uint64), ("stored_chunks", C.c_uint64), ("matches", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("device_ms", C.c_float), ("total_ms", C.c_float),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-        ("stage_ms", C.c_float * 8), ("stage_launches", C.c_uint32 * 8),
+        ("stage_ms", C.c_float * 10), ("stage_launches", C.c_uint32 * 10),
     ]
 
-STAGES = ["cand", "parse", "huff", "offs", "emit", "cksum", "fixed", "gather"]
+STAGES = ["cand", "parse", "huff", "offs", "emit", "cksum", "fixed", "gather", "info", "spare"]
 
 
 # every symbol include/zzgpu.h declares; tests check that the library exports all of them

@@ -33,7 +33,7 @@ struct Ctx {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     uint32_t slots = 0;
     uint32_t slotChunk = 0;
-    uint16_t* cand = nullptr; uint32_t* tokA = nullptr; uint16_t* tokD = nullptr; uint32_t* hist = nullptr;
+    uint16_t* cand = nullptr; uint8_t* info = nullptr; uint32_t* tokA = nullptr; uint16_t* tokD = nullptr; uint32_t* hist = nullptr;
     ChunkCodes* codes = nullptr; ChunkState* state = nullptr;
     uint64_t* total = nullptr;              // device [4]
     uint64_t* hTotal = nullptr;             // pinned [4]
@@ -69,8 +69,8 @@ int fail(int status, const char* what, cudaError_t e = cudaSuccess)
 
 void freeScratch(Ctx& c)
 {
-    cudaFree(c.cand); cudaFree(c.tokA); cudaFree(c.tokD); cudaFree(c.hist); cudaFree(c.codes); cudaFree(c.state);
-    c.cand = nullptr; c.tokA = nullptr; c.tokD = nullptr; c.hist = nullptr; c.codes = nullptr; c.state = nullptr;
+    cudaFree(c.cand); cudaFree(c.info); cudaFree(c.tokA); cudaFree(c.tokD); cudaFree(c.hist); cudaFree(c.codes); cudaFree(c.state);
+    c.cand = nullptr; c.info = nullptr; c.tokA = nullptr; c.tokD = nullptr; c.hist = nullptr; c.codes = nullptr; c.state = nullptr;
     c.slots = 0;
 }
 
@@ -109,6 +109,7 @@ int ensureScratch(Ctx& c, uint32_t slots, uint32_t chunk)
     if (c.slots >= slots && c.slotChunk >= chunk) return ZZGPU_OK;
     freeScratch(c);
     CK(cudaMalloc(&c.cand, (size_t)slots * chunk * sizeof(uint16_t)));
+    CK(cudaMalloc(&c.info, (size_t)slots * chunk));
     CK(cudaMalloc(&c.tokA, (size_t)slots * kMaxTokens * sizeof(uint32_t)));
     CK(cudaMalloc(&c.tokD, (size_t)slots * kMaxTokens * sizeof(uint16_t)));
     CK(cudaMalloc(&c.hist, (size_t)slots * kHistStride * sizeof(uint32_t)));
@@ -247,7 +248,7 @@ Job makeJob(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, u
     job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
     job.first_chunk = first; job.nchunks = count;
     job.final_stream = final; job.level = level; job.want_checksums = wantCk;
-    job.cand = c.cand + so * chunk; job.tokA = c.tokA + so * kMaxTokens; job.tokD = c.tokD + so * kMaxTokens;
+    job.cand = c.cand + so * chunk; job.info = c.info + so * chunk; job.tokA = c.tokA + so * kMaxTokens; job.tokD = c.tokD + so * kMaxTokens;
     job.hist = c.hist + so * kHistStride; job.codes = c.codes + so; job.state = c.state + so;
     job.dst = d_dst; job.cap = cap; job.total = c.total; job.ck = c.ck;
     return job;
@@ -274,6 +275,7 @@ int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final,
             rc = markStage(c, -1, st); if (rc) return rc;
             if (level >= 2) {
                 launches += launch_candidates(job, st); rc = markStage(c, ZZGPU_STAGE_CAND, st); if (rc) return rc;
+                launches += launch_info(job, st); rc = markStage(c, ZZGPU_STAGE_INFO, st); if (rc) return rc;
                 launches += launch_parse(job, st); rc = markStage(c, ZZGPU_STAGE_PARSE, st); if (rc) return rc;
             }
             if (level == 1) {
@@ -308,6 +310,7 @@ int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final,
         if (k >= 2) CK(cudaStreamWaitEvent(sA, evEmit(k - 2), 0));
         rc = markStage(c, -1, sA); if (rc) return rc;
         launches += launch_candidates(job, sA); rc = markStage(c, ZZGPU_STAGE_CAND, sA); if (rc) return rc;
+        launches += launch_info(job, sA); rc = markStage(c, ZZGPU_STAGE_INFO, sA); if (rc) return rc;
         if (k >= 1) CK(cudaStreamWaitEvent(sA, evEmit(k - 1), 0));
         rc = markStage(c, -1, sA); if (rc) return rc;
         launches += launch_parse(job, sA); rc = markStage(c, ZZGPU_STAGE_PARSE, sA); if (rc) return rc;
@@ -615,7 +618,7 @@ int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int final, in
         cudaEventElapsedTime(&stats->total_ms, c.ev[0], c.ev[3]);
         if (h2d + d2h > 0) {
             stats->device_ms = 0;                    // host buffers: kernels interleave with copies; sum the stages
-            for (int i = 0; i < 8; ++i) stats->device_ms += stats->stage_ms[i];
+            for (int i = 0; i < ZZGPU_NSTAGES; ++i) stats->device_ms += stats->stage_ms[i];
         } else {
             cudaEventElapsedTime(&stats->device_ms, c.ev[1], c.ev[2]);
         }

@@ -286,6 +286,125 @@ __device__ __forceinline__ unsigned long long ld8(const uint8_t* win, int o)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K-INFO : per-position match info, parse independent (the compare part of FirstPass, encoder.cpp:391-403).
+//
+//   info[j] = 0                         position j cannot start a match (no candidate, or fewer than 4 bytes agree
+//                                       around j even with the backward extension)
+//           = 1 + min(fwd, 32)          otherwise; fwd = bytes that agree forwards between j and its hash candidate
+//
+// A position whose forward part is shorter than 4 is usable only if the candidate supplies the missing bytes
+// backwards.  One CTA handles a piece of 16 384 positions of one chunk with the 32 KiB before the piece
+// in shared memory (four CTAs per SM, no barrier after the window load); the candidate gathers are the cost.
+// K-MATCH masks the batch edges and recomputes the few positions whose candidate changes with the parse.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCapLen = 32;                        // cap of the parallel forward compare
+constexpr int kInfoPiece = 16384;
+constexpr int kInfoThreads = 256;
+constexpr int kInfoBack = kMaxDistance + 16;        // bytes kept before the piece (candidate + 4 bytes backwards)
+constexpr int kInfoSmem = 16 + 16 + kInfoBack + kInfoPiece + 64 + 32;
+
+// forward match length beyond the first 4 bytes, capped at kCapLen - 4 (oj, op already advanced by 4)
+__device__ __forceinline__ int fwd_more(const uint8_t* win, int oj, int op)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned long long x = ld8(win, oj + 8 * k) ^ ld8(win, op + 8 * k);
+        const unsigned xl = (unsigned)x, xh = (unsigned)(x >> 32);
+        if (xl) return 8 * k + ((__ffs(xl) - 1) >> 3);
+        if (xh) return 8 * k + 4 + ((__ffs(xh) - 1) >> 3);
+    }
+    const unsigned x1 = ld4(win, oj + 24) ^ ld4(win, op + 24);
+    return x1 ? 24 + ((__ffs(x1) - 1) >> 3) : kCapLen - 4;
+}
+
+// info of one position from a shared-memory window (position i at win[wb + i]); pre = real history before the chunk
+__device__ __forceinline__ unsigned info_of(const uint8_t* win, int wb, int j, int d, int pre)
+{
+    if (d == 0) return 0u;
+    const unsigned* w32 = reinterpret_cast<const unsigned*>(win);
+    // bytes [j-4, j+4) and [p-4, p+4) from three aligned words each: one funnel shift gives the 4 bytes after the
+    // position, one the 4 bytes before it
+    const int oj = wb + j, op = oj - d;
+    const unsigned* wj = w32 + (oj >> 2);
+    const unsigned* wp = w32 + (op >> 2);
+    const int sj = (oj & 3) * 8, sp = (op & 3) * 8;
+    const unsigned j0 = wj[0], p0 = wp[0];
+    const unsigned x = __funnelshift_r(j0, wj[1], sj) ^ __funnelshift_r(p0, wp[1], sp);
+    const int fwd = x ? ((__ffs(x) - 1) >> 3) : 4 + fwd_more(win, oj + 4, op + 4);
+    bool ok = fwd >= 4;
+    if (!ok) {
+        const unsigned y = __funnelshift_r(wj[-1], j0, sj) ^ __funnelshift_r(wp[-1], p0, sp);
+        int back = y ? (__clz(y) >> 3) : 4;
+        const int room = j - d + pre;                     // bytes of real history before the candidate (R4 clamp)
+        if (back > room) back = room;
+        ok = fwd + back >= 4;
+    }
+    return ok ? (unsigned)fwd + 1u : 0u;
+}
+
+__global__ void __launch_bounds__(kInfoThreads, 4) k_info(Job job, int piecesPerChunk)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const unsigned slot = blockIdx.x / (unsigned)piecesPerChunk;
+    const int piece = (int)(blockIdx.x % (unsigned)piecesPerChunk);
+    const Geom g = chunk_geom(job, slot);
+    const int P0 = piece * kInfoPiece;
+    int P1 = P0 + kInfoPiece; if (P1 > g.t0) P1 = g.t0;       // positions >= t0 are never probed (encoder.cpp:222)
+    if (P0 >= P1) return;
+    const uint8_t* chunk0 = job.src + g.off;
+    const int wb = 16 + kInfoBack + (int)(reinterpret_cast<uintptr_t>(chunk0) & 15) - P0;    // position i at smem[wb + i]
+    int lo = P0 - kInfoBack; if (lo < -g.pre) lo = -g.pre;
+    int hi = P1 + 48; if (hi > g.n) hi = g.n;
+    load_window(smem, wb, chunk0, lo, hi, hi + 16);
+    __syncthreads();
+    const uint16_t* cand = job.cand + (size_t)slot * job.chunk;
+    uint8_t* out = job.info + (size_t)slot * job.chunk;
+    const int tid = threadIdx.x;
+    const unsigned* w32 = reinterpret_cast<const unsigned*>(smem);
+    const int ph8 = (wb & 3) * 8;                       // j0 is a multiple of 4: every thread sees the same byte phase
+    // Four consecutive positions per thread: their own bytes [j0-4, j0+8) come from four aligned words (lanes read
+    // consecutive words: conflict free), the candidate side is two gathered words per position (all eight gathers are
+    // issued before the first compare), a third one only where bytes are missing forwards.
+    for (int j0 = P0 + 4 * tid; j0 < P1; j0 += 4 * kInfoThreads) {
+        const uint2 dd = __ldg(reinterpret_cast<const uint2*>(cand + j0));
+        int d[4] = { (int)(dd.x & 0xFFFFu), (int)(dd.x >> 16), (int)(dd.y & 0xFFFFu), (int)(dd.y >> 16) };
+        if (j0 == 0) d[0] = 0;                          // position 0 is never probed (encoder.cpp:384)
+        if (j0 + 3 >= P1) {
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (j0 + k >= P1) d[k] = 0;
+        }
+        const int oj0 = wb + j0;
+        const unsigned* wj = w32 + (oj0 >> 2);
+        const unsigned W0 = wj[-1], W1 = wj[0], W2 = wj[1], W3 = wj[2];
+        const unsigned V0 = __funnelshift_r(W0, W1, ph8), V1 = __funnelshift_r(W1, W2, ph8), V2 = __funnelshift_r(W2, W3, ph8);
+        unsigned pw0[4], pw1[4]; int op[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            op[k] = oj0 + k - d[k];
+            const unsigned* wp = w32 + (op[k] >> 2);
+            pw0[k] = wp[0]; pw1[k] = wp[1];
+        }
+        unsigned packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned x = __funnelshift_r(V1, V2, 8 * k) ^ __funnelshift_r(pw0[k], pw1[k], op[k] * 8);
+            if (d[k] == 0) x = 1u;
+            const int fwd = x ? ((__ffs(x) - 1) >> 3) : 4 + fwd_more(smem, oj0 + k + 4, op[k] + 4);
+            bool ok = fwd >= 4;
+            if (!ok) {
+                const unsigned y = __funnelshift_r(V0, V1, 8 * k) ^ __funnelshift_r(w32[(op[k] >> 2) - 1], pw0[k], op[k] * 8);
+                int back = y ? (__clz(y) >> 3) : 4;
+                const int room = j0 + k - d[k] + g.pre;   // bytes of real history before the candidate (R4 clamp)
+                if (back > room) back = room;
+                ok = fwd + back >= 4;
+            }
+            if (ok && d[k]) packed |= (unsigned)(fwd + 1) << (8 * k);
+        }
+        *reinterpret_cast<unsigned*>(out + j0) = packed;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K-MATCH : one CTA per chunk.
 //
 // The reference's greedy parse (FirstPass, encoder.cpp:375-440) is a sequential walk, but it factors into
@@ -315,7 +434,6 @@ constexpr int kSegCap = kTilesCap + 32;
 constexpr int kSuperShift = 9;                     // super tile = 16 tiles = 512 states: one per warp and batch
 constexpr int kSuperStates = 1 << kSuperShift;
 constexpr int kSuperTiles = kSuperStates / 32;
-constexpr int kCapLen = 32;                        // cap of the parallel forward compare
 constexpr int kLongGap = kMaxMatch - kCapLen + 1;   // literal gap from which fwd + backward extension can exceed 258
 
 // F(b) = j + fwd holds while the match length fwd + lb stays below the 258 cap.  A match is resolved exactly (by the
@@ -363,20 +481,6 @@ __device__ __forceinline__ int patched_cand(const uint16_t* cand, const ParseSha
     int d = __ldg(cand + j);
     if (npatch) for (int k = 0; k < npatch; ++k) if (ps->patchJ[k] == j) d = ps->patchD[k];
     return d;
-}
-
-// forward match length beyond the first 4 bytes, capped at kCapLen - 4 (oj, op already advanced by 4)
-__device__ __forceinline__ int fwd_more(const uint8_t* win, int oj, int op)
-{
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const unsigned long long x = ld8(win, oj + 8 * k) ^ ld8(win, op + 8 * k);
-        const unsigned xl = (unsigned)x, xh = (unsigned)(x >> 32);
-        if (xl) return 8 * k + ((__ffs(xl) - 1) >> 3);
-        if (xh) return 8 * k + 4 + ((__ffs(xh) - 1) >> 3);
-    }
-    const unsigned x1 = ld4(win, oj + 24) ^ ld4(win, op + 24);
-    return x1 ? 24 + ((__ffs(x1) - 1) >> 3) : kCapLen - 4;
 }
 
 // exact forward match length (<= 258), all 32 lanes cooperate (remain(), encoder.cpp:81-90)
@@ -527,53 +631,30 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         const int ntiles = (E - base + 31) >> 5;
         const int nsuper = (ntiles + kSuperTiles - 1) / kSuperTiles;
 
-        // ---- P0: candidate distances of the batch, staged through the (still unused) E2 array so that the
-        //      global loads are issued back to back instead of one per loop iteration of P1 ----
+        // ---- P1: per-position match info of the batch (computed by K-INFO), masked to the batch's probe range
+        //      [B0, E); the positions whose candidate changed with the parse are recomputed here ----
         {
             const int lim = ntiles * 32 + 64;
-            for (int idx0 = tid; idx0 < lim; idx0 += 4 * kParseThreads) {
-                unsigned short dv[4];
+            const uint8_t* ginfo = job.info + (size_t)slot * job.chunk + base;          // 32-byte aligned
+            for (int idx = tid * 4; idx < lim; idx += 4 * kParseThreads) {
+                unsigned v = __ldg(reinterpret_cast<const unsigned*>(ginfo + idx));
+                const int j = base + idx;
+                if (j < B0 || j + 3 >= E) {
+                    unsigned m = 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int idx = idx0 + u * kParseThreads, j = base + idx;
-                    dv[u] = (idx < lim && j >= B0 && j < E) ? __ldg(cand + j) : (unsigned short)0;
+                    for (int k = 0; k < 4; ++k) if (j + k >= B0 && j + k < E) m |= 0xFFu << (8 * k);
+                    v &= m;
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int idx = idx0 + u * kParseThreads; if (idx < lim) E2[idx] = dv[u]; }
+                *reinterpret_cast<unsigned*>(info + idx) = v;
             }
             __syncthreads();
-            if (tid < npatch) { const int pj = ps.patchJ[tid]; if (pj >= B0 && pj < E) E2[pj - base] = (uint16_t)ps.patchD[tid]; }
+            if (tid < npatch) {
+                const int pj = ps.patchJ[tid];
+                if (pj >= B0 && pj < E) info[pj - base] = (uint8_t)info_of(win, wb, pj, ps.patchD[tid], g.pre);
+            }
             __syncthreads();
-        }
-        // ---- P1: per-position match info (parse independent) ----
-        {
-            const int lim = ntiles * 32 + 64;
-            const unsigned* w32 = reinterpret_cast<const unsigned*>(win);
             for (int idx = tid; idx < lim; idx += kParseThreads) {
-                const int j = base + idx;
-                const int d = E2[idx];
-                unsigned inf = 0;
-                if (d) {
-                    // bytes [j-4, j+4) and [p-4, p+4) from three aligned words each: one funnel shift gives the
-                    // 4 bytes after the position, one the 4 bytes before it
-                    const int oj = wb + j, op = oj - d;
-                    const unsigned* wj = w32 + (oj >> 2);
-                    const unsigned* wp = w32 + (op >> 2);
-                    const int sj = (oj & 3) * 8, sp = (op & 3) * 8;
-                    const unsigned j0 = wj[0], p0 = wp[0];
-                    const unsigned x = __funnelshift_r(j0, wj[1], sj) ^ __funnelshift_r(p0, wp[1], sp);
-                    int fwd = x ? ((__ffs(x) - 1) >> 3) : 4 + fwd_more(win, oj + 4, op + 4);
-                    bool ok = fwd >= 4;
-                    if (!ok) {
-                        const unsigned y = __funnelshift_r(wj[-1], j0, sj) ^ __funnelshift_r(wp[-1], p0, sp);
-                        int back = y ? (__clz(y) >> 3) : 4;
-                        const int room = j - d + g.pre;  // bytes of real history before the candidate (R4 clamp)
-                        if (back > room) back = room;
-                        ok = fwd + back >= 4;
-                    }
-                    if (ok) inf = (unsigned)fwd + 1u;
-                }
-                info[idx] = (uint8_t)inf;
+                const unsigned inf = info[idx];
                 const unsigned m4 = __ballot_sync(0xffffffffu, inf != 0);
                 const unsigned m1 = __ballot_sync(0xffffffffu, inf >= 4);
                 const unsigned m2 = __ballot_sync(0xffffffffu, inf >= 3);
@@ -1587,6 +1668,7 @@ cudaError_t configure_kernels()
     cudaError_t e;
     e = cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kParseSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem); if (e) return e;
+    e = cudaFuncSetAttribute(k_info, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfoSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffSmem); if (e) return e;
     static uint32_t tab[4][256];
     uint32_t powL[257], pow1[256];
@@ -1620,6 +1702,13 @@ int launch_candidates(const Job& job, cudaStream_t s)
         if (run > 64) run = 64;
     }
     k_candidates<<<(job.nchunks + run - 1) / run, 32, 0, s>>>(job, run);
+    return 1;
+}
+
+int launch_info(const Job& job, cudaStream_t s)
+{
+    const int ppc = (int)((job.chunk + kInfoPiece - 1) / kInfoPiece);
+    k_info<<<job.nchunks * (unsigned)ppc, kInfoThreads, kInfoSmem, s>>>(job, ppc);
     return 1;
 }
 
