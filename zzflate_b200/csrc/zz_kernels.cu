@@ -427,7 +427,7 @@ __device__ unsigned long long g_phaseCycles[16];
 #else
 #define PHASE_MARK(i) do { } while (0)
 #endif
-constexpr int kParseThreads = 1024;
+constexpr int kParseThreads = 512;               // two CTAs per SM: the serial phases of one overlap the other's parallel phases
 constexpr int kBatchCap = kBatch + 128;            // entries of the per-batch arrays (tile-aligned base + slack)
 constexpr int kTilesCap = kBatchCap / 32;
 constexpr int kSegCap = kTilesCap + 32;
@@ -441,8 +441,19 @@ constexpr int kLongGap = kMaxMatch - kCapLen + 1;   // literal gap from which fw
 // backward extension alone could push fwd + lb over 258 (then the next state is j - lb + 258 < j + fwd).
 __device__ __forceinline__ bool needs_exact(int fwd, int gap) { return fwd >= kCapLen || gap >= kLongGap; }
 constexpr unsigned kNone16 = 0xFFFFu;
-constexpr int kParseSmem = kWinBytes + kBatchCap /*info*/ + 3 * kBatchCap * 2 /*F,E1,E2*/ +
-                           (kTilesCap + 4) * (4 + 4 + 2 + 2 + 12) + kSegCap * 2;
+constexpr int kParseSmem = kBatchCap /*info*/ + 2 * kBatchCap * 2 /*F,E2*/ + kBatchCap /*E1*/ +
+                           (kTilesCap + 4) * (4 + 4 + 2 + 2) + kSegCap * 2 + 16;
+static_assert(2 * (kParseSmem + 1024 + 512) <= 228 * 1024, "two K-MATCH CTAs must fit one SM");
+
+// tile exit packed to a byte: 0 = the orbit ends in the tile, 1..32 = it meets a long match at state tileStart + v - 1,
+// 33..254 = first state beyond the tile at tileEnd + v - 33, 255 = further away (the reader follows F instead)
+__device__ __forceinline__ unsigned e1_pack(unsigned e, int tileStart)
+{
+    if (e == 0u) return 0u;
+    const int rel = (int)e - tileStart;
+    if (rel < 32) return 1u + (unsigned)rel;
+    return rel - 32 <= 221 ? 33u + (unsigned)(rel - 32) : 255u;
+}
 
 struct ParseShared {
     int pos;            // start of the next FirstPass batch
@@ -483,42 +494,104 @@ __device__ __forceinline__ int patched_cand(const uint16_t* cand, const ParseSha
     return d;
 }
 
-// exact forward match length (<= 258), all 32 lanes cooperate (remain(), encoder.cpp:81-90)
-__device__ __forceinline__ int coop_fwd(const uint8_t* win, int oj, int op, int lane)
+// unaligned 8-byte little-endian load from global memory; bytes outside [lo, hi) read as zero
+__device__ __forceinline__ unsigned long long gload8(const uint8_t* p, const uint8_t* lo, const uint8_t* hi)
 {
-    const unsigned long long xa = ld8(win, oj + lane * 8) ^ ld8(win, op + lane * 8);
-    const unsigned mm = __ballot_sync(0xffffffffu, xa != 0);
-    if (mm) {
-        const int src = __ffs(mm) - 1;
-        const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src);
-        return src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint8_t* al = reinterpret_cast<const uint8_t*>(a & ~(uintptr_t)7);
+    if (al >= lo && al + 16 <= hi) {
+        const unsigned long long x = __ldg(reinterpret_cast<const unsigned long long*>(al));
+        const unsigned long long y = __ldg(reinterpret_cast<const unsigned long long*>(al) + 1);
+        const int sh = (int)(a & 7) * 8;
+        return sh ? ((x >> sh) | (y << (64 - sh))) : x;
     }
-    int fwd = 256;
-    if (win[oj + 256] == win[op + 256]) { fwd = 257; if (win[oj + 257] == win[op + 257]) fwd = 258; }
-    return fwd;
+    unsigned long long v = 0;
+    for (int k = 0; k < 8; ++k) if (p + k >= lo && p + k < hi) v |= (unsigned long long)p[k] << (8 * k);
+    return v;
 }
 
-// exact backward match length (<= 258), all 32 lanes cooperate (countMatchBackward, encoder.cpp:92-102)
-__device__ __forceinline__ int coop_back(const uint8_t* win, int oj, int op, int lane)
+
+// unaligned 4-byte little-endian load from global memory; bytes outside [lo, hi) read as zero
+__device__ __forceinline__ unsigned gload4(const uint8_t* p, const uint8_t* lo, const uint8_t* hi)
 {
-    const unsigned long long xb = ld8(win, oj - 8 - lane * 8) ^ ld8(win, op - 8 - lane * 8);
-    const unsigned mm = __ballot_sync(0xffffffffu, xb != 0);
-    if (mm) {
-        const int src = __ffs(mm) - 1;
-        const unsigned long long xs = __shfl_sync(0xffffffffu, xb, src);
-        return src * 8 + (__clzll((long long)xs) >> 3);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint8_t* al = reinterpret_cast<const uint8_t*>(a & ~(uintptr_t)3);
+    if (al >= lo && al + 8 <= hi) {
+        const unsigned x = __ldg(reinterpret_cast<const unsigned*>(al));
+        const unsigned y = __ldg(reinterpret_cast<const unsigned*>(al) + 1);
+        return __funnelshift_r(x, y, (int)(a & 3) * 8);
     }
-    int lb = 256;
-    if (win[oj - 257] == win[op - 257]) { lb = 257; if (win[oj - 258] == win[op - 258]) lb = 258; }
-    return lb;
+    unsigned v = 0;
+    for (int k = 0; k < 4; ++k) if (p + k >= lo && p + k < hi) v |= (unsigned)p[k] << (8 * k);
+    return v;
+}
+
+// The stream bytes K-MATCH still needs (exact lengths of long matches, backward extension of the tokens, literal
+// histogram, the rare patched positions) are read from global memory: pj / pp point at the position and its candidate,
+// [lo, hi) is the readable stream.
+struct Stream { const uint8_t* lo; const uint8_t* hi; };
+
+// info of one position (same definition as K-INFO)
+__device__ int info_of_g(const uint8_t* pj, int d, int room, Stream st)
+{
+    if (d == 0) return 0;
+    const uint8_t* pp = pj - d;
+    int fwd = 0;
+    while (fwd < kCapLen) {
+        const unsigned x = gload4(pj + fwd, st.lo, st.hi) ^ gload4(pp + fwd, st.lo, st.hi);
+        if (x) { fwd += (__ffs(x) - 1) >> 3; break; }
+        fwd += 4;
+    }
+    bool ok = fwd >= 4;
+    if (!ok) {
+        const unsigned y = gload4(pj - 4, st.lo, st.hi) ^ gload4(pp - 4, st.lo, st.hi);
+        int back = y ? (__clz(y) >> 3) : 4;
+        if (back > room) back = room;                    // bytes of real history before the candidate (R4 clamp)
+        ok = fwd + back >= 4;
+    }
+    return ok ? fwd + 1 : 0;
+}
+
+// exact forward and backward match lengths (<= 258 each) of a long match, all 32 lanes cooperate (remain(),
+// countMatchBackward; encoder.cpp:81-102).  Both sides are loaded before the first vote so that the global-memory
+// latency is paid once.
+__device__ __forceinline__ void coop_lengths(const uint8_t* pj, const uint8_t* pp, Stream st, int lane, bool wantBack, int& fwd, int& lb)
+{
+    const unsigned long long xa = gload8(pj + lane * 8, st.lo, st.hi) ^ gload8(pp + lane * 8, st.lo, st.hi);
+    unsigned long long xb = 0;
+    unsigned ta = 1, tb = 1;
+    if (wantBack) xb = gload8(pj - 8 - lane * 8, st.lo, st.hi) ^ gload8(pp - 8 - lane * 8, st.lo, st.hi);
+    if (lane < 2) ta = (unsigned)(gload4(pj + 256 + lane, st.lo, st.hi) ^ gload4(pp + 256 + lane, st.lo, st.hi)) & 0xFFu;
+    if (wantBack && lane < 2) tb = (unsigned)(gload4(pj - 257 - lane, st.lo, st.hi) ^ gload4(pp - 257 - lane, st.lo, st.hi)) & 0xFFu;
+    const unsigned ma = __ballot_sync(0xffffffffu, xa != 0);
+    const unsigned mta = __ballot_sync(0xffffffffu, ta == 0);       // bit 0: byte 256 equal, bit 1: byte 257 equal
+    if (ma) {
+        const int src = __ffs(ma) - 1;
+        const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src);
+        fwd = src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
+    } else {
+        fwd = 256 + ((mta & 1u) ? ((mta & 2u) ? 2 : 1) : 0);
+    }
+    lb = 0;
+    if (wantBack) {
+        const unsigned mb = __ballot_sync(0xffffffffu, xb != 0);
+        const unsigned mtb = __ballot_sync(0xffffffffu, tb == 0);
+        if (mb) {
+            const int src = __ffs(mb) - 1;
+            const unsigned long long xs = __shfl_sync(0xffffffffu, xb, src);
+            lb = src * 8 + (__clzll((long long)xs) >> 3);
+        } else {
+            lb = 256 + ((mtb & 1u) ? ((mtb & 2u) ? 2 : 1) : 0);
+        }
+    }
 }
 
 // single-thread backward match length, at most `limit` bytes (token expansion: limit is the literal gap, mostly <= 3)
-__device__ __forceinline__ int back_upto(const uint8_t* win, int oj, int op, int limit)
+__device__ __forceinline__ int back_upto(const uint8_t* pj, const uint8_t* pp, int limit, Stream st)
 {
     int lb = 0;
     while (lb < limit) {
-        const unsigned y = ld4(win, oj - 4 - lb) ^ ld4(win, op - 4 - lb);
+        const unsigned y = gload4(pj - 4 - lb, st.lo, st.hi) ^ gload4(pp - 4 - lb, st.lo, st.hi);
         const int c = y ? (__clz(y) >> 3) : 4;
         lb += c;
         if (c < 4) break;
@@ -569,22 +642,17 @@ __device__ __forceinline__ void walk_positions(const uint32_t* tokA, int ntok, i
     }
 }
 
-__global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
+__global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* win = smem;
-    uint8_t* info = smem + kWinBytes;
+    uint8_t* info = smem;
     uint16_t* F = reinterpret_cast<uint16_t*>(info + kBatchCap);
-    uint16_t* E1 = F + kBatchCap;
-    uint16_t* E2 = E1 + kBatchCap;
-    unsigned* okbits = reinterpret_cast<unsigned*>(E2 + kBatchCap);
+    uint16_t* E2 = F + kBatchCap;
+    uint8_t* E1 = reinterpret_cast<uint8_t*>(E2 + kBatchCap);        // tile exits, packed to a byte (e1_pack)
+    unsigned* okbits = reinterpret_cast<unsigned*>(E1 + kBatchCap);  // bit per position: usable (info != 0)
     unsigned* entry = okbits + (kTilesCap + 4);      // first orbit state inside each tile (atomicMin: a tile can be entered twice)
     uint16_t* nzw = reinterpret_cast<uint16_t*>(entry + (kTilesCap + 4));
     uint16_t* seg = nzw + 2 * (kTilesCap + 4);
-    // bit per position: usable at distance >= 1 / 2 / 3 from the state (info >= 4 / 3 / 2); okbits is distance >= 4
-    unsigned* elig1 = reinterpret_cast<unsigned*>(seg + kSegCap);
-    unsigned* elig2 = elig1 + (kTilesCap + 4);
-    unsigned* elig3 = elig2 + (kTilesCap + 4);
     __shared__ ParseShared ps;
     __shared__ unsigned wsum[32];
 
@@ -592,7 +660,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
     const Geom g = chunk_geom(job, slot);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kParseThreads >> 5;
     const uint8_t* chunk0 = job.src + g.off;
-    const int wb = kPreCap + (int)(reinterpret_cast<uintptr_t>(chunk0) & 15);
+    const Stream strm = { job.src - job.history, job.src + job.n };
     const uint16_t* cand = job.cand + (size_t)slot * job.chunk;
     uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
     uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
@@ -600,7 +668,6 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
 #ifdef ZZ_PHASE_TIMING
     long long tPhase = clock64();
 #endif
-    load_window(win, wb, chunk0, -g.pre, g.n, g.n + 48);
     if (tid == 0) { ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npatch = 0; ps.fixS = -1; ps.fixJ = 0x7fffffff; }
     __syncthreads();
     PHASE_MARK(0);
@@ -650,16 +717,13 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             __syncthreads();
             if (tid < npatch) {
                 const int pj = ps.patchJ[tid];
-                if (pj >= B0 && pj < E) info[pj - base] = (uint8_t)info_of(win, wb, pj, ps.patchD[tid], g.pre);
+                if (pj >= B0 && pj < E) { const int pd = ps.patchD[tid]; info[pj - base] = (uint8_t)info_of_g(chunk0 + pj, pd, pj - pd + g.pre, strm); }
             }
             __syncthreads();
             for (int idx = tid; idx < lim; idx += kParseThreads) {
                 const unsigned inf = info[idx];
                 const unsigned m4 = __ballot_sync(0xffffffffu, inf != 0);
-                const unsigned m1 = __ballot_sync(0xffffffffu, inf >= 4);
-                const unsigned m2 = __ballot_sync(0xffffffffu, inf >= 3);
-                const unsigned m3 = __ballot_sync(0xffffffffu, inf >= 2);
-                if (lane == 0) { okbits[idx >> 5] = m4; elig1[idx >> 5] = m1; elig2[idx >> 5] = m2; elig3[idx >> 5] = m3; }
+                if (lane == 0) okbits[idx >> 5] = m4;
             }
         }
         for (int t = tid; t < kTilesCap; t += kParseThreads) entry[t] = kNone16;
@@ -680,19 +744,23 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         //      the state by >= 4, so 3 rounds of pointer jumping (8 hops) cover a 32-state tile.
         for (int sp = warp; sp < nsuper; sp += nwarps) {
           const int superEnd = base + (sp + 1) * kSuperStates;
-          int tLast = sp * kSuperTiles + kSuperTiles - 1; if (tLast >= ntiles) tLast = ntiles - 1;
-          for (int t = tLast; t >= sp * kSuperTiles; --t) {
+          const int tFirst = sp * kSuperTiles;
+          int tLast = tFirst + kSuperTiles - 1; if (tLast >= ntiles) tLast = ntiles - 1;
+          // pass A: F and the tile exits; the tiles of the super tile are independent, so their shared-memory
+          // round trips overlap
+#pragma unroll 2
+          for (int t = tFirst; t <= tLast; ++t) {
             const int tileStart = base + t * 32, tileEnd = tileStart + 32;
-            const int b = tileStart + lane;
+            const int r = t * 32 + lane, b = tileStart + lane;
             unsigned f = 0;
             {
-                // probe_next for the 32 states of the tile from the (warp-uniform) eligibility bitmaps:
-                // funnel shifts line bit b+k of the two words covering [tile, tile+64) up with lane b
+                // probe_next for the 32 states of the tile: positions b+1..b+3 need 1..3 bytes backwards less than a
+                // full match (info >= 4 / 3 / 2), from b+4 on any usable position is taken (bitmap)
                 int j = -1;
-                auto bitAt = [](unsigned lo, unsigned hi, int i) { return (((i & 32) ? hi : lo) >> (i & 31)) & 1u; };
-                if (bitAt(elig1[t], elig1[t + 1], lane + 1)) j = b + 1;
-                else if (bitAt(elig2[t], elig2[t + 1], lane + 2)) j = b + 2;
-                else if (bitAt(elig3[t], elig3[t + 1], lane + 3)) j = b + 3;
+                const unsigned i1 = info[r + 1], i2 = info[r + 2], i3 = info[r + 3];
+                if (i1 >= 4) j = b + 1;
+                else if (i2 >= 3) j = b + 2;
+                else if (i3 >= 2) j = b + 3;
                 else {
                     const unsigned low = okbits[t], hiw = okbits[t + 1];
                     const int sh = lane + 4;                                           // first position that needs nothing backwards
@@ -710,20 +778,26 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                     f = needs_exact((int)fwd, j - b) ? 1u : (unsigned)j + fwd;
                 }
             }
-            F[t * 32 + lane] = (uint16_t)f;
+            F[r] = (uint16_t)f;
             const bool myLong = f == 1u;
             unsigned e = myLong ? (unsigned)b : f;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
+            for (int rr = 0; rr < 3; ++rr) {
                 const int src = ((int)e - tileStart) & 31;
                 const unsigned e2 = __shfl_sync(0xffffffffu, e, src);
                 const bool lz = __shfl_sync(0xffffffffu, myLong ? 1 : 0, src) != 0;
                 if (e >= 2 && (int)e < tileEnd && !lz) e = e2;
             }
-            E1[t * 32 + lane] = (uint16_t)e;
-            // E2 = where the orbit leaves the super tile (kSuperTiles tiles).  The warp walks the super tile's tiles from the
-            // last to the first: a state whose tile exit lands on a later tile of the same super tile inherits that state's
-            // (already final) super-tile exit, so every state is touched once and no separate pass is needed.
+            E1[r] = (uint8_t)e1_pack(e, tileStart);
+            E2[r] = (uint16_t)e;                       // tile exit for now; pass B turns it into the super-tile exit
+          }
+          __syncwarp();
+          // pass B: E2 = where the orbit leaves the super tile (kSuperTiles tiles).  The warp walks the super tile's tiles
+          // from the last to the first: a state whose tile exit lands on a later tile of the same super tile inherits that
+          // state's (already final) super-tile exit, so every state is touched once.
+          for (int t = tLast; t >= tFirst; --t) {
+            const int tileEnd = base + (t + 1) * 32;
+            const unsigned e = E2[t * 32 + lane];
             unsigned fin = e;
             if (e >= 2 && (int)e < superEnd && (int)e < E && (int)e >= tileEnd && F[(int)e - base] != 1) fin = E2[(int)e - base];
             E2[t * 32 + lane] = (uint16_t)fin;
@@ -743,7 +817,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 if (inf >= 5) {                           // first probe of the batch: j == backRefEnd, no backward room
                     const int d = patched_cand(cand, &ps, npatch, B0);
                     int fwd = (int)inf - 1;
-                    if (fwd >= kCapLen) fwd = coop_fwd(win, wb + B0, wb + B0 - d, lane);
+                    if (fwd >= kCapLen) { int lbNone; coop_lengths(chunk0 + B0, chunk0 + B0 - d, strm, lane, false, fwd, lbNone); }
                     if (lane == 0) { tokA[tokBase] = (uint32_t)B0 | ((uint32_t)fwd << 16); tokD[tokBase] = (uint16_t)d; }
                     b = B0 + fwd; npre = 1;
                 }
@@ -778,12 +852,12 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 const int j = probe_next(info, okbits, nzw, ntiles, base, x);
                 const int d = patched_cand(cand, &ps, npatch, j);
                 const int p = j - d;
-                const int fwd = coop_fwd(win, wb + j, wb + p, lane);
                 int maxBack = j - x;
                 { const int room = p + g.pre; if (room < maxBack) maxBack = room; }     // R4: clamp at stream start
                 if (maxBack > kMaxMatch) maxBack = kMaxMatch;                            // R6: cap (reference breaks at 259)
-                int lb = 0;
-                if (maxBack > 0) { lb = coop_back(win, wb + j, wb + p, lane); if (lb > maxBack) lb = maxBack; }
+                int fwd, lb;
+                coop_lengths(chunk0 + j, chunk0 + p, strm, lane, maxBack > 0, fwd, lb);
+                if (lb > maxBack) lb = maxBack;
                 int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
                 const int ms = j - lb;
                 b = ms + m;
@@ -796,14 +870,23 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         __syncthreads();
         PHASE_MARK(5);
         // ---- P4b: every segment marks the tiles it enters ----
-        if (tid < ps.nseg) {
-            int b = seg[tid];
+        for (int sg = tid; sg < ps.nseg; sg += kParseThreads) {
+            int b = seg[sg];
             const int superEnd = base + (((b - base) >> kSuperShift) + 1) * kSuperStates;
             for (;;) {
                 const int t = (b - base) >> 5;
+                const int tileEnd = base + (t + 1) * 32;
                 atomicMin(&entry[t], (unsigned)b);
-                const unsigned e = E1[b - base];
-                if (e == 0 || (int)e < base + (t + 1) * 32 || (int)e >= superEnd || (int)e >= E) break;
+                const unsigned v = E1[b - base];
+                if (v <= 32u) break;                       // orbit ends in the tile (0) or meets a long match there (1..32)
+                unsigned e;
+                if (v < 255u) e = (unsigned)tileEnd + (v - 33u);
+                else {                                     // exit too far for the byte: follow F through the tile (no long match on the way)
+                    int x = b;
+                    for (;;) { e = F[x - base]; if (e < 2u || (int)e >= tileEnd) break; x = (int)e; }
+                    if (e < 2u) break;
+                }
+                if ((int)e >= superEnd || (int)e >= E) break;
                 b = (int)e;
             }
         }
@@ -813,10 +896,12 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         // ---- P5: tiles list the orbit states they hold (each state yields one token), then the tokens of the batch are
         //      expanded token-parallel: the candidate loads overlap and the token stores are coalesced ----
         unsigned cnt = 0;
-        if (tid < ntiles) {
-            const unsigned e = entry[tid];
+        const int tBeg = tid < ntiles ? tid : ntiles;
+        const int tEnd = tid == kParseThreads - 1 ? ntiles : (tid + 1 < ntiles ? tid + 1 : ntiles);   // the last thread takes the tail
+        for (int tt = tBeg; tt < tEnd; ++tt) {
+            const unsigned e = entry[tt];
             if (e != kNone16) {
-                const int tileEnd = base + (tid + 1) * 32;
+                const int tileEnd = base + (tt + 1) * 32;
                 int x = (int)e;
                 for (;;) {
                     const unsigned f = F[x - base];
@@ -833,7 +918,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         if (lane == 31) wsum[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            unsigned v = wsum[lane];
+            unsigned v = lane < nwarps ? wsum[lane] : 0u;
             for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
             wsum[lane] = v;
         }
@@ -841,14 +926,18 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
         uint16_t* stateList = E2;                                    // E2 is dead after the chase
         if (cnt) {
             int out = (int)((warp ? wsum[warp - 1] : 0) + inc - cnt);
-            const int tileEnd = base + (tid + 1) * 32;
-            int x = (int)entry[tid];
-            for (;;) {
-                const unsigned f = F[x - base];
-                if (f == 0) break;
-                stateList[out++] = (uint16_t)x;
-                if (f == 1 || (int)f >= tileEnd) break;
-                x = (int)f;
+            for (int tt = tBeg; tt < tEnd; ++tt) {
+                const unsigned e0 = entry[tt];
+                if (e0 == kNone16) continue;
+                const int tileEnd = base + (tt + 1) * 32;
+                int x = (int)e0;
+                for (;;) {
+                    const unsigned f = F[x - base];
+                    if (f == 0) break;
+                    stateList[out++] = (uint16_t)x;
+                    if (f == 1 || (int)f >= tileEnd) break;
+                    x = (int)f;
+                }
             }
         }
         __syncthreads();
@@ -864,7 +953,7 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
                 int limit = j - x;                                     // pending literals (encoder.cpp:404)
                 { const int room = j - d + g.pre; if (room < limit) limit = room; }
                 if (limit > kMaxMatch) limit = kMaxMatch;
-                const int lb = back_upto(win, wb + j, wb + j - d, limit);
+                const int lb = back_upto(chunk0 + j, chunk0 + j - d, limit, strm);
                 const int ms = j - lb;
                 // matches of 32 bytes or more were measured exactly by the orbit chase, which left the exact next
                 // state in F: their length is the distance from the match start to that state
@@ -915,8 +1004,13 @@ __global__ void __launch_bounds__(kParseThreads, 1) k_parse(Job job)
             }
         }
         __syncthreads();
-        for (int pos = tid; pos < g.body; pos += kParseThreads)
-            if (!((cov[pos >> 5] >> (pos & 31)) & 1u)) atomicAdd(&myh[win[wb + pos]], 1u);
+        for (int pos = tid * 4; pos < g.body; pos += 4 * kParseThreads) {
+            const unsigned v = gload4(chunk0 + pos, strm.lo, strm.hi);
+            const unsigned cw = (cov[pos >> 5] >> (pos & 31)) & 0xFu;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (!((cw >> k) & 1u) && pos + k < g.body) atomicAdd(&myh[(v >> (8 * k)) & 0xFFu], 1u);
+        }
     }
     __syncthreads();
     for (int i = tid; i < 316; i += kParseThreads) {
@@ -1393,22 +1487,6 @@ __device__ __forceinline__ unsigned fixed_lit_code(unsigned v, int& len)     // 
     if (v < 256) { len = 9; return __brev(0x190u + (v - 144)) >> 23; }
     if (v < 280) { len = 7; return __brev(v - 256) >> 25; }
     len = 8; return __brev(0xC0u + (v - 280)) >> 24;
-}
-
-// unaligned 8-byte little-endian load from global memory; bytes outside [lo, hi) read as zero
-__device__ __forceinline__ unsigned long long gload8(const uint8_t* p, const uint8_t* lo, const uint8_t* hi)
-{
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint8_t* al = reinterpret_cast<const uint8_t*>(a & ~(uintptr_t)7);
-    if (al >= lo && al + 16 <= hi) {
-        const unsigned long long x = __ldg(reinterpret_cast<const unsigned long long*>(al));
-        const unsigned long long y = __ldg(reinterpret_cast<const unsigned long long*>(al) + 1);
-        const int sh = (int)(a & 7) * 8;
-        return sh ? ((x >> sh) | (y << (64 - sh))) : x;
-    }
-    unsigned long long v = 0;
-    for (int k = 0; k < 8; ++k) if (p + k >= lo && p + k < hi) v |= (unsigned long long)p[k] << (8 * k);
-    return v;
 }
 
 // One warp per chunk.  The level-1 walk inserts only the positions it visits, so candidates depend on the parse;
