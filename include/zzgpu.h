@@ -82,7 +82,8 @@ ZZGPU_API const char* zzgpu_strerror(int status);
 ZZGPU_API const char* zzgpu_last_error(void);
 
 /* Tuning knobs that do not change the produced bytes.  "overlap" (default 0): batches of 4096 chunks on two streams, so
- * that the candidate kernel of batch k+1 runs beside the Huffman / emit / checksum kernels of batch k. */
+ * that the candidate kernel of batch k+1 runs beside the Huffman / emit / checksum kernels of batch k.
+ * "emit" (default 1): 1 = token-parallel bit emission, 0 = the position-range variant (same bytes, kept for A/B runs). */
 ZZGPU_API int zzgpu_set_option(const char* name, int value);
 
 /* Worst-case size of the raw deflate stream for n input bytes (A.6: 65 546 bytes per 65 536-byte chunk at

@@ -678,6 +678,7 @@ int zzgpu_checksums(const uint8_t* src, size_t n, int src_mem, uint32_t adler_st
 int zzgpu_set_option(const char* name, int value)
 {
     if (name && !strcmp(name, "overlap")) { g_overlap = value ? 1 : 0; return ZZGPU_OK; }
+    if (name && !strcmp(name, "emit")) { set_emit_variant(value ? 1 : 0); return ZZGPU_OK; }       // 0: position-range K-EMIT, 1: token-parallel (default)
     return fail(ZZGPU_E_ARG, "unknown option");
 }
 

@@ -1024,24 +1024,23 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-HUFF : one thread per chunk (tie-breaks follow the libstdc++ heap layout, so the tree build is serial)
+// K-HUFF : one warp per chunk.  Tie-breaks follow the libstdc++ heap layout, so the tree build itself is serial
+// (lane 0, everything in shared memory); the loops around it (frequency loads, leaf compaction, sums, canonical
+// codes, copies to global memory) use all lanes.
 // ------------------------------------------------------------------------------------------------
-// Heap entries are packed as frequency << 10 | id and live in shared memory, interleaved by lane
-// ([index][lane], 32 chunks per CTA) so that 32 independent heaps never conflict on a bank.  Comparisons look
-// at the frequency only: ties are decided by the heap layout alone, as in the reference (huffman.cpp:55-63).
-constexpr int kHuffLanes = 32;
+// Heap entries are packed as frequency << 10 | id.  Comparisons look at the frequency only: ties are decided by
+// the heap layout alone, as in the reference (huffman.cpp:55-63).
 #define HF(v) ((v) >> 10)
-#define HS(i) ((i) * kHuffLanes)
 
 __device__ __forceinline__ void heap_push_(unsigned* h, int hole, int top, unsigned v)
 {
     int parent = (hole - 1) / 2;
-    while (hole > top && HF(h[HS(parent)]) > HF(v)) {
-        h[HS(hole)] = h[HS(parent)];
+    while (hole > top && HF(h[parent]) > HF(v)) {
+        h[hole] = h[parent];
         hole = parent;
         parent = (hole - 1) / 2;
     }
-    h[HS(hole)] = v;
+    h[hole] = v;
 }
 
 __device__ __forceinline__ void heap_adjust(unsigned* h, int hole, int len, unsigned v)
@@ -1050,94 +1049,119 @@ __device__ __forceinline__ void heap_adjust(unsigned* h, int hole, int len, unsi
     int child = hole;
     while (child < (len - 1) / 2) {
         child = 2 * (child + 1);
-        const unsigned cr = h[HS(child)], cl = h[HS(child - 1)];
+        const unsigned cr = h[child], cl = h[child - 1];
         unsigned pick = cr;
         if (HF(cr) > HF(cl)) { child--; pick = cl; }
-        h[HS(hole)] = pick;
+        h[hole] = pick;
         hole = child;
     }
     if ((len & 1) == 0 && child == (len - 2) / 2) {
         child = 2 * (child + 1);
-        h[HS(hole)] = h[HS(child - 1)];
+        h[hole] = h[child - 1];
         hole = child - 1;
     }
     heap_push_(h, hole, top, v);
 }
 
-// CalcLengths (huffman.cpp:122-154).  n <= 286.  `heap` points at this lane's shared-memory column.  The heap
-// shrinks by one entry per merge while the tree grows by one node, so node t (tree id n + t) is stored in the slot the
-// heap has just vacated (slot nsym-1-t) as left | right << 10 | depth << 20: heap, tree links and depths share one
-// 286-word column and the latency-critical chain never leaves shared memory.  Leaf depths go straight to `lens`.
-__device__ __noinline__ void calc_lengths(const int* freqs, int n, int maxLength, uint8_t* lens, unsigned* heap)
+__device__ __forceinline__ int warp_sum(int v)
+{
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// CalcLengths (huffman.cpp:122-154), called by the whole warp; freqs, lens and heap are shared-memory arrays of the
+// warp, n <= 286.  The heap shrinks by one entry per merge while the tree grows by one node, so node t (tree id n + t)
+// is stored in the slot the heap has just vacated (slot nsym-1-t) as left | right << 10 | depth << 20: heap, tree
+// links and depths share one 286-word array.  Leaf depths go straight to `lens`.
+__device__ __noinline__ void calc_lengths(const int* freqs, int n, int maxLength, uint8_t* lens, unsigned* heap, int lane)
 {
     int total = 0;
-    for (int i = 0; i < n; ++i) total += freqs[i];
+    for (int i = lane; i < n; i += 32) total += freqs[i];
+    total = warp_sum(total);
+    const unsigned ltMask = (1u << lane) - 1u;
     int minFreq = 0;
     for (;;) {
-        int rn = 0;
-        for (int i = 0; i < n; ++i) {
-            lens[i] = freqs[i] == 0 ? 0 : 1;                        // a used symbol that stays at depth 0 gets length 1
-            if (freqs[i] == 0) continue;
-            const unsigned f = (unsigned)(freqs[i] > minFreq ? freqs[i] : minFreq);
-            heap[HS(rn++)] = (f << 10) | (unsigned)i;
+        int rn = 0;                                              // leaves in symbol order
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const int f = i < n ? freqs[i] : 0;
+            const unsigned m = __ballot_sync(0xffffffffu, f != 0);
+            if (i < n) lens[i] = f ? 1 : 0;                      // a used symbol that stays at depth 0 gets length 1
+            if (f) heap[rn + __popc(m & ltMask)] = ((unsigned)(f > minFreq ? f : minFreq) << 10) | (unsigned)i;
+            rn += __popc(m);
         }
-        const int nsym = rn;
-        if (rn >= 2)
-            for (int parent = (rn - 2) / 2; ; --parent) { heap_adjust(heap, parent, rn, heap[HS(parent)]); if (parent == 0) break; }
-        int tn = n;                                              // tree id of the next internal node
-        while (rn >= 2) {
-            unsigned a, b;
-            if (rn > 1) { const unsigned v = heap[HS(rn - 1)]; heap[HS(rn - 1)] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
-            a = heap[HS(--rn)];
-            if (rn > 1) { const unsigned v = heap[HS(rn - 1)]; heap[HS(rn - 1)] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
-            b = heap[HS(--rn)];
-            const unsigned r = ((HF(a) + HF(b)) << 10) | (unsigned)tn;
-            heap[HS(rn++)] = r;
-            heap_push_(heap, rn - 1, 0, r);
-            heap[HS(rn)] = (a & 1023u) | ((b & 1023u) << 10);       // node tn lives in the slot just vacated (depth 0 for now)
-            ++tn;
-        }
-        // depths, root first: the root is the last node created = slot 1, node t sits in slot nsym-1-t
+        __syncwarp();
         int maxDepth = 0;
-        for (int sl = 1; sl < nsym; ++sl) {
-            const unsigned nd = heap[HS(sl)];
-            const int dd = (int)(nd >> 20) + 1;
-            const int ids[2] = { (int)(nd & 1023u), (int)((nd >> 10) & 1023u) };
+        if (lane == 0) {
+            const int nsym = rn;
+            if (rn >= 2)
+                for (int parent = (rn - 2) / 2; ; --parent) { heap_adjust(heap, parent, rn, heap[parent]); if (parent == 0) break; }
+            int tn = n;                                          // tree id of the next internal node
+            while (rn >= 2) {
+                unsigned a, b;
+                if (rn > 1) { const unsigned v = heap[rn - 1]; heap[rn - 1] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
+                a = heap[--rn];
+                if (rn > 1) { const unsigned v = heap[rn - 1]; heap[rn - 1] = heap[0]; heap_adjust(heap, 0, rn - 1, v); }
+                b = heap[--rn];
+                const unsigned r = ((HF(a) + HF(b)) << 10) | (unsigned)tn;
+                heap[rn++] = r;
+                heap_push_(heap, rn - 1, 0, r);
+                heap[rn] = (a & 1023u) | ((b & 1023u) << 10);   // node tn lives in the slot just vacated (depth 0 for now)
+                ++tn;
+            }
+            // depths, root first: the root is the last node created = slot 1, node t sits in slot nsym-1-t
+            for (int sl = 1; sl < nsym; ++sl) {
+                const unsigned nd = heap[sl];
+                const int dd = (int)(nd >> 20) + 1;
+                const int ids[2] = { (int)(nd & 1023u), (int)((nd >> 10) & 1023u) };
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int id = ids[c];
-                if (id < n) { lens[id] = (uint8_t)dd; if (id != 0 && dd > maxDepth) maxDepth = dd; }   // leaf 0 is not looked at (huffman.cpp:108)
-                else { const int cs = nsym - 1 - (id - n); heap[HS(cs)] = (heap[HS(cs)] & 0xFFFFFu) | ((unsigned)dd << 20); }
+                for (int c = 0; c < 2; ++c) {
+                    const int id = ids[c];
+                    if (id < n) { lens[id] = (uint8_t)dd; if (id != 0 && dd > maxDepth) maxDepth = dd; }   // leaf 0 is not looked at (huffman.cpp:108)
+                    else { const int cs = nsym - 1 - (id - n); heap[cs] = (heap[cs] & 0xFFFFFu) | ((unsigned)dd << 20); }
+                }
             }
         }
+        maxDepth = __shfl_sync(0xffffffffu, maxDepth, 0);
+        __syncwarp();
         if (maxDepth <= maxLength) return;
-        int step = total / (1 << maxLength);
+        const int step = total / (1 << maxLength);
         minFreq += step > 1 ? step : 1;
     }
 }
 
 __device__ __forceinline__ unsigned bit_reverse(unsigned v, int len) { return __brev(v) >> (32 - len); }
 
-// huffman::generate (huffman.h:49-81): canonical codes, bit-reversed.  out[i] = bits | len << 16 (0 if unused)
-__device__ __noinline__ void generate_codes(const uint8_t* lens, int n, uint32_t* out)
+// huffman::generate (huffman.h:49-81): canonical codes, bit-reversed.  out[i] = bits | len << 16 (0 if unused); `out` may
+// be global memory (coalesced stores).  Symbols of one length take consecutive codes in index order: the rank of a
+// symbol among the equal-length symbols of its 32-symbol step comes from __match_any_sync, the running next_code per
+// length lives in `next` (16 words of the warp's shared memory).
+__device__ __noinline__ void generate_codes(const uint8_t* lens, int n, uint32_t* out, unsigned* next, int lane)
 {
-    int blCount[16];
-    for (int i = 0; i < 16; ++i) blCount[i] = 0;
-    for (int i = 0; i < n; ++i) blCount[lens[i]]++;
-    unsigned nextCode[16];
-    unsigned bits = 0;
-    blCount[0] = 0;
-    nextCode[0] = 0;
-    for (int b = 1; b < 16; ++b) { bits = (bits + blCount[b - 1]) << 1; nextCode[b] = bits; }
-    for (int i = 0; i < n; ++i) {
-        const int len = lens[i];
-        if (len == 0) { out[i] = 0; continue; }
-        out[i] = bit_reverse(nextCode[len], len) | ((uint32_t)len << 16);
-        nextCode[len]++;
+    if (lane < 16) next[lane] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) atomicAdd(&next[lens[i]], 1u);
+    __syncwarp();
+    if (lane == 0) {
+        unsigned blPrev = 0, bits = 0;                           // bl_count[0] = 0 (huffman.h:60)
+        for (int b = 1; b < 16; ++b) { bits = (bits + blPrev) << 1; blPrev = next[b]; next[b] = bits; }
+        next[0] = 0;
+    }
+    __syncwarp();
+    const unsigned ltMask = (1u << lane) - 1u;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const int len = i < n ? lens[i] : 0;
+        const unsigned grp = __match_any_sync(0xffffffffu, len);
+        const unsigned code = next[len] + (unsigned)__popc(grp & ltMask);
+        __syncwarp();
+        if ((grp >> lane) == 1u) next[len] += (unsigned)__popc(grp);
+        __syncwarp();
+        if (i < n) out[i] = len ? (bit_reverse(code, len) | ((uint32_t)len << 16)) : 0u;
     }
 }
 
-// FromLengths / AddRecords (huffman.cpp:158-216): records as value | payLoad << 8
+// FromLengths / AddRecords (huffman.cpp:158-216): records as value | payLoad << 8 (one lane; shared-memory arrays)
 __device__ __noinline__ int rle_lengths(const uint8_t* lens, int n, unsigned short* rec, int* freqs19)
 {
     int vn = 0, current = -1, count = 0;
@@ -1176,16 +1200,238 @@ __device__ __forceinline__ int dist_extra_bits(int sym) { return sym < 4 ? 0 : (
 __device__ __forceinline__ uint32_t stored_size(int body)           // WriteUncompressedBlock: <= 65535 bytes + 5 per block
 {
     if (body <= 0) return 0;
-    const int blocks = (body + 0xFFFE) / 0xFFFF;
+    const int blocks = (body + 0xFFFF - 1) / 0xFFFF;
     return (uint32_t)(body + 5 * blocks);
 }
 
-constexpr int kHuffThreads = 32;
-constexpr int kHuffSmem = 286 * kHuffLanes * 4;
+constexpr int kHuffWarps = 4;
+constexpr int kHuffThreads = kHuffWarps * 32;
+
+struct HuffShared {                         // one per warp
+    int freq[316];
+    unsigned heap[288];
+    uint32_t metaCodes[20];
+    int metaF[20];
+    unsigned next[16];
+    unsigned short symRec[288], distRec[32];
+    uint8_t lens[336];
+    uint8_t hdr[kHdrBytes];
+};
 
 __global__ void __launch_bounds__(kHuffThreads) k_huffman(Job job)
 {
-    const unsigned slot = blockIdx.x * kHuffThreads + threadIdx.x;
+    __shared__ __align__(16) HuffShared sh[kHuffWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned slot = blockIdx.x * kHuffWarps + warp;
+    if (slot >= job.nchunks) return;                                 // warp-uniform; the kernel has no CTA barrier
+    HuffShared& w = sh[warp];
+    const Geom g = chunk_geom(job, slot);
+    ChunkState& st = job.state[slot];
+    ChunkCodes& cc = job.codes[slot];
+    const uint32_t tail = g.final ? 0u : 6u;                        // aligning 1-byte stored block (zzflate.cpp:116-120)
+
+    if (job.level == 0 || g.body == 0) {
+        if (lane == 0) {
+            st.block_type = 0; st.hdr_bits = 0; st.total_bits = 0;
+            st.out_bytes = stored_size(g.body) + tail;
+            if (job.level == 0) st.ntok = 0;
+        }
+        return;
+    }
+
+    const uint32_t* hist = job.hist + (size_t)slot * kHistStride;
+    for (int i = lane; i < 316; i += 32) w.freq[i] = (int)hist[i];
+    if (lane < 20) w.metaF[lane] = 0;
+    __syncwarp();
+
+    calc_lengths(w.freq, 286, 15, w.lens, w.heap, lane);
+    generate_codes(w.lens, 286, cc.lit, w.next, lane);
+    int nSym = 0;
+    if (lane == 0) nSym = rle_lengths(w.lens, 286, w.symRec, w.metaF);
+    nSym = __shfl_sync(0xffffffffu, nSym, 0);
+    int bits = 0;
+    for (int i = lane; i < 286; i += 32) bits += w.freq[i] * (w.lens[i] + len_extra_bits(i));
+
+    calc_lengths(w.freq + 286, 30, 15, w.lens + 286, w.heap, lane);
+    generate_codes(w.lens + 286, 30, cc.dist, w.next, lane);
+    int nDist = 0;
+    if (lane == 0) nDist = rle_lengths(w.lens + 286, 30, w.distRec, w.metaF);
+    nDist = __shfl_sync(0xffffffffu, nDist, 0);
+    if (lane < 30) bits += w.freq[286 + lane] * (w.lens[286 + lane] + dist_extra_bits(lane));
+    __syncwarp();
+
+    uint8_t* metaL = w.lens + 316;
+    calc_lengths(w.metaF, 19, 7, metaL, w.heap, lane);
+    generate_codes(metaL, 19, w.metaCodes, w.next, lane);
+    if (lane == 0) w.lens[335] = 0;
+    __syncwarp();
+    for (int i = lane; i < 336 / 4; i += 32)
+        reinterpret_cast<uint32_t*>(cc.lens)[i] = reinterpret_cast<const uint32_t*>(w.lens)[i];
+
+    for (int i = lane; i < nSym + nDist; i += 32) {
+        const int v = (i < nSym ? w.symRec[i] : w.distRec[i - nSym]) & 0xFF;
+        bits += metaL[v] + (v == 16 ? 2 : v == 17 ? 3 : v == 18 ? 7 : 0);
+    }
+    const long long total = 3 + 5 + 5 + 4 + 3 * 19 + (long long)warp_sum(bits);
+    const long long required = (total + 8) / 8;                      // encoder.cpp:269
+    if (required >= g.body) {                                        // UncompressedFallback (encoder.cpp:271-274)
+        if (lane == 0) {
+            st.total_bits = (uint64_t)total;
+            st.block_type = 0; st.hdr_bits = 0;
+            st.out_bytes = stored_size(g.body) + tail;
+        }
+        return;
+    }
+    int hdrBits = 17 + 57;
+    if (lane == 0) {
+        HdrWriter hw; hw.out = w.hdr; hw.acc = 0; hw.used = 0; hw.pos = 0;
+        hw.put(g.final ? 1u : 0u, 1); hw.put(2u, 2);                     // StartBlock (encoder.cpp:143-147)
+        hw.put(29u, 5); hw.put(29u, 5); hw.put(15u, 4);                  // encoder.cpp:283-285
+        for (int i = 0; i < 19; ++i) hw.put(metaL[kOrder[i]], 3);
+        for (int pass = 0; pass < 2; ++pass) {                           // WriteLengths (encoder.cpp:20-35)
+            const unsigned short* rec = pass ? w.distRec : w.symRec;
+            const int cnt = pass ? nDist : nSym;
+            for (int i = 0; i < cnt; ++i) {
+                const int v = rec[i] & 0xFF, pl = rec[i] >> 8;
+                const uint32_t c = w.metaCodes[v];
+                hw.put(c & 0xFFFF, (int)(c >> 16)); hdrBits += (int)(c >> 16);
+                if (v == 16) { hw.put((unsigned)(pl - 3), 2); hdrBits += 2; }
+                else if (v == 17) { hw.put((unsigned)(pl - 3), 3); hdrBits += 3; }
+                else if (v == 18) { hw.put((unsigned)(pl - 11), 7); hdrBits += 7; }
+            }
+        }
+        hw.flush();
+        while (hw.pos & 3) w.hdr[hw.pos++] = 0;
+        st.total_bits = (uint64_t)total;
+        st.block_type = 2;
+        st.hdr_bits = (uint32_t)hdrBits;
+        // dynamic block occupies `total` bits; a non-final chunk appends 3 header bits, pads, then LEN/NLEN + 1 byte
+        st.out_bytes = g.final ? (uint32_t)((total + 7) / 8) : (uint32_t)((total + 3 + 7) / 8) + 5u;
+    }
+    hdrBits = __shfl_sync(0xffffffffu, hdrBits, 0);
+    __syncwarp();
+    for (int i = lane; i < (hdrBits + 31) / 32; i += 32)
+        reinterpret_cast<uint32_t*>(cc.hdr)[i] = reinterpret_cast<const uint32_t*>(w.hdr)[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-HUFF, batch variant: one THREAD per chunk, 32 chunks per CTA.  Same algorithm as the warp-per-chunk kernel above; the
+// heaps of the 32 chunks are interleaved by lane ([index][lane]) so that they never conflict on a bank.  Each lane
+// runs the whole chain serially, so a launch takes ~0.9 ms whatever its size, but all lanes of a warp do useful work:
+// this variant is used for launches large enough to fill the GPU several times over, the warp-per-chunk kernel
+// (half the latency) for the smaller pieces of the host-buffer pipeline.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHuffLanes = 32;
+#define HS(i) ((i) * kHuffLanes)
+
+__device__ __forceinline__ void heap_push_L(unsigned* h, int hole, int top, unsigned v)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > top && HF(h[HS(parent)]) > HF(v)) {
+        h[HS(hole)] = h[HS(parent)];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    h[HS(hole)] = v;
+}
+
+__device__ __forceinline__ void heap_adjustL(unsigned* h, int hole, int len, unsigned v)
+{
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        const unsigned cr = h[HS(child)], cl = h[HS(child - 1)];
+        unsigned pick = cr;
+        if (HF(cr) > HF(cl)) { child--; pick = cl; }
+        h[HS(hole)] = pick;
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        h[HS(hole)] = h[HS(child - 1)];
+        hole = child - 1;
+    }
+    heap_push_L(h, hole, top, v);
+}
+
+// CalcLengths (huffman.cpp:122-154).  n <= 286.  `heap` points at this lane's shared-memory column.  The heap
+// shrinks by one entry per merge while the tree grows by one node, so node t (tree id n + t) is stored in the slot the
+// heap has just vacated (slot nsym-1-t) as left | right << 10 | depth << 20: heap, tree links and depths share one
+// 286-word column and the latency-critical chain never leaves shared memory.  Leaf depths go straight to `lens`.
+__device__ __noinline__ void calc_lengthsL(const int* freqs, int n, int maxLength, uint8_t* lens, unsigned* heap)
+{
+    int total = 0;
+    for (int i = 0; i < n; ++i) total += freqs[i];
+    int minFreq = 0;
+    for (;;) {
+        int rn = 0;
+        for (int i = 0; i < n; ++i) {
+            lens[i] = freqs[i] == 0 ? 0 : 1;                        // a used symbol that stays at depth 0 gets length 1
+            if (freqs[i] == 0) continue;
+            const unsigned f = (unsigned)(freqs[i] > minFreq ? freqs[i] : minFreq);
+            heap[HS(rn++)] = (f << 10) | (unsigned)i;
+        }
+        const int nsym = rn;
+        if (rn >= 2)
+            for (int parent = (rn - 2) / 2; ; --parent) { heap_adjustL(heap, parent, rn, heap[HS(parent)]); if (parent == 0) break; }
+        int tn = n;                                              // tree id of the next internal node
+        while (rn >= 2) {
+            unsigned a, b;
+            if (rn > 1) { const unsigned v = heap[HS(rn - 1)]; heap[HS(rn - 1)] = heap[0]; heap_adjustL(heap, 0, rn - 1, v); }
+            a = heap[HS(--rn)];
+            if (rn > 1) { const unsigned v = heap[HS(rn - 1)]; heap[HS(rn - 1)] = heap[0]; heap_adjustL(heap, 0, rn - 1, v); }
+            b = heap[HS(--rn)];
+            const unsigned r = ((HF(a) + HF(b)) << 10) | (unsigned)tn;
+            heap[HS(rn++)] = r;
+            heap_push_L(heap, rn - 1, 0, r);
+            heap[HS(rn)] = (a & 1023u) | ((b & 1023u) << 10);       // node tn lives in the slot just vacated (depth 0 for now)
+            ++tn;
+        }
+        // depths, root first: the root is the last node created = slot 1, node t sits in slot nsym-1-t
+        int maxDepth = 0;
+        for (int sl = 1; sl < nsym; ++sl) {
+            const unsigned nd = heap[HS(sl)];
+            const int dd = (int)(nd >> 20) + 1;
+            const int ids[2] = { (int)(nd & 1023u), (int)((nd >> 10) & 1023u) };
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int id = ids[c];
+                if (id < n) { lens[id] = (uint8_t)dd; if (id != 0 && dd > maxDepth) maxDepth = dd; }   // leaf 0 is not looked at (huffman.cpp:108)
+                else { const int cs = nsym - 1 - (id - n); heap[HS(cs)] = (heap[HS(cs)] & 0xFFFFFu) | ((unsigned)dd << 20); }
+            }
+        }
+        if (maxDepth <= maxLength) return;
+        int step = total / (1 << maxLength);
+        minFreq += step > 1 ? step : 1;
+    }
+}
+
+// huffman::generate (huffman.h:49-81): canonical codes, bit-reversed.  out[i] = bits | len << 16 (0 if unused)
+__device__ __noinline__ void generate_codesL(const uint8_t* lens, int n, uint32_t* out)
+{
+    int blCount[16];
+    for (int i = 0; i < 16; ++i) blCount[i] = 0;
+    for (int i = 0; i < n; ++i) blCount[lens[i]]++;
+    unsigned nextCode[16];
+    unsigned bits = 0;
+    blCount[0] = 0;
+    nextCode[0] = 0;
+    for (int b = 1; b < 16; ++b) { bits = (bits + blCount[b - 1]) << 1; nextCode[b] = bits; }
+    for (int i = 0; i < n; ++i) {
+        const int len = lens[i];
+        if (len == 0) { out[i] = 0; continue; }
+        out[i] = bit_reverse(nextCode[len], len) | ((uint32_t)len << 16);
+        nextCode[len]++;
+    }
+}
+
+constexpr int kHuffLThreads = 32;
+constexpr int kHuffLSmem = 286 * kHuffLanes * 4;
+
+__global__ void __launch_bounds__(kHuffLThreads) k_huffman_lanes(Job job)
+{
+    const unsigned slot = blockIdx.x * kHuffLThreads + threadIdx.x;
     if (slot >= job.nchunks) return;
     const Geom g = chunk_geom(job, slot);
     ChunkState& st = job.state[slot];
@@ -1213,19 +1459,19 @@ __global__ void __launch_bounds__(kHuffThreads) k_huffman(Job job)
 
     for (int i = 0; i < 19; ++i) metaF[i] = 0;
     for (int i = 0; i < 286; ++i) freq[i] = (int)hist[i];
-    calc_lengths(freq, 286, 15, lens, heap);
-    generate_codes(lens, 286, cc.lit);
+    calc_lengthsL(freq, 286, 15, lens, heap);
+    generate_codesL(lens, 286, cc.lit);
     const int nSym = rle_lengths(lens, 286, symRec, metaF);
     for (int i = 0; i < 286; ++i) bits += (long long)freq[i] * (lens[i] + len_extra_bits(i));
 
     for (int i = 0; i < 30; ++i) freq[i] = (int)hist[286 + i];
-    calc_lengths(freq, 30, 15, lens + 286, heap);
-    generate_codes(lens + 286, 30, cc.dist);
+    calc_lengthsL(freq, 30, 15, lens + 286, heap);
+    generate_codesL(lens + 286, 30, cc.dist);
     const int nDist = rle_lengths(lens + 286, 30, distRec, metaF);
     for (int i = 0; i < 30; ++i) bits += (long long)freq[i] * (lens[286 + i] + dist_extra_bits(i));
 
-    calc_lengths(metaF, 19, 7, metaL, heap);
-    generate_codes(metaL, 19, metaCodes);
+    calc_lengthsL(metaF, 19, 7, metaL, heap);
+    generate_codesL(metaL, 19, metaCodes);
     for (int i = 0; i < 19; ++i) lens[316 + i] = metaL[i];
     lens[335] = 0;
     for (int i = 0; i < 336 / 4; ++i)
@@ -1467,6 +1713,229 @@ __global__ void __launch_bounds__(kEmitThreads, 1) k_emit(Job job)
             const unsigned bp = (q + 3 + 7) >> 3;                   // 3 header bits of the stored block, then pad
             uint8_t* o8 = reinterpret_cast<uint8_t*>(out);
             o8[bp] = 1; o8[bp + 1] = 0; o8[bp + 2] = 0xFE; o8[bp + 3] = 0xFF; o8[bp + 4] = win[wb + g.n - 1];
+            bytes = bp + 5;
+        }
+        if (bytes != st.out_bytes) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 4ull);
+    }
+    __syncthreads();
+    copy_out(D, out, st.out_bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-EMIT, token-parallel variant.  One thread per token (a match with the literal run in front of it), 512 tokens per
+// step: the threads of a step do the same work -- a short literal loop and one match -- instead of walking position
+// ranges with a data-dependent mix of both.  A block scan of the tokens' bit counts gives the write offsets of the step;
+// steps are software pipelined (the next step's tokens are loaded while the current one is emitted).
+// Literal runs longer than kRunCap (always the chunk's tail, which the tokeniser never probes; otherwise only data
+// with few matches) are cut into pieces of 1024 positions that warps sum and emit position-parallel; their piece
+// table lives in the chunk's candidate row, which is dead by now.
+// The output image is assembled in shared memory (no window: literals are read through L1), two CTAs per SM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEmit2Threads = 512;
+constexpr int kRunCap = 32;
+constexpr int kPieceLen = 1024;
+constexpr int kEmit2Smem = kOutWords * 4 + (286 + 259 + 30) * 4;
+
+struct LitPiece { uint32_t begin, end, bits, start; };     // positions [begin, end), their code bits, bit offset of the first
+
+__device__ __forceinline__ void or_bits(unsigned* out, unsigned bitOff, unsigned bits, unsigned n)   // n <= 32
+{
+    const unsigned w = bitOff >> 5, sh = bitOff & 31u;
+    atomicOr(&out[w], bits << sh);
+    if (sh + n > 32u) atomicOr(&out[w + 1], bits >> (32u - sh));
+}
+
+__global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    unsigned* out = reinterpret_cast<unsigned*>(smem);
+    unsigned* litc = out + kOutWords;        // bits | len << 24
+    unsigned* lenc = litc + 286;             // merged length codes (CreateMergedLengthCodes, encoder.cpp:126-133)
+    unsigned* dstc = lenc + 259;
+    __shared__ unsigned wsum[32];
+    __shared__ unsigned sCarry, sPieces;
+
+    const unsigned slot = blockIdx.x;
+    const Geom g = chunk_geom(job, slot);
+    const ChunkState st = job.state[slot];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kEmit2Threads / 32;
+    const uint8_t* chunk0 = job.src + g.off;
+    if (st.out_off + st.out_bytes > job.cap) {                        // never write past the caller's buffer
+        if (tid == 0) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 1ull);
+        return;
+    }
+    uint8_t* D = job.dst + st.out_off;
+
+    if (st.block_type == 0) {
+        // stored blocks of <= 65535 bytes (encoder.cpp:482-502), then the aligning block for non-final chunks
+        int written = 0; unsigned o = 0;
+        while (written < g.body) {
+            const int len = min(g.body - written, 0xFFFF);
+            if (tid == 0) {
+                D[o] = (uint8_t)((g.final && written + len == g.body) ? 1 : 0);
+                D[o + 1] = (uint8_t)len; D[o + 2] = (uint8_t)(len >> 8);
+                D[o + 3] = (uint8_t)~len; D[o + 4] = (uint8_t)((~len) >> 8);
+            }
+            for (int i = tid; i < len; i += kEmit2Threads) D[o + 5 + i] = chunk0[written + i];
+            o += 5 + len; written += len;
+        }
+        if (!g.final && tid == 0) {
+            D[o] = 0; D[o + 1] = 1; D[o + 2] = 0; D[o + 3] = 0xFE; D[o + 4] = 0xFF; D[o + 5] = chunk0[g.n - 1];
+        }
+        return;
+    }
+
+    for (int i = tid; i < kOutWords; i += kEmit2Threads) out[i] = 0;
+    const ChunkCodes& cc = job.codes[slot];
+    for (int i = tid; i < 286; i += kEmit2Threads) { uint32_t c = cc.lit[i]; litc[i] = (c & 0xFFFF) | ((c >> 16) << 24); }
+    for (int i = tid; i < 30; i += kEmit2Threads) { uint32_t c = cc.dist[i]; dstc[i] = (c & 0xFFFF) | ((c >> 16) << 24); }
+    if (tid == 0) { sCarry = st.hdr_bits; sPieces = 0; }
+    __syncthreads();
+    for (int i = tid; i < 259; i += kEmit2Threads) {
+        unsigned v = 0;
+        if (i >= 3) {
+            int eb, ev; const int sym = len_symbol(i, eb, ev);
+            const unsigned c = litc[sym]; const unsigned cl = c >> 24;
+            v = ((c & 0xFFFFFF) | ((unsigned)ev << cl)) | ((cl + eb) << 24);
+        }
+        lenc[i] = v;
+    }
+    // header bit string
+    for (unsigned i = tid; i < (st.hdr_bits + 31) / 32; i += kEmit2Threads) {
+        unsigned v = reinterpret_cast<const uint32_t*>(cc.hdr)[i];
+        const unsigned rem = st.hdr_bits - i * 32;
+        if (rem < 32) v &= (1u << rem) - 1u;
+        atomicOr(&out[i], v);
+    }
+    const uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
+    const uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
+    const int ntok = (int)st.ntok;
+    // scratch in the chunk's candidate row (2 * chunk bytes): piece table, then one reference word per token
+    LitPiece* pieces = reinterpret_cast<LitPiece*>(job.cand + (size_t)slot * job.chunk);
+    uint32_t* tokRef = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(pieces) + ((job.chunk / 2 + 64) & ~15u));
+
+    // token k (0 <= k <= ntok; k == ntok is the tail: literals only): literal run [prevEnd, ms), match (ms, len, d)
+    auto tokenAt = [&](int k, int& prevEnd, int& ms, int& len) {
+        prevEnd = 0; ms = g.body; len = 0;
+        if (k > 0) { const uint32_t t = __ldg(tokA + k - 1); prevEnd = (int)(t & 0xFFFF) + (int)(t >> 16); }
+        if (k < ntok) { const uint32_t t = __ldg(tokA + k); ms = (int)(t & 0xFFFF); len = (int)(t >> 16); }
+    };
+
+    // ---- long literal runs: register pieces ----
+    for (int k = tid; k <= ntok; k += kEmit2Threads) {
+        int prevEnd, ms, len; tokenAt(k, prevEnd, ms, len);
+        const int nlit = ms - prevEnd;
+        if (nlit > kRunCap) {
+            const int cnt = (nlit + kPieceLen - 1) / kPieceLen;
+            const unsigned base = atomicAdd(&sPieces, (unsigned)cnt);
+            tokRef[k] = base | ((unsigned)cnt << 16);
+            for (int i = 0; i < cnt; ++i) {
+                LitPiece pc; pc.begin = (uint32_t)(prevEnd + i * kPieceLen); pc.end = (uint32_t)min(prevEnd + (i + 1) * kPieceLen, ms); pc.bits = 0; pc.start = 0;
+                pieces[base + i] = pc;
+            }
+        }
+    }
+    __syncthreads();
+    const int npieces = (int)sPieces;
+    for (int pi = warp; pi < npieces; pi += nwarps) {
+        const LitPiece pc = pieces[pi];
+        unsigned s = 0;
+        for (unsigned p = pc.begin + lane; p < pc.end; p += 32) s += litc[__ldg(chunk0 + p)] >> 24;
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) pieces[pi].bits = s;
+    }
+    __syncthreads();
+
+    // ---- tokens, 512 per step ----
+    int prevEnd = 0, ms = 0, len = 0; unsigned dist = 0;
+    {
+        const int k = tid;
+        if (k <= ntok) { tokenAt(k, prevEnd, ms, len); if (k < ntok) dist = __ldg(tokD + k); }
+    }
+    for (int k0 = 0; k0 <= ntok; k0 += kEmit2Threads) {
+        const int k = k0 + tid;
+        const bool act = k <= ntok;
+        const int cPrev = prevEnd, cMs = ms, cLen = len; const unsigned cDist = dist;
+        {   // prefetch the next step's token
+            const int kn = k + kEmit2Threads;
+            if (kn <= ntok) { tokenAt(kn, prevEnd, ms, len); if (kn < ntok) dist = __ldg(tokD + kn); }
+        }
+        unsigned litBits = 0, mLo = 0, mHi = 0, mLoN = 0, mHiN = 0;
+        const int nlit = act ? cMs - cPrev : 0;
+        const bool isLong = nlit > kRunCap;
+        unsigned ref = 0;
+        if (act) {
+            if (isLong) {
+                ref = tokRef[k];
+                for (unsigned i = 0; i < (ref >> 16); ++i) litBits += pieces[(ref & 0xFFFFu) + i].bits;
+            } else {
+                for (int p = cPrev; p < cMs; ++p) litBits += litc[__ldg(chunk0 + p)] >> 24;
+            }
+            if (cLen) {
+                const unsigned lc = lenc[cLen];
+                mLo = lc & 0xFFFFFFu; mLoN = lc >> 24;
+                int eb, ev; const int ds = dist_symbol((int)cDist, eb, ev);
+                const unsigned dc = dstc[ds]; const unsigned dl = dc >> 24;
+                mHi = (dc & 0xFFFFFFu) | ((unsigned)ev << dl); mHiN = dl + (unsigned)eb;
+            }
+        }
+        const unsigned mybits = litBits + mLoN + mHiN;
+        unsigned inc = mybits;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        const unsigned carry = sCarry;
+        unsigned before = 0;
+        for (int w = 0; w < nwarps; ++w) { const unsigned v = wsum[w]; if (w < warp) before += v; }
+        unsigned total = 0;
+        for (int w = 0; w < nwarps; ++w) total += wsum[w];
+        const unsigned start = carry + before + inc - mybits;
+        __syncthreads();
+        if (tid == 0) sCarry = carry + total;
+        if (act) {
+            if (isLong) {
+                unsigned o = start;
+                for (unsigned i = 0; i < (ref >> 16); ++i) { LitPiece& pc = pieces[(ref & 0xFFFFu) + i]; pc.start = o; o += pc.bits; }
+                if (cLen) { or_bits(out, o, mLo, mLoN); or_bits(out, o + mLoN, mHi, mHiN); }
+            } else {
+                BitWriter bw; bw.init(out, start);
+                for (int p = cPrev; p < cMs; ++p) { const unsigned c = litc[__ldg(chunk0 + p)]; bw.put(c & 0xFFFFFFu, (int)(c >> 24)); }
+                if (cLen) { bw.put(mLo, (int)mLoN); bw.put(mHi, (int)mHiN); }
+                bw.flush();
+            }
+        }
+    }
+    __syncthreads();
+    // ---- long literal runs: emit, one warp per piece ----
+    for (int pi = warp; pi < npieces; pi += nwarps) {
+        const LitPiece pc = pieces[pi];
+        unsigned off = pc.start;
+        for (unsigned p0 = pc.begin; p0 < pc.end; p0 += 32) {
+            const unsigned p = p0 + lane;
+            unsigned c = 0;
+            if (p < pc.end) c = litc[__ldg(chunk0 + p)];
+            const unsigned n = c >> 24;
+            unsigned incl = n;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (n) or_bits(out, off + incl - n, c & 0xFFFFFFu, n);
+            off += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        unsigned q = sCarry;
+        const unsigned eob = litc[256];
+        or_bits(out, q, eob & 0xFFFFFFu, eob >> 24);
+        q += eob >> 24;
+        if ((unsigned long long)q != st.total_bits)                 // K-HUFF's exact size and K-EMIT must agree
+            atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 2ull);
+        unsigned bytes = (q + 7) >> 3;
+        if (!g.final) {
+            const unsigned bp = (q + 3 + 7) >> 3;                   // 3 header bits of the stored block, then pad
+            uint8_t* o8 = reinterpret_cast<uint8_t*>(out);
+            o8[bp] = 1; o8[bp + 1] = 0; o8[bp + 2] = 0xFE; o8[bp + 3] = 0xFF; o8[bp + 4] = chunk0[g.n - 1];
             bytes = bp + 5;
         }
         if (bytes != st.out_bytes) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 4ull);
@@ -1746,8 +2215,9 @@ cudaError_t configure_kernels()
     cudaError_t e;
     e = cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kParseSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem); if (e) return e;
+    e = cudaFuncSetAttribute(k_huffman_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffLSmem); if (e) return e;
+    e = cudaFuncSetAttribute(k_emit2, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmit2Smem); if (e) return e;
     e = cudaFuncSetAttribute(k_info, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfoSmem); if (e) return e;
-    e = cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffSmem); if (e) return e;
     static uint32_t tab[4][256];
     uint32_t powL[257], pow1[256];
     for (uint32_t i = 0; i < 256; ++i) {
@@ -1801,7 +2271,9 @@ int launch_parse(const Job& job, cudaStream_t s)
 
 int launch_huffman(const Job& job, cudaStream_t s)
 {
-    k_huffman<<<(job.nchunks + kHuffThreads - 1) / kHuffThreads, kHuffThreads, kHuffSmem, s>>>(job);
+    // resident warps of the warp-per-chunk kernel: 13 CTAs of 4 warps per SM (17 KiB of shared memory each)
+    if (job.nchunks <= 148u * 52u) k_huffman<<<(job.nchunks + kHuffWarps - 1) / kHuffWarps, kHuffThreads, 0, s>>>(job);
+    else k_huffman_lanes<<<(job.nchunks + kHuffLThreads - 1) / kHuffLThreads, kHuffLThreads, kHuffLSmem, s>>>(job);
     return 1;
 }
 
@@ -1811,9 +2283,13 @@ int launch_offsets(const Job& job, cudaStream_t s)
     return 1;
 }
 
+static int g_emitVariant = 0;        // 0: position-range walk (k_emit), 1: token-parallel (k_emit2, measured slower: 5.3 vs 5.0 ms/GiB)
+void set_emit_variant(int v) { g_emitVariant = v; }
+
 int launch_emit(const Job& job, cudaStream_t s)
 {
-    k_emit<<<job.nchunks, kEmitThreads, kEmitSmem, s>>>(job);
+    if (g_emitVariant == 0) k_emit<<<job.nchunks, kEmitThreads, kEmitSmem, s>>>(job);
+    else k_emit2<<<job.nchunks, kEmit2Threads, kEmit2Smem, s>>>(job);
     return 1;
 }
 
