@@ -757,10 +757,10 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
                 // probe_next for the 32 states of the tile: positions b+1..b+3 need 1..3 bytes backwards less than a
                 // full match (info >= 4 / 3 / 2), from b+4 on any usable position is taken (bitmap)
                 int j = -1;
-                const unsigned i1 = info[r + 1], i2 = info[r + 2], i3 = info[r + 3];
-                if (i1 >= 4) j = b + 1;
-                else if (i2 >= 3) j = b + 2;
-                else if (i3 >= 2) j = b + 3;
+                // info[r+1..r+3] from two aligned words; one byte-wise compare against the thresholds 4 / 3 / 2
+                const unsigned* iw = reinterpret_cast<const unsigned*>(info) + ((r + 1) >> 2);
+                const unsigned near3 = __vcmpgeu4(__funnelshift_r(iw[0], iw[1], ((r + 1) & 3) * 8), 0xFF020304u) & 0x00FFFFFFu;
+                if (near3) j = b + 1 + ((__ffs(near3) - 1) >> 3);
                 else {
                     const unsigned low = okbits[t], hiw = okbits[t + 1];
                     const int sh = lane + 4;                                           // first position that needs nothing backwards
@@ -779,15 +779,17 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
                 }
             }
             F[r] = (uint16_t)f;
-            const bool myLong = f == 1u;
-            unsigned e = myLong ? (unsigned)b : f;
+            // a state that meets a long match carries kLongFlag: a lane that lands on it inherits "long match at that
+            // state" and stops (flagged values fail the inside-the-tile test).  Tiles start at multiples of 32, so the
+            // lane that holds state e is e & 31, which is what the shuffle takes.
+            constexpr unsigned kLongFlag = 0x80000000u;
+            unsigned e = f == 1u ? ((unsigned)b | kLongFlag) : f;
 #pragma unroll
             for (int rr = 0; rr < 3; ++rr) {
-                const int src = ((int)e - tileStart) & 31;
-                const unsigned e2 = __shfl_sync(0xffffffffu, e, src);
-                const bool lz = __shfl_sync(0xffffffffu, myLong ? 1 : 0, src) != 0;
-                if (e >= 2 && (int)e < tileEnd && !lz) e = e2;
+                const unsigned e2 = __shfl_sync(0xffffffffu, e, (int)e);
+                if (e >= 2u && e < (unsigned)tileEnd) e = e2;
             }
+            e &= ~kLongFlag;
             E1[r] = (uint8_t)e1_pack(e, tileStart);
             E2[r] = (uint16_t)e;                       // tile exit for now; pass B turns it into the super-tile exit
           }
@@ -1005,8 +1007,9 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
         }
         __syncthreads();
         for (int pos = tid * 4; pos < g.body; pos += 4 * kParseThreads) {
-            const unsigned v = gload4(chunk0 + pos, strm.lo, strm.hi);
             const unsigned cw = (cov[pos >> 5] >> (pos & 31)) & 0xFu;
+            if (cw == 0xFu) continue;                                   // four covered positions: nothing to count
+            const unsigned v = gload4(chunk0 + pos, strm.lo, strm.hi);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (!((cw >> k) & 1u) && pos + k < g.body) atomicAdd(&myh[(v >> (8 * k)) & 0xFFu], 1u);
