@@ -718,7 +718,13 @@ int zzgpu_debug_chunk(const uint8_t* src, size_t n, int src_mem, int level, uint
     const size_t slot = (size_t)chunk_index;
     ChunkState st;
     CK(cudaMemcpy(&st, c.state + slot, sizeof st, cudaMemcpyDeviceToHost));
-    if (cand) CK(cudaMemcpy(cand, c.cand + slot * chunk, (size_t)chunk * 2, cudaMemcpyDeviceToHost));
+    if (cand) {
+        // K-EMIT reuses the candidate rows as scratch: run K-CAND again for the tap
+        const Job job = makeJob(c, d_src, n, 0, 1, c.dOut, cap, level, chunk, dict, 0, 0, (uint32_t)nchunks, 0);
+        launch_candidates(job, c.stream);
+        CK(cudaStreamSynchronize(c.stream));
+        CK(cudaMemcpy(cand, c.cand + slot * chunk, (size_t)chunk * 2, cudaMemcpyDeviceToHost));
+    }
     if (n_tokens) *n_tokens = st.ntok;
     if (tokens) {
         const uint32_t cnt = std::min(st.ntok, max_tokens);

@@ -987,6 +987,8 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
     // position-parallel (coalesced window reads) into per-warp private histograms.
     unsigned* hist = reinterpret_cast<unsigned*>(info);            // per-warp private copies (batch arrays are dead)
     unsigned* cov = hist + nwarps * kHistStride;                   // bit per position: covered by a match
+    unsigned* litBase = cov + kMaxChunk / 32;                      // literals before each 32-position word
+    uint8_t* lits = job.info + (size_t)slot * job.chunk;           // the block's literal bytes in order (the info row is dead)
     for (int i = tid; i < nwarps * kHistStride + kMaxChunk / 32; i += kParseThreads) hist[i] = 0;
     __syncthreads();
     {
@@ -1006,13 +1008,45 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
             }
         }
         __syncthreads();
+        // positions at or beyond the block's end are not literals
+        for (int w = tid; w < kMaxChunk / 32; w += kParseThreads) {
+            const int lo = w * 32;
+            if (lo + 32 > g.body) cov[w] |= lo >= g.body ? 0xffffffffu : (0xffffffffu << (g.body - lo));
+        }
+        __syncthreads();
+        {   // exclusive scan of the literal counts per word (four consecutive words per thread)
+            static_assert(kParseThreads * 4 == kMaxChunk / 32, "one pass over the coverage bitmap");
+            const int w0 = tid * 4;
+            unsigned c[4], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { c[k] = (unsigned)__popc(~cov[w0 + k]); sum += c[k]; }
+            unsigned inc = sum;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                unsigned v = lane < nwarps ? wsum[lane] : 0u;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+                wsum[lane] = v;
+            }
+            __syncthreads();
+            unsigned before = (warp ? wsum[warp - 1] : 0u) + inc - sum;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { litBase[w0 + k] = before; before += c[k]; }
+            if (tid == kParseThreads - 1) job.state[slot].nlit = before;
+        }
+        __syncthreads();
+        // literals: histogram, and the literal bytes written out in order for K-EMIT (position -> rank through the
+        // coverage bitmap)
         for (int pos = tid * 4; pos < g.body; pos += 4 * kParseThreads) {
-            const unsigned cw = (cov[pos >> 5] >> (pos & 31)) & 0xFu;
+            const unsigned cword = cov[pos >> 5];
+            const unsigned cw = (cword >> (pos & 31)) & 0xFu;
             if (cw == 0xFu) continue;                                   // four covered positions: nothing to count
             const unsigned v = gload4(chunk0 + pos, strm.lo, strm.hi);
+            unsigned rank = litBase[pos >> 5] + (unsigned)__popc(~cword & ((1u << (pos & 31)) - 1u));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (!((cw >> k) & 1u) && pos + k < g.body) atomicAdd(&myh[(v >> (8 * k)) & 0xFFu], 1u);
+                if (!((cw >> k) & 1u)) { const unsigned b = (v >> (8 * k)) & 0xFFu; atomicAdd(&myh[b], 1u); lits[rank++] = (uint8_t)b; }
         }
     }
     __syncthreads();
@@ -1725,23 +1759,28 @@ __global__ void __launch_bounds__(kEmitThreads, 1) k_emit(Job job)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-EMIT, token-parallel variant.  One thread per token (a match with the literal run in front of it), 512 tokens per
-// step: the threads of a step do the same work -- a short literal loop and one match -- instead of walking position
-// ranges with a data-dependent mix of both.  A block scan of the tokens' bit counts gives the write offsets of the step;
-// steps are software pipelined (the next step's tokens are loaded while the current one is emitted).
-// Literal runs longer than kRunCap (always the chunk's tail, which the tokeniser never probes; otherwise only data
-// with few matches) are cut into pieces of 1024 positions that warps sum and emit position-parallel; their piece
-// table lives in the chunk's candidate row, which is dead by now.
-// The output image is assembled in shared memory (no window: literals are read through L1), two CTAs per SM.
+// K-EMIT, symbol-parallel variant.  The bit stream interleaves two sequences that are each compact in memory: the
+// literals (K-MATCH leaves the literal bytes of the block in order in the chunk's info row) and the matches (the token
+// list).  With l_k = number of literals before match k, the write offsets are
+//     literal i : header + (code bits of literals < i) + (bits of the matches k with l_k <= i)
+//     match k   : header + (code bits of literals < l_k) + (bits of the matches < k)
+// so both are prefix sums over compact arrays, and every lane of a warp does the same work: no walk over positions,
+// no data-dependent mix of literals and matches per thread.
+//   pass A (tokens, 512 per step): match bits, l_k and the match-bit prefix M_k, kept in the chunk's candidate row
+//   pass B (literals, 2048 per step): the matches that sit inside the step scatter their bits onto the literal index
+//           they precede (shared-memory D), one block scan of (literal bits, D) gives all offsets; literals are written,
+//           then the step's matches at header + literal-prefix(l_k) + M_k.
+// The output image is assembled in shared memory; two CTAs per SM.
 // ------------------------------------------------------------------------------------------------
 constexpr int kEmit2Threads = 512;
-constexpr int kRunCap = 32;
-constexpr int kPieceLen = 1024;
-constexpr int kEmit2Smem = kOutWords * 4 + (286 + 259 + 30) * 4;
+constexpr int kLitStep = 4 * kEmit2Threads;           // literals per step of pass B (four per thread)
+constexpr int kMaxLitSteps = kMaxChunk / kLitStep + 2;
+constexpr int kEmit2Smem = kOutWords * 4 + (286 + 259 + 30 + 1) * 4 + (kLitStep + 4) * 4 * 2 + kMaxTokens + 16;
+static_assert((kOutWords * 4 + (286 + 259 + 30 + 1) * 4) % 16 == 0, "D must be 16-byte aligned");
 
-struct LitPiece { uint32_t begin, end, bits, start; };     // positions [begin, end), their code bits, bit offset of the first
+struct TokInfo { uint32_t lit; uint32_t mbits; };      // l_k, M_k
 
-__device__ __forceinline__ void or_bits(unsigned* out, unsigned bitOff, unsigned bits, unsigned n)   // n <= 32
+__device__ __forceinline__ void or_bits(unsigned* out, unsigned bitOff, unsigned bits, unsigned n)   // 1 <= n <= 32
 {
     const unsigned w = bitOff >> 5, sh = bitOff & 31u;
     atomicOr(&out[w], bits << sh);
@@ -1755,8 +1794,12 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
     unsigned* litc = out + kOutWords;        // bits | len << 24
     unsigned* lenc = litc + 286;             // merged length codes (CreateMergedLengthCodes, encoder.cpp:126-133)
     unsigned* dstc = lenc + 259;
-    __shared__ unsigned wsum[32];
-    __shared__ unsigned sCarry, sPieces;
+    unsigned* D = dstc + 30 + 1;             // match bits that precede each literal of the step (16-byte aligned: 65600 + 2304)
+    unsigned* PL = D + kLitStep + 4;         // literal-bit prefix of each literal index of the step
+    uint8_t* MBs = reinterpret_cast<uint8_t*>(PL + kLitStep + 4);      // bits of every match
+    __shared__ unsigned wsumA[32], wsumB[32];
+    __shared__ unsigned sCarryA, sCarryB;
+    __shared__ unsigned tokStart[kMaxLitSteps + 1];
 
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
@@ -1768,7 +1811,7 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
         if (tid == 0) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 1ull);
         return;
     }
-    uint8_t* D = job.dst + st.out_off;
+    uint8_t* Dst = job.dst + st.out_off;
 
     if (st.block_type == 0) {
         // stored blocks of <= 65535 bytes (encoder.cpp:482-502), then the aligning block for non-final chunks
@@ -1776,15 +1819,15 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
         while (written < g.body) {
             const int len = min(g.body - written, 0xFFFF);
             if (tid == 0) {
-                D[o] = (uint8_t)((g.final && written + len == g.body) ? 1 : 0);
-                D[o + 1] = (uint8_t)len; D[o + 2] = (uint8_t)(len >> 8);
-                D[o + 3] = (uint8_t)~len; D[o + 4] = (uint8_t)((~len) >> 8);
+                Dst[o] = (uint8_t)((g.final && written + len == g.body) ? 1 : 0);
+                Dst[o + 1] = (uint8_t)len; Dst[o + 2] = (uint8_t)(len >> 8);
+                Dst[o + 3] = (uint8_t)~len; Dst[o + 4] = (uint8_t)((~len) >> 8);
             }
-            for (int i = tid; i < len; i += kEmit2Threads) D[o + 5 + i] = chunk0[written + i];
+            for (int i = tid; i < len; i += kEmit2Threads) Dst[o + 5 + i] = chunk0[written + i];
             o += 5 + len; written += len;
         }
         if (!g.final && tid == 0) {
-            D[o] = 0; D[o + 1] = 1; D[o + 2] = 0; D[o + 3] = 0xFE; D[o + 4] = 0xFF; D[o + 5] = chunk0[g.n - 1];
+            Dst[o] = 0; Dst[o + 1] = 1; Dst[o + 2] = 0; Dst[o + 3] = 0xFE; Dst[o + 4] = 0xFF; Dst[o + 5] = chunk0[g.n - 1];
         }
         return;
     }
@@ -1793,7 +1836,7 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
     const ChunkCodes& cc = job.codes[slot];
     for (int i = tid; i < 286; i += kEmit2Threads) { uint32_t c = cc.lit[i]; litc[i] = (c & 0xFFFF) | ((c >> 16) << 24); }
     for (int i = tid; i < 30; i += kEmit2Threads) { uint32_t c = cc.dist[i]; dstc[i] = (c & 0xFFFF) | ((c >> 16) << 24); }
-    if (tid == 0) { sCarry = st.hdr_bits; sPieces = 0; }
+    if (tid == 0) { sCarryA = 0; sCarryB = 0; }
     __syncthreads();
     for (int i = tid; i < 259; i += kEmit2Threads) {
         unsigned v = 0;
@@ -1811,124 +1854,120 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
         if (rem < 32) v &= (1u << rem) - 1u;
         atomicOr(&out[i], v);
     }
+    __syncthreads();
     const uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
     const uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
     const int ntok = (int)st.ntok;
-    // scratch in the chunk's candidate row (2 * chunk bytes): piece table, then one reference word per token
-    LitPiece* pieces = reinterpret_cast<LitPiece*>(job.cand + (size_t)slot * job.chunk);
-    uint32_t* tokRef = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(pieces) + ((job.chunk / 2 + 64) & ~15u));
+    const int nlit = (int)st.nlit;
+    const uint8_t* lits = job.info + (size_t)slot * job.chunk;
+    TokInfo* tinfo = reinterpret_cast<TokInfo*>(job.cand + (size_t)slot * job.chunk);    // 8 bytes per token <= 2 * chunk bytes
+    const unsigned hdr = st.hdr_bits;
 
-    // token k (0 <= k <= ntok; k == ntok is the tail: literals only): literal run [prevEnd, ms), match (ms, len, d)
-    auto tokenAt = [&](int k, int& prevEnd, int& ms, int& len) {
-        prevEnd = 0; ms = g.body; len = 0;
-        if (k > 0) { const uint32_t t = __ldg(tokA + k - 1); prevEnd = (int)(t & 0xFFFF) + (int)(t >> 16); }
-        if (k < ntok) { const uint32_t t = __ldg(tokA + k); ms = (int)(t & 0xFFFF); len = (int)(t >> 16); }
+    auto matchCode = [&](int len, unsigned dist, unsigned& lo, unsigned& loN, unsigned& hi, unsigned& hiN) {
+        const unsigned lc = lenc[len];
+        lo = lc & 0xFFFFFFu; loN = lc >> 24;
+        int eb, ev; const int ds = dist_symbol((int)dist, eb, ev);
+        const unsigned dc = dstc[ds]; const unsigned dl = dc >> 24;
+        hi = (dc & 0xFFFFFFu) | ((unsigned)ev << dl); hiN = dl + (unsigned)eb;
     };
 
-    // ---- long literal runs: register pieces ----
-    for (int k = tid; k <= ntok; k += kEmit2Threads) {
-        int prevEnd, ms, len; tokenAt(k, prevEnd, ms, len);
-        const int nlit = ms - prevEnd;
-        if (nlit > kRunCap) {
-            const int cnt = (nlit + kPieceLen - 1) / kPieceLen;
-            const unsigned base = atomicAdd(&sPieces, (unsigned)cnt);
-            tokRef[k] = base | ((unsigned)cnt << 16);
-            for (int i = 0; i < cnt; ++i) {
-                LitPiece pc; pc.begin = (uint32_t)(prevEnd + i * kPieceLen); pc.end = (uint32_t)min(prevEnd + (i + 1) * kPieceLen, ms); pc.bits = 0; pc.start = 0;
-                pieces[base + i] = pc;
-            }
+    // ---- pass A: per token l_k = start - (match bytes before) and M_k = match bits before ----
+    for (int k0 = 0; k0 < ntok; k0 += kEmit2Threads) {
+        const int k = k0 + tid;
+        unsigned mb = 0, len = 0, ms = 0;
+        if (k < ntok) {
+            const uint32_t t = __ldg(tokA + k);
+            ms = t & 0xFFFFu; len = t >> 16;
+            unsigned lo, loN, hi, hiN; matchCode((int)len, __ldg(tokD + k), lo, loN, hi, hiN);
+            mb = loN + hiN;
+            MBs[k] = (uint8_t)mb;
         }
+        unsigned ia = mb, ib = len;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ta; ib += tb; }
+        }
+        if (lane == 31) { wsumA[warp] = ia; wsumB[warp] = ib; }
+        __syncthreads();
+        unsigned beforeA = sCarryA, beforeB = sCarryB, totA = 0, totB = 0;
+        for (int w = 0; w < nwarps; ++w) {
+            const unsigned va = wsumA[w], vb = wsumB[w];
+            if (w < warp) { beforeA += va; beforeB += vb; }
+            totA += va; totB += vb;
+        }
+        if (k < ntok) { TokInfo ti; ti.lit = ms - (beforeB + ib - len); ti.mbits = beforeA + ia - mb; tinfo[k] = ti; }
+        __syncthreads();
+        if (tid == 0) { sCarryA += totA; sCarryB += totB; }
     }
     __syncthreads();
-    const int npieces = (int)sPieces;
-    for (int pi = warp; pi < npieces; pi += nwarps) {
-        const LitPiece pc = pieces[pi];
-        unsigned s = 0;
-        for (unsigned p = pc.begin + lane; p < pc.end; p += 32) s += litc[__ldg(chunk0 + p)] >> 24;
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) pieces[pi].bits = s;
+    // first token of every literal step: tokStart[s] = first k with l_k >= s * kLitStep (l_k never decreases)
+    const int nsteps = nlit / kLitStep + 1;                            // the last step also holds the virtual index nlit
+    if (tid <= nsteps) {
+        int lo = 0, hi = ntok;
+        const unsigned want = (unsigned)tid * kLitStep;
+        if (tid == nsteps) lo = ntok;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (tinfo[mid].lit >= want) hi = mid; else lo = mid + 1; }
+        tokStart[tid] = (unsigned)lo;
     }
+    if (tid == 0) { sCarryA = 0; sCarryB = 0; }                        // now: literal bits / match bits before the step
     __syncthreads();
 
-    // ---- tokens, 512 per step ----
-    int prevEnd = 0, ms = 0, len = 0; unsigned dist = 0;
-    {
-        const int k = tid;
-        if (k <= ntok) { tokenAt(k, prevEnd, ms, len); if (k < ntok) dist = __ldg(tokD + k); }
-    }
-    for (int k0 = 0; k0 <= ntok; k0 += kEmit2Threads) {
-        const int k = k0 + tid;
-        const bool act = k <= ntok;
-        const int cPrev = prevEnd, cMs = ms, cLen = len; const unsigned cDist = dist;
-        {   // prefetch the next step's token
-            const int kn = k + kEmit2Threads;
-            if (kn <= ntok) { tokenAt(kn, prevEnd, ms, len); if (kn < ntok) dist = __ldg(tokD + kn); }
-        }
-        unsigned litBits = 0, mLo = 0, mHi = 0, mLoN = 0, mHiN = 0;
-        const int nlit = act ? cMs - cPrev : 0;
-        const bool isLong = nlit > kRunCap;
-        unsigned ref = 0;
-        if (act) {
-            if (isLong) {
-                ref = tokRef[k];
-                for (unsigned i = 0; i < (ref >> 16); ++i) litBits += pieces[(ref & 0xFFFFu) + i].bits;
-            } else {
-                for (int p = cPrev; p < cMs; ++p) litBits += litc[__ldg(chunk0 + p)] >> 24;
-            }
-            if (cLen) {
-                const unsigned lc = lenc[cLen];
-                mLo = lc & 0xFFFFFFu; mLoN = lc >> 24;
-                int eb, ev; const int ds = dist_symbol((int)cDist, eb, ev);
-                const unsigned dc = dstc[ds]; const unsigned dl = dc >> 24;
-                mHi = (dc & 0xFFFFFFu) | ((unsigned)ev << dl); mHiN = dl + (unsigned)eb;
-            }
-        }
-        const unsigned mybits = litBits + mLoN + mHiN;
-        unsigned inc = mybits;
-        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) wsum[warp] = inc;
+    // ---- pass B: literal steps ----
+    for (int s = 0; s < nsteps; ++s) {
+        const int i0 = s * kLitStep;
+        const int ka = (int)tokStart[s], kb = (int)tokStart[s + 1];
+        for (int i = tid; i < kLitStep + 4; i += kEmit2Threads) D[i] = 0;
         __syncthreads();
-        const unsigned carry = sCarry;
-        unsigned before = 0;
-        for (int w = 0; w < nwarps; ++w) { const unsigned v = wsum[w]; if (w < warp) before += v; }
-        unsigned total = 0;
-        for (int w = 0; w < nwarps; ++w) total += wsum[w];
-        const unsigned start = carry + before + inc - mybits;
+        for (int k = ka + tid; k < kb; k += kEmit2Threads) atomicAdd(&D[tinfo[k].lit - (unsigned)i0], (unsigned)MBs[k]);
         __syncthreads();
-        if (tid == 0) sCarry = carry + total;
-        if (act) {
-            if (isLong) {
-                unsigned o = start;
-                for (unsigned i = 0; i < (ref >> 16); ++i) { LitPiece& pc = pieces[(ref & 0xFFFFu) + i]; pc.start = o; o += pc.bits; }
-                if (cLen) { or_bits(out, o, mLo, mLoN); or_bits(out, o + mLoN, mHi, mHiN); }
-            } else {
-                BitWriter bw; bw.init(out, start);
-                for (int p = cPrev; p < cMs; ++p) { const unsigned c = litc[__ldg(chunk0 + p)]; bw.put(c & 0xFFFFFFu, (int)(c >> 24)); }
-                if (cLen) { bw.put(mLo, (int)mLoN); bw.put(mHi, (int)mHiN); }
-                bw.flush();
-            }
+        const int j0 = 4 * tid, i = i0 + j0;
+        unsigned v = 0;
+        if (i < nlit) v = __ldg(reinterpret_cast<const unsigned*>(lits + i));
+        const uint4 d4 = *reinterpret_cast<const uint4*>(D + j0);
+        unsigned code[4], n[4];
+        const unsigned dd[4] = { d4.x, d4.y, d4.z, d4.w };
+        unsigned sumN = 0, sumD = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned c = i + q < nlit ? litc[(v >> (8 * q)) & 0xFFu] : 0u;
+            code[q] = c & 0xFFFFFFu; n[q] = c >> 24;
+            sumN += n[q]; sumD += dd[q];
         }
-    }
-    __syncthreads();
-    // ---- long literal runs: emit, one warp per piece ----
-    for (int pi = warp; pi < npieces; pi += nwarps) {
-        const LitPiece pc = pieces[pi];
-        unsigned off = pc.start;
-        for (unsigned p0 = pc.begin; p0 < pc.end; p0 += 32) {
-            const unsigned p = p0 + lane;
-            unsigned c = 0;
-            if (p < pc.end) c = litc[__ldg(chunk0 + p)];
-            const unsigned n = c >> 24;
-            unsigned incl = n;
-            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (n) or_bits(out, off + incl - n, c & 0xFFFFFFu, n);
-            off += __shfl_sync(0xffffffffu, incl, 31);
+        unsigned ia = sumN, ib = sumD;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ta; ib += tb; }
         }
+        if (lane == 31) { wsumA[warp] = ia; wsumB[warp] = ib; }
+        __syncthreads();
+        unsigned pn = sCarryA, pd = sCarryB, totA = 0, totB = 0;
+        for (int w = 0; w < nwarps; ++w) {
+            const unsigned va = wsumA[w], vb = wsumB[w];
+            if (w < warp) { pn += va; pd += vb; }
+            totA += va; totB += vb;
+        }
+        pn += ia - sumN; pd += ib - sumD;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            pd += dd[q];
+            PL[j0 + q] = pn;
+            if (n[q]) or_bits(out, hdr + pn + pd, code[q], n[q]);
+            pn += n[q];
+        }
+        __syncthreads();
+        if (tid == 0) { sCarryA += totA; sCarryB += totB; }
+        for (int k = ka + tid; k < kb; k += kEmit2Threads) {
+            const TokInfo ti = tinfo[k];
+            const uint32_t t = __ldg(tokA + k);
+            unsigned lo, loN, hi, hiN; matchCode((int)(t >> 16), __ldg(tokD + k), lo, loN, hi, hiN);
+            const unsigned off = hdr + PL[ti.lit - (unsigned)i0] + ti.mbits;
+            or_bits(out, off, lo, loN); or_bits(out, off + loN, hi, hiN);
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     if (tid == 0) {
-        unsigned q = sCarry;
+        unsigned q = hdr + sCarryA + sCarryB;
         const unsigned eob = litc[256];
         or_bits(out, q, eob & 0xFFFFFFu, eob >> 24);
         q += eob >> 24;
@@ -1944,7 +1983,7 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
         if (bytes != st.out_bytes) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 4ull);
     }
     __syncthreads();
-    copy_out(D, out, st.out_bytes);
+    copy_out(Dst, out, st.out_bytes);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2286,7 +2325,7 @@ int launch_offsets(const Job& job, cudaStream_t s)
     return 1;
 }
 
-static int g_emitVariant = 0;        // 0: position-range walk (k_emit), 1: token-parallel (k_emit2, measured slower: 5.3 vs 5.0 ms/GiB)
+static int g_emitVariant = 1;        // 0: position-range walk (k_emit), 1: symbol-parallel (k_emit2)
 void set_emit_variant(int v) { g_emitVariant = v; }
 
 int launch_emit(const Job& job, cudaStream_t s)

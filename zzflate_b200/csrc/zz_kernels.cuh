@@ -32,7 +32,7 @@ struct ChunkState {
     uint32_t hdr_bits;        // bits in ChunkCodes::hdr
     uint64_t total_bits;      // LengthCounter total of the dynamic block (encoder.cpp:267-269)
     uint32_t out_bytes;       // size of E(c)
-    uint32_t pad;
+    uint32_t nlit;            // literals of the main block (K-MATCH writes them in order into the chunk's info row)
     uint64_t out_off;         // byte offset of E(c) in the output stream
 };
 
