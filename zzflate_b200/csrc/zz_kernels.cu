@@ -101,6 +101,7 @@ __device__ __forceinline__ int len_symbol(int len, int& extraBits, int& extraVal
 constexpr int kCandTile = 1024;
 constexpr int kEmptySlot = -(1 << 30);
 constexpr int kCandStage = kCandTile + 16;
+constexpr int kCandFlight = 8;            // steps of 32 positions whose table exchanges are in flight together
 
 __device__ __forceinline__ void cp_async4(void* smemDst, const void* gsrc)
 {
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
         const int phase = (int)(reinterpret_cast<uintptr_t>(base0 + q0) & 3);
         const int tileEnd = min(q0 + kCandTile, qEnd);
         // Fast path: a full tile of positions that are all probed and inserted (no priming, no chunk start, no tail).
-        // Four steps (128 positions) are in flight at once: their hashes are independent, the four exchanges are issued
+        // kCandFlight steps (256 positions) are in flight at once: their hashes are independent, the exchanges are issued
         // back to back (shared-memory operations of one warp complete in program order, so step u+1 sees the slots as
         // step u left them) and the ascending-order check is made once for the group.  If any lane received a position
         // above its own, the slots the group touched are restored from the pre-group values the lanes hold (exactly one
@@ -172,23 +173,26 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
             const unsigned* swl = sw + (ob >> 2);
             const int sh = (ob & 3) * 8;
             uint16_t* outp = candOut + q0 + lane;
-            for (int g4 = 0; g4 < kCandTile / 128; ++g4) {
-                const int qs = q0 + g4 * 128;
-                unsigned h[4]; int old[4];
+            constexpr int U = kCandFlight, G = 32 * U;        // steps in flight, positions per group
+            for (int g4 = 0; g4 < kCandTile / G; ++g4) {
+                const int qs = q0 + g4 * G;
+                unsigned h[U]; int old[U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const unsigned v = __funnelshift_r(swl[g4 * 32 + u * 8], swl[g4 * 32 + u * 8 + 1], sh) & 0xFFFFFFu;
+                for (int u = 0; u < U; ++u) {
+                    const unsigned v = __funnelshift_r(swl[g4 * (G / 4) + u * 8], swl[g4 * (G / 4) + u * 8 + 1], sh) & 0xFFFFFFu;
                     h[u] = hash3(v);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) old[u] = atomicExch(&table[h[u]], qs + u * 32 + lane);
-                const bool bad = old[0] > qs + lane || old[1] > qs + 32 + lane || old[2] > qs + 64 + lane || old[3] > qs + 96 + lane;
+                for (int u = 0; u < U; ++u) old[u] = atomicExch(&table[h[u]], qs + u * 32 + lane);
+                bool bad = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) bad |= old[u] > qs + u * 32 + lane;
                 if (__ballot_sync(0xffffffffu, bad)) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (old[u] < qs) table[h[u]] = old[u];
+                    for (int u = 0; u < U; ++u) if (old[u] < qs) table[h[u]] = old[u];
                     __syncwarp();
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < U; ++u) {
                         const int pre = table[h[u]];
                         const unsigned grp = __match_any_sync(0xffffffffu, h[u]);
                         const unsigned lower = grp & ltMask;
@@ -199,9 +203,9 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int d = qs + u * 32 + lane - old[u];
-                    outp[g4 * 128 + u * 32] = (uint16_t)(d < kMaxDistance ? d : 0);
+                    outp[g4 * G + u * 32] = (uint16_t)(d < kMaxDistance ? d : 0);
                 }
             }
             buf ^= 1;
@@ -1889,11 +1893,16 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
         }
         if (lane == 31) { wsumA[warp] = ia; wsumB[warp] = ib; }
         __syncthreads();
-        unsigned beforeA = sCarryA, beforeB = sCarryB, totA = 0, totB = 0;
-        for (int w = 0; w < nwarps; ++w) {
-            const unsigned va = wsumA[w], vb = wsumB[w];
-            if (w < warp) { beforeA += va; beforeB += vb; }
-            totA += va; totB += vb;
+        unsigned beforeA = sCarryA, beforeB = sCarryB, totA, totB;
+        {   // every warp scans the 16 warp totals with shuffles
+            unsigned va = lane < nwarps ? wsumA[lane] : 0u, vb = lane < nwarps ? wsumB[lane] : 0u;
+            for (int o = 1; o < nwarps; o <<= 1) {
+                const unsigned ta = __shfl_up_sync(0xffffffffu, va, o), tb = __shfl_up_sync(0xffffffffu, vb, o);
+                if (lane >= o) { va += ta; vb += tb; }
+            }
+            totA = __shfl_sync(0xffffffffu, va, nwarps - 1); totB = __shfl_sync(0xffffffffu, vb, nwarps - 1);
+            const unsigned pa = __shfl_sync(0xffffffffu, va, (warp + 31) & 31), pb = __shfl_sync(0xffffffffu, vb, (warp + 31) & 31);
+            if (warp) { beforeA += pa; beforeB += pb; }
         }
         if (k < ntok) { TokInfo ti; ti.lit = ms - (beforeB + ib - len); ti.mbits = beforeA + ia - mb; tinfo[k] = ti; }
         __syncthreads();
@@ -1916,13 +1925,18 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
     for (int s = 0; s < nsteps; ++s) {
         const int i0 = s * kLitStep;
         const int ka = (int)tokStart[s], kb = (int)tokStart[s + 1];
-        for (int i = tid; i < kLitStep + 4; i += kEmit2Threads) D[i] = 0;
-        __syncthreads();
-        for (int k = ka + tid; k < kb; k += kEmit2Threads) atomicAdd(&D[tinfo[k].lit - (unsigned)i0], (unsigned)MBs[k]);
-        __syncthreads();
+        // the step's global loads are issued before its first barrier: this thread's literals and its first token
         const int j0 = 4 * tid, i = i0 + j0;
         unsigned v = 0;
         if (i < nlit) v = __ldg(reinterpret_cast<const unsigned*>(lits + i));
+        const int k1 = ka + tid;
+        TokInfo ti1; ti1.lit = 0; ti1.mbits = 0; uint32_t t1 = 0; unsigned d1 = 0;
+        if (k1 < kb) { ti1 = tinfo[k1]; t1 = __ldg(tokA + k1); d1 = __ldg(tokD + k1); }
+        for (int i = tid; i < kLitStep + 4; i += kEmit2Threads) D[i] = 0;
+        __syncthreads();
+        if (k1 < kb) atomicAdd(&D[ti1.lit - (unsigned)i0], (unsigned)MBs[k1]);
+        for (int k = k1 + kEmit2Threads; k < kb; k += kEmit2Threads) atomicAdd(&D[tinfo[k].lit - (unsigned)i0], (unsigned)MBs[k]);
+        __syncthreads();
         const uint4 d4 = *reinterpret_cast<const uint4*>(D + j0);
         unsigned code[4], n[4];
         const unsigned dd[4] = { d4.x, d4.y, d4.z, d4.w };
@@ -1940,11 +1954,16 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
         }
         if (lane == 31) { wsumA[warp] = ia; wsumB[warp] = ib; }
         __syncthreads();
-        unsigned pn = sCarryA, pd = sCarryB, totA = 0, totB = 0;
-        for (int w = 0; w < nwarps; ++w) {
-            const unsigned va = wsumA[w], vb = wsumB[w];
-            if (w < warp) { pn += va; pd += vb; }
-            totA += va; totB += vb;
+        unsigned pn = sCarryA, pd = sCarryB, totA, totB;
+        {
+            unsigned va = lane < nwarps ? wsumA[lane] : 0u, vb = lane < nwarps ? wsumB[lane] : 0u;
+            for (int o = 1; o < nwarps; o <<= 1) {
+                const unsigned ta = __shfl_up_sync(0xffffffffu, va, o), tb = __shfl_up_sync(0xffffffffu, vb, o);
+                if (lane >= o) { va += ta; vb += tb; }
+            }
+            totA = __shfl_sync(0xffffffffu, va, nwarps - 1); totB = __shfl_sync(0xffffffffu, vb, nwarps - 1);
+            const unsigned pa = __shfl_sync(0xffffffffu, va, (warp + 31) & 31), pb = __shfl_sync(0xffffffffu, vb, (warp + 31) & 31);
+            if (warp) { pn += pa; pd += pb; }
         }
         pn += ia - sumN; pd += ib - sumD;
 #pragma unroll
@@ -1956,10 +1975,10 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
         }
         __syncthreads();
         if (tid == 0) { sCarryA += totA; sCarryB += totB; }
-        for (int k = ka + tid; k < kb; k += kEmit2Threads) {
-            const TokInfo ti = tinfo[k];
-            const uint32_t t = __ldg(tokA + k);
-            unsigned lo, loN, hi, hiN; matchCode((int)(t >> 16), __ldg(tokD + k), lo, loN, hi, hiN);
+        for (int k = k1; k < kb; k += kEmit2Threads) {
+            TokInfo ti = ti1; uint32_t t = t1; unsigned dist = d1;
+            if (k != k1) { ti = tinfo[k]; t = __ldg(tokA + k); dist = __ldg(tokD + k); }
+            unsigned lo, loN, hi, hiN; matchCode((int)(t >> 16), dist, lo, loN, hi, hiN);
             const unsigned off = hdr + PL[ti.lit - (unsigned)i0] + ti.mbits;
             or_bits(out, off, lo, loN); or_bits(out, off + loN, hi, hiN);
         }
