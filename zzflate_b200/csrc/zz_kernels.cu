@@ -305,7 +305,10 @@ constexpr int kCapLen = 32;                        // cap of the parallel forwar
 constexpr int kInfoPiece = 16384;
 constexpr int kInfoThreads = 256;
 constexpr int kInfoBack = kMaxDistance + 16;        // bytes kept before the piece (candidate + 4 bytes backwards)
-constexpr int kInfoSmem = 16 + 16 + kInfoBack + kInfoPiece + 64 + 32;
+constexpr int kInfoWin = 16 + 16 + kInfoBack + kInfoPiece + 64 + 32;      // window bytes (multiple of 16)
+constexpr int kInfoQueue = 32 + 128;                                       // per-warp queue: a remainder + one step
+constexpr int kInfoSmem = kInfoWin + (kInfoThreads / 32) * kInfoQueue * 4;
+static_assert(kInfoWin % 16 == 0, "queue alignment");
 
 // forward match length beyond the first 4 bytes, capped at kCapLen - 4 (oj, op already advanced by 4)
 __device__ __forceinline__ int fwd_more(const uint8_t* win, int oj, int op)
@@ -363,21 +366,38 @@ __global__ void __launch_bounds__(kInfoThreads, 4) k_info(Job job, int piecesPer
     __syncthreads();
     const uint16_t* cand = job.cand + (size_t)slot * job.chunk;
     uint8_t* out = job.info + (size_t)slot * job.chunk;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
     const unsigned* w32 = reinterpret_cast<const unsigned*>(smem);
     const int ph8 = (wb & 3) * 8;                       // j0 is a multiple of 4: every thread sees the same byte phase
+    // Positions whose first four bytes agree need the longer compare (up to 32 bytes).  They are a minority of the lanes
+    // of every step, so they are queued per warp (position and candidate as shared-memory offsets) and measured 32 at a
+    // time with all lanes busy, instead of letting every step pay for the longest lane.
+    unsigned* queue = reinterpret_cast<unsigned*>(smem + kInfoWin) + (tid >> 5) * kInfoQueue;
+    int queued = 0;
+    auto drain = [&](int n) {                            // measures queue[0, n), n <= 32
+        if (lane < n) {
+            const unsigned e = queue[lane];
+            const int oj = (int)(e & 0xFFFFu), op = (int)(e >> 16);
+            out[oj - wb] = (uint8_t)(4 + fwd_more(smem, oj + 4, op + 4) + 1);
+        }
+    };
     // Four consecutive positions per thread: their own bytes [j0-4, j0+8) come from four aligned words (lanes read
     // consecutive words: conflict free), the candidate side is two gathered words per position (all eight gathers are
     // issued before the first compare), a third one only where bytes are missing forwards.
-    for (int j0 = P0 + 4 * tid; j0 < P1; j0 += 4 * kInfoThreads) {
-        const uint2 dd = __ldg(reinterpret_cast<const uint2*>(cand + j0));
+    const int iters = (P1 - P0 + 4 * kInfoThreads - 1) / (4 * kInfoThreads);
+    for (int it = 0; it < iters; ++it) {
+        const int j0 = P0 + 4 * tid + it * 4 * kInfoThreads;
+        const bool live = j0 < P1;
+        uint2 dd = make_uint2(0u, 0u);
+        if (live) dd = __ldg(reinterpret_cast<const uint2*>(cand + j0));
         int d[4] = { (int)(dd.x & 0xFFFFu), (int)(dd.x >> 16), (int)(dd.y & 0xFFFFu), (int)(dd.y >> 16) };
         if (j0 == 0) d[0] = 0;                          // position 0 is never probed (encoder.cpp:384)
         if (j0 + 3 >= P1) {
 #pragma unroll
             for (int k = 1; k < 4; ++k) if (j0 + k >= P1) d[k] = 0;
         }
-        const int oj0 = wb + j0;
+        const int oj0 = wb + (live ? j0 : P0);
         const unsigned* wj = w32 + (oj0 >> 2);
         const unsigned W0 = wj[-1], W1 = wj[0], W2 = wj[1], W3 = wj[2];
         const unsigned V0 = __funnelshift_r(W0, W1, ph8), V1 = __funnelshift_r(W1, W2, ph8), V2 = __funnelshift_r(W2, W3, ph8);
@@ -388,24 +408,55 @@ __global__ void __launch_bounds__(kInfoThreads, 4) k_info(Job job, int piecesPer
             const unsigned* wp = w32 + (op[k] >> 2);
             pw0[k] = wp[0]; pw1[k] = wp[1];
         }
-        unsigned packed = 0;
+        unsigned packed = 0, longMask = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            unsigned x = __funnelshift_r(V1, V2, 8 * k) ^ __funnelshift_r(pw0[k], pw1[k], op[k] * 8);
-            if (d[k] == 0) x = 1u;
-            const int fwd = x ? ((__ffs(x) - 1) >> 3) : 4 + fwd_more(smem, oj0 + k + 4, op[k] + 4);
-            bool ok = fwd >= 4;
-            if (!ok) {
-                const unsigned y = __funnelshift_r(V0, V1, 8 * k) ^ __funnelshift_r(w32[(op[k] >> 2) - 1], pw0[k], op[k] * 8);
-                int back = y ? (__clz(y) >> 3) : 4;
-                const int room = j0 + k - d[k] + g.pre;   // bytes of real history before the candidate (R4 clamp)
-                if (back > room) back = room;
-                ok = fwd + back >= 4;
+            const unsigned x = __funnelshift_r(V1, V2, 8 * k) ^ __funnelshift_r(pw0[k], pw1[k], op[k] * 8);
+            if (d[k] != 0) {
+                if (x == 0) longMask |= 1u << k;         // >= 4 bytes forwards: usable whatever lies behind; length from the queue
+                else {
+                    const int fwd = (__ffs(x) - 1) >> 3;
+                    const unsigned y = __funnelshift_r(V0, V1, 8 * k) ^ __funnelshift_r(w32[(op[k] >> 2) - 1], pw0[k], op[k] * 8);
+                    int back = y ? (__clz(y) >> 3) : 4;
+                    const int room = j0 + k - d[k] + g.pre;   // bytes of real history before the candidate (R4 clamp)
+                    if (back > room) back = room;
+                    if (fwd + back >= 4) packed |= (unsigned)(fwd + 1) << (8 * k);
+                }
             }
-            if (ok && d[k]) packed |= (unsigned)(fwd + 1) << (8 * k);
         }
-        *reinterpret_cast<unsigned*>(out + j0) = packed;
+        // the word store leaves the queued bytes as they are: each byte of the row has exactly one writer
+        if (live) {
+            if (longMask == 0) *reinterpret_cast<unsigned*>(out + j0) = packed;
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (!((longMask >> k) & 1u)) out[j0 + k] = (uint8_t)(packed >> (8 * k));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool f = (longMask >> k) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (f) queue[queued + __popc(m & ltMask)] = (unsigned)(oj0 + k) | ((unsigned)op[k] << 16);
+            queued += __popc(m);
+        }
+        __syncwarp();
+        int head = 0;
+        while (queued - head >= 32) {
+            if (true) { const unsigned e = queue[head + lane]; const int oj = (int)(e & 0xFFFFu), opq = (int)(e >> 16);
+                        out[oj - wb] = (uint8_t)(4 + fwd_more(smem, oj + 4, opq + 4) + 1); }
+            head += 32;
+        }
+        if (head) {                                      // keep the remainder (< 32 entries) at the front
+            const int rem = queued - head;
+            unsigned e = 0;
+            if (lane < rem) e = queue[head + lane];
+            __syncwarp();
+            if (lane < rem) queue[lane] = e;
+            queued = rem;
+        }
+        __syncwarp();
     }
+    drain(queued);
 }
 
 // ------------------------------------------------------------------------------------------------
