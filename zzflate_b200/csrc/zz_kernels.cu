@@ -101,7 +101,7 @@ __device__ __forceinline__ int len_symbol(int len, int& extraBits, int& extraVal
 constexpr int kCandTile = 1024;
 constexpr int kEmptySlot = -(1 << 30);
 constexpr int kCandStage = kCandTile + 16;
-constexpr int kCandFlight = 8;            // steps of 32 positions whose table exchanges are in flight together
+constexpr int kCandFlight = 16;           // steps of 32 positions whose table exchanges are in flight together
 
 __device__ __forceinline__ void cp_async4(void* smemDst, const void* gsrc)
 {
@@ -424,20 +424,17 @@ __global__ void __launch_bounds__(kInfoThreads, 4) k_info(Job job, int piecesPer
                 }
             }
         }
-        // the word store leaves the queued bytes as they are: each byte of the row has exactly one writer
-        if (live) {
-            if (longMask == 0) *reinterpret_cast<unsigned*>(out + j0) = packed;
-            else {
+        // queued bytes are stored as 0 here and overwritten when the queue is drained: the drain comes after a
+        // __syncwarp(), which orders the two stores of the warp
+        if (live) *reinterpret_cast<unsigned*>(out + j0) = packed;
+        {   // append: a lane queues 0..4 positions; its slot = positions queued by lower lanes (three votes on the count's bits)
+            const unsigned cnt = (unsigned)__popc(longMask);
+            const unsigned b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u), b2 = __ballot_sync(0xffffffffu, cnt & 4u);
+            int slotq = queued + __popc(b0 & ltMask) + 2 * __popc(b1 & ltMask) + 4 * __popc(b2 & ltMask);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) if (!((longMask >> k) & 1u)) out[j0 + k] = (uint8_t)(packed >> (8 * k));
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool f = (longMask >> k) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, f);
-            if (f) queue[queued + __popc(m & ltMask)] = (unsigned)(oj0 + k) | ((unsigned)op[k] << 16);
-            queued += __popc(m);
+            for (int k = 0; k < 4; ++k)
+                if ((longMask >> k) & 1u) queue[slotq++] = (unsigned)(oj0 + k) | ((unsigned)op[k] << 16);
+            queued += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
         }
         __syncwarp();
         int head = 0;
@@ -1927,13 +1924,16 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
     };
 
     // ---- pass A: per token l_k = start - (match bytes before) and M_k = match bits before ----
+    uint32_t tNext = 0; unsigned dNext = 0;
+    if (tid < ntok) { tNext = __ldg(tokA + tid); dNext = __ldg(tokD + tid); }
     for (int k0 = 0; k0 < ntok; k0 += kEmit2Threads) {
         const int k = k0 + tid;
+        const uint32_t t = tNext; const unsigned dist = dNext;
+        if (k + kEmit2Threads < ntok) { tNext = __ldg(tokA + k + kEmit2Threads); dNext = __ldg(tokD + k + kEmit2Threads); }   // next step's token
         unsigned mb = 0, len = 0, ms = 0;
         if (k < ntok) {
-            const uint32_t t = __ldg(tokA + k);
             ms = t & 0xFFFFu; len = t >> 16;
-            unsigned lo, loN, hi, hiN; matchCode((int)len, __ldg(tokD + k), lo, loN, hi, hiN);
+            unsigned lo, loN, hi, hiN; matchCode((int)len, dist, lo, loN, hi, hiN);
             mb = loN + hiN;
             MBs[k] = (uint8_t)mb;
         }
