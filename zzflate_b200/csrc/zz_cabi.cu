@@ -343,18 +343,19 @@ int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int fina
 // the middle (full occupancy, one dictionary-priming pass per long run of chunks), small at the end (short drain).
 std::vector<uint64_t> pieceSchedule(uint64_t nchunks)
 {
-    // Every piece costs one launch of each kernel, and the Huffman kernel is ~1 ms however few chunks it gets
-    // (one serial thread per chunk), so pieces are few: 1024, 2048, then 4096 chunks, and the last <= 6144 chunks in
-    // two pieces (60/40) so that the final D2H is short.
+    // Every piece costs one launch of each kernel (the Huffman kernel alone is ~0.4 ms however few chunks it gets), so
+    // pieces are few.  Their sizes are multiples of 888 chunks = 148 SMs x 6 resident K-CAND warps, which is also a
+    // whole number of waves of K-MATCH / K-EMIT (296 CTAs) and K-INFO (148 chunks): 888, 1776, 3552, then 4440 chunks,
+    // and the last <= 7104 chunks in two pieces (about 60/40) so that the final D2H is short.
     std::vector<uint64_t> ends;
-    const uint64_t big = 4096;
-    uint64_t pos = 0, size = 1024;
-    while (nchunks - pos > big + big / 2) {
+    const uint64_t unit = 888, big = 5 * unit;
+    uint64_t pos = 0, size = unit;
+    while (nchunks - pos > big + 3 * unit) {
         pos += size; ends.push_back(pos);
-        if (size < big) size *= 2;
+        size = size < 4 * unit ? size * 2 : big;
     }
     const uint64_t rem = nchunks - pos;
-    if (rem > 1024) { const uint64_t take = rem * 3 / 5; pos += take; ends.push_back(pos); }
+    if (rem > 2 * unit) { uint64_t take = ((rem * 3 / 5 + unit / 2) / unit) * unit; if (take == 0 || take >= rem) take = rem / 2; pos += take; ends.push_back(pos); }
     if (pos < nchunks) ends.push_back(nchunks);
     return ends;
 }
