@@ -809,9 +809,9 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
                 // probe_next for the 32 states of the tile: positions b+1..b+3 need 1..3 bytes backwards less than a
                 // full match (info >= 4 / 3 / 2), from b+4 on any usable position is taken (bitmap)
                 int j = -1;
-                // info[r+1..r+3] from two aligned words; one byte-wise compare against the thresholds 4 / 3 / 2
+                // info[r+1..r+3] from two aligned words; adding 0x7C / 0x7D / 0x7E sets bit 7 of a byte iff it is >= 4 / 3 / 2
                 const unsigned* iw = reinterpret_cast<const unsigned*>(info) + ((r + 1) >> 2);
-                const unsigned near3 = __vcmpgeu4(__funnelshift_r(iw[0], iw[1], ((r + 1) & 3) * 8), 0xFF020304u) & 0x00FFFFFFu;
+                const unsigned near3 = (__funnelshift_r(iw[0], iw[1], ((r + 1) & 3) * 8) + 0x007E7D7Cu) & 0x00808080u;   // info <= 33: no carry between bytes
                 if (near3) j = b + 1 + ((__ffs(near3) - 1) >> 3);
                 else {
                     const unsigned low = okbits[t], hiw = okbits[t + 1];
