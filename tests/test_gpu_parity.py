@@ -248,6 +248,29 @@ def test_host_buffers_pipelined_path(zz, oracle):
     assert zlib.decompress(g1, 31) == data[: 40 << 20].tobytes()
 
 
+def test_kernel_variants_give_the_same_bytes(zz, oracle, golden):
+    """K-EMIT has two variants (symbol-parallel, the default, and the position-range walk behind the "emit" option) and
+    K-HUFF two (warp per chunk for launches of one wave, thread per chunk for full batches, picked by launch size):
+    every combination must give the oracle's bytes."""
+    from zzflate_b200 import synth, _lib
+    lib = _lib.load()
+    small = golden.input("mixed")                                # a few chunks: warp-per-chunk K-HUFF
+    n = 8000 * S + 777                                           # > 148 * 52 chunks: thread-per-chunk K-HUFF
+    big = synth.markov_text(n, seg0=3)
+    big[5 * S: 6 * S] = synth.random_bytes(S)                    # a stored chunk, a run of zeros and few-symbol data in between
+    big[9 * S: 9 * S + 3000] = 0
+    big[11 * S: 12 * S] = synth.random_bytes(S) % 7 + 48
+    want_small, _ = oracle.stream_chunked(small, DEFLATE, 2)
+    want_big, _ = oracle.stream_chunked(big, DEFLATE, 2, threads=8)
+    try:
+        for variant in (0, 1):
+            assert lib.zzgpu_set_option(b"emit", variant) == 0
+            assert zz.deflate_raw(small, level=2)[0] == want_small, variant
+            assert zz.deflate_raw(big, level=2)[0] == want_big, variant
+    finally:
+        lib.zzgpu_set_option(b"emit", 1)
+
+
 @pytest.mark.parametrize("workload,size_mib", [("text", 1024), ("text", 1088), ("random", 256), ("zeros", 256), ("pattern", 256)])
 def test_baseline_sizes_round_trip(zz, workload, size_mib):
     """BASELINE.json configs 2-4 at full size: every output inflates through zlib to the input and the
