@@ -1970,6 +1970,7 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
         tokStart[tid] = (unsigned)lo;
     }
     if (tid == 0) { sCarryA = 0; sCarryB = 0; }                        // now: literal bits / match bits before the step
+    for (int i = tid; i < kLitStep + 4; i += kEmit2Threads) D[i] = 0;
     __syncthreads();
 
     // ---- pass B: literal steps ----
@@ -1983,12 +1984,13 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
         const int k1 = ka + tid;
         TokInfo ti1; ti1.lit = 0; ti1.mbits = 0; uint32_t t1 = 0; unsigned d1 = 0;
         if (k1 < kb) { ti1 = tinfo[k1]; t1 = __ldg(tokA + k1); d1 = __ldg(tokD + k1); }
-        for (int i = tid; i < kLitStep + 4; i += kEmit2Threads) D[i] = 0;
-        __syncthreads();
+        // D is all zero here: every thread clears the four entries it has read (below), and the scatter of a step
+        // starts after the previous step's barrier in front of the match phase
         if (k1 < kb) atomicAdd(&D[ti1.lit - (unsigned)i0], (unsigned)MBs[k1]);
         for (int k = k1 + kEmit2Threads; k < kb; k += kEmit2Threads) atomicAdd(&D[tinfo[k].lit - (unsigned)i0], (unsigned)MBs[k]);
         __syncthreads();
         const uint4 d4 = *reinterpret_cast<const uint4*>(D + j0);
+        *reinterpret_cast<uint4*>(D + j0) = make_uint4(0u, 0u, 0u, 0u);
         unsigned code[4], n[4];
         const unsigned dd[4] = { d4.x, d4.y, d4.z, d4.w };
         unsigned sumN = 0, sumD = 0;
@@ -2033,8 +2035,9 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
             const unsigned off = hdr + PL[ti.lit - (unsigned)i0] + ti.mbits;
             or_bits(out, off, lo, loN); or_bits(out, off + loN, hi, hiN);
         }
-        __syncthreads();
+        // no barrier here: the next step's PL is written after two more barriers, its D entries are already clear
     }
+    __syncthreads();
 
     if (tid == 0) {
         unsigned q = hdr + sCarryA + sCarryB;
