@@ -250,7 +250,6 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
 // shared-memory window helpers
 // ------------------------------------------------------------------------------------------------
 constexpr int kPreCap = kMaxDict + kPreExtra;                       // 33056, multiple of 16
-constexpr int kWinBytes = kPreCap + 16 + kMaxChunk + 64;            // + alignment slack + tail pad
 static_assert(kPreCap % 16 == 0, "window base must keep 16-byte phase");
 
 // Copies src[lo, hi) (positions relative to the chunk start) into win so that position i lands at byte
@@ -322,31 +321,6 @@ __device__ __forceinline__ int fwd_more(const uint8_t* win, int oj, int op)
     }
     const unsigned x1 = ld4(win, oj + 24) ^ ld4(win, op + 24);
     return x1 ? 24 + ((__ffs(x1) - 1) >> 3) : kCapLen - 4;
-}
-
-// info of one position from a shared-memory window (position i at win[wb + i]); pre = real history before the chunk
-__device__ __forceinline__ unsigned info_of(const uint8_t* win, int wb, int j, int d, int pre)
-{
-    if (d == 0) return 0u;
-    const unsigned* w32 = reinterpret_cast<const unsigned*>(win);
-    // bytes [j-4, j+4) and [p-4, p+4) from three aligned words each: one funnel shift gives the 4 bytes after the
-    // position, one the 4 bytes before it
-    const int oj = wb + j, op = oj - d;
-    const unsigned* wj = w32 + (oj >> 2);
-    const unsigned* wp = w32 + (op >> 2);
-    const int sj = (oj & 3) * 8, sp = (op & 3) * 8;
-    const unsigned j0 = wj[0], p0 = wp[0];
-    const unsigned x = __funnelshift_r(j0, wj[1], sj) ^ __funnelshift_r(p0, wp[1], sp);
-    const int fwd = x ? ((__ffs(x) - 1) >> 3) : 4 + fwd_more(win, oj + 4, op + 4);
-    bool ok = fwd >= 4;
-    if (!ok) {
-        const unsigned y = __funnelshift_r(wj[-1], j0, sj) ^ __funnelshift_r(wp[-1], p0, sp);
-        int back = y ? (__clz(y) >> 3) : 4;
-        const int room = j - d + pre;                     // bytes of real history before the candidate (R4 clamp)
-        if (back > room) back = room;
-        ok = fwd + back >= 4;
-    }
-    return ok ? (unsigned)fwd + 1u : 0u;
 }
 
 __global__ void __launch_bounds__(kInfoThreads, 4) k_info(Job job, int piecesPerChunk)
