@@ -892,6 +892,55 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
                 // F becomes exact for this state.  With a long backward part the match can end inside x's own tile
                 // (b = j - lb + 258 may be as small as j): the tile's expansion then simply walks on from b.
                 if (lane == 0) F[x - base] = (uint16_t)(b < 65535 ? b : 65535);
+                // Runs (RLE-like data): a full-length match whose successor states repeat it 258 bytes further on.  Each
+                // of them would cost two dependent trips to memory on this serial path; instead the equality between
+                // the two sides is measured once beyond the first 258 bytes (R, as far as 32 more matches can use it) and
+                // lane i-1 checks that state x + 258 i is an unresolved long state whose probe position has the same gap
+                // and the same distance.  For those states fwd_i = min(258, R - 258 i) and the backward part is the gap
+                // again (its bytes lie inside [j, j + R)), so match i is (start x_i, length 258) exactly as the walk
+                // would find it, as long as R - 258 i >= 258 - gap.
+                const int gap = j - x;
+                if (fwd == kMaxMatch && lb == gap && b + 1 < E) {
+                    const int xi = x + kMaxMatch * (lane + 1);
+                    bool ok = xi < E;
+                    if (ok) ok = F[xi - base] == 1;
+                    if (ok) ok = probe_next(info, okbits, nzw, ntiles, base, xi) == xi + gap;
+                    if (ok) ok = patched_cand(cand, &ps, npatch, xi + gap) == d;
+                    const unsigned okm = __ballot_sync(0xffffffffu, ok);
+                    int K = okm == 0xffffffffu ? 32 : __ffs(~okm) - 1;            // candidates of the run
+                    if (K > 0) {
+                        // R: equal bytes between the two sides from j on, measured only as far as K matches need it
+                        int Rcap = kMaxMatch * (K + 1) - gap; { const int lim = g.body - j; if (lim < Rcap) Rcap = lim; }
+                        int R = Rcap;
+                        for (int off = 256; off < Rcap && R == Rcap; off += 1024) {
+                            unsigned long long xa[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                xa[u] = off + 256 * u < Rcap ? gload8(chunk0 + j + off + 256 * u + lane * 8, strm.lo, strm.hi) ^ gload8(chunk0 + p + off + 256 * u + lane * 8, strm.lo, strm.hi) : 0ull;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const unsigned mm = __ballot_sync(0xffffffffu, xa[u] != 0);
+                                if (mm && R == Rcap) {
+                                    const int src = __ffs(mm) - 1;
+                                    const unsigned long long xs = __shfl_sync(0xffffffffu, xa[u], src);
+                                    const int r = off + 256 * u + src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
+                                    if (r < R) R = r;
+                                }
+                            }
+                        }
+                        // match i needs R - 258 i >= 258 - gap
+                        const int byR = (R - kMaxMatch + gap) / kMaxMatch;
+                        if (byR < K) K = byR < 0 ? 0 : byR;
+                        if (lane < K) {
+                            const int nb = xi + kMaxMatch;
+                            F[xi - base] = (uint16_t)(nb < 65535 ? nb : 65535);
+                            seg[nseg + lane] = (uint16_t)xi;         // every resolved long state starts a segment
+                        }
+                        nseg += K;
+                        b = x + kMaxMatch * (K + 1);
+                        __syncwarp();
+                    }
+                }
             }
             if (lane == 0) { ps.npre = npre; ps.nseg = nseg; ps.finalB = finalB; }
         }
