@@ -2103,24 +2103,32 @@ __device__ __forceinline__ unsigned fixed_lit_code(unsigned v, int& len)     // 
 // written to the chunk's scratch slot word by word.
 __global__ void __launch_bounds__(32) k_fixed(Job job)
 {
-    __shared__ int table[kHashSize];
+    // The table holds positions modulo 65536 in 16 bits (16 KiB per warp: twice the resident warps of an int table).
+    // age = (i - entry) & 0xFFFF is exact while it stays below 65536: a sweep every 8192 positions turns the entries that
+    // are more than 32768 behind (invalid from then on, encoder.cpp:347) into "empty" ones of age 40000, so no entry ever
+    // gets older than ~48500 positions.
+    __shared__ unsigned short table[kHashSize];
     __shared__ unsigned obuf[16];
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
     const int lane = threadIdx.x;
     const unsigned ltMask = (1u << lane) - 1u;
-    for (int i = lane; i < kHashSize; i += 32) table[i] = kEmptySlot;
+    constexpr int kEmptyAge = 40000, kSweep = 8192;
+    for (int i = lane; i < kHashSize; i += 32) table[i] = (unsigned short)(0 - kEmptyAge);
     if (lane < 16) obuf[lane] = 0;
     __syncwarp();
     const uint8_t* base = job.src + g.off;
     const uint8_t* lo = job.src - job.history;
     const uint8_t* hi = job.src + job.n;
     // level-1 priming convention: table[h(i+1)] = i for every dictionary position
-    for (int i = -g.dict + lane; i < 0; i += 32) {
-        const unsigned v = (unsigned)(gload8(base + i, lo, hi) >> 8) & 0xFFFFFFu;
-        atomicMax(&table[hash3(v)], i);
+    for (int i0 = -g.dict; i0 < 0; i0 += 32) {
+        const int i = i0 + lane;
+        const bool v = i < 0;
+        const unsigned h = v ? hash3((unsigned)(gload8(base + i, lo, hi) >> 8) & 0xFFFFFFu) : 0x10000u + lane;
+        const unsigned grp = __match_any_sync(0xffffffffu, h);
+        if (v && (grp >> lane) == 1u) table[h] = (unsigned short)i;       // the highest position of a group owns the slot
+        __syncwarp();
     }
-    __syncwarp();
     ChunkState& st = job.state[slot];
     unsigned* out32 = reinterpret_cast<unsigned*>(job.cand + (size_t)slot * job.chunk);
     const int n = g.body;
@@ -2151,15 +2159,21 @@ __global__ void __launch_bounds__(32) k_fixed(Job job)
     if (n > 0) {
         if (lane == 0) putAt(0, (g.final ? 1u : 0u) | (1u << 1), 3);     // StartBlock(FixedHuffman, final)
         stepFlush(3);
-        int i0 = 0;
+        int i0 = 0, nextSweep = kSweep;
         while (i0 < n) {
+            if (i0 >= nextSweep) {
+                for (int k = lane; k < kHashSize; k += 32)
+                    if (((i0 - (int)table[k]) & 0xFFFF) > kMaxDistance) table[k] = (unsigned short)(i0 - kEmptyAge);
+                nextSweep = i0 + kSweep;
+                __syncwarp();
+            }
             const int i = i0 + lane;
             const bool valid = i < n;
             const unsigned long long v8 = valid ? gload8(base + i, lo, hi) : 0ull;
             const unsigned h = hash3((unsigned)(v8 >> 8) & 0xFFFFFFu);
             const unsigned grp = __match_any_sync(0xffffffffu, valid ? h : (0x10000u + lane));
             const unsigned lower = grp & ltMask;
-            const int old = valid ? table[h] : kEmptySlot;
+            const int old = i - (valid ? ((i - (int)table[h]) & 0xFFFF) : 0xFFFF);
             const int cand = lower ? (i0 + 31 - __clz(lower)) : old;
             const int d = i - cand;
             int m = 0;
@@ -2174,7 +2188,7 @@ __global__ void __launch_bounds__(32) k_fixed(Job job)
             // commit: lanes <= first were visited; the highest visited lane of a hash group owns the slot
             const unsigned visited = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
             __syncwarp();
-            if (valid && ((visited >> lane) & 1u) && (grp & ~ltMask & ~(1u << lane) & visited) == 0) table[h] = i;
+            if (valid && ((visited >> lane) & 1u) && (grp & ~ltMask & ~(1u << lane) & visited) == 0) table[h] = (unsigned short)i;
             // exact length of the winning match (remain(a, b, 8, n - i), encoder.cpp:352)
             int mlen = 0, mdist = 0;
             if (first < 32) {
