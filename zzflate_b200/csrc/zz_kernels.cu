@@ -360,11 +360,14 @@ __global__ void __launch_bounds__(kInfoThreads, 4) k_info(Job job, int piecesPer
     // consecutive words: conflict free), the candidate side is two gathered words per position (all eight gathers are
     // issued before the first compare), a third one only where bytes are missing forwards.
     const int iters = (P1 - P0 + 4 * kInfoThreads - 1) / (4 * kInfoThreads);
+    uint2 ddNext = make_uint2(0u, 0u);
+    if (P0 + 4 * tid < P1) ddNext = __ldg(reinterpret_cast<const uint2*>(cand + P0 + 4 * tid));
     for (int it = 0; it < iters; ++it) {
         const int j0 = P0 + 4 * tid + it * 4 * kInfoThreads;
         const bool live = j0 < P1;
-        uint2 dd = make_uint2(0u, 0u);
-        if (live) dd = __ldg(reinterpret_cast<const uint2*>(cand + j0));
+        const uint2 dd = ddNext;
+        ddNext = make_uint2(0u, 0u);                                     // the next step's candidates travel during this one
+        if (j0 + 4 * kInfoThreads < P1) ddNext = __ldg(reinterpret_cast<const uint2*>(cand + j0 + 4 * kInfoThreads));
         int d[4] = { (int)(dd.x & 0xFFFFu), (int)(dd.x >> 16), (int)(dd.y & 0xFFFFu), (int)(dd.y >> 16) };
         if (j0 == 0) d[0] = 0;                          // position 0 is never probed (encoder.cpp:384)
         if (j0 + 3 >= P1) {
