@@ -5,15 +5,21 @@
 //   K-CAND   k_candidates  hash heads: nearest earlier position with the same 13-bit hash, per position
 //                          (replaces CalcHash / the table probe+insert of FirstPass / AddHashEntries,
 //                           zzflate/encoder.cpp:11-17,388-390,474-480)
-//   K-MATCH  k_parse       match verification, greedy acceptance with backward extension, histograms
+//   K-INFO   k_info        per-position match info against the candidate: min(forward length, 32), usable or not
+//                          (the compare part of FirstPass: remain / countMatchBackward; encoder.cpp:81-102,391-403)
+//   K-MATCH  k_parse       greedy acceptance as the orbit of a successor function, exact lengths and backward
+//                          extension of the taken matches, histograms, literal stream
 //                          (FirstPass, countMatchBackward, remain, GetFrequencies; encoder.cpp:375-471)
 //   K-HUFF   k_huffman     code lengths (libstdc++-heap Huffman with the reference's limiter), canonical
-//                          codes, code-length RLE, exact block size, stored fallback decision, block header
-//                          (huffman.cpp:67-216, huffman.h:49-81, encoder.cpp:171-187,250-293)
+//            k_huffman_lanes  codes, code-length RLE, exact block size, stored fallback decision, block header
+//                          (huffman.cpp:67-216, huffman.h:49-81, encoder.cpp:171-187,250-293); warp per chunk for
+//                          small launches, thread per chunk for full batches
 //   K-OFFS   k_offsets     exclusive scan of chunk sizes -> output offsets (stitch of zzflate.cpp:136-154)
-//   K-EMIT   k_emit        bit emission of header, records, EOB and the aligning stored block
-//                          (WriteRecords / WriteDistance / StartBlock / outputbitstream; encoder.cpp:135-169,
-//                           UncompressedFallback / WriteUncompressedBlock; encoder.cpp:305-317,482-502)
+//   K-EMIT   k_emit2       bit emission of header, records, EOB and the aligning stored block
+//            (k_emit)      (WriteRecords / WriteDistance / StartBlock / outputbitstream; encoder.cpp:135-169,
+//                           UncompressedFallback / WriteUncompressedBlock; encoder.cpp:305-317,482-502);
+//                          symbol-parallel, k_emit = the older position-range walk kept for A/B runs
+//   K-FIXED  k_fixed, k_gather   level 1: WriteBlockFixedHuff (encoder.cpp:329-373)
 //   K-CKSUM  k_checksums   per-chunk Adler-32 / CRC-32 partials (adler.cpp:17, crc.cpp:24)
 //
 // Everything is integer work; nothing here is a dense contraction, so tensor cores are not used.
