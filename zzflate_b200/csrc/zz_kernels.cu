@@ -832,11 +832,12 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
           // pass B: E2 = where the orbit leaves the super tile (kSuperTiles tiles).  The warp walks the super tile's tiles
           // from the last to the first: a state whose tile exit lands on a later tile of the same super tile inherits that
           // state's (already final) super-tile exit, so every state is touched once.
+          const unsigned stayEnd = (unsigned)(superEnd < E ? superEnd : E);   // exits below it stay inside the super tile and the batch
           for (int t = tLast; t >= tFirst; --t) {
-            const int tileEnd = base + (t + 1) * 32;
+            const unsigned tileEnd = (unsigned)(base + (t + 1) * 32);
             const unsigned e = E2[t * 32 + lane];
             unsigned fin = e;
-            if (e >= 2 && (int)e < superEnd && (int)e < E && (int)e >= tileEnd && F[(int)e - base] != 1) fin = E2[(int)e - base];
+            if (e >= tileEnd && e < stayEnd && F[(int)e - base] != 1) fin = E2[(int)e - base];
             E2[t * 32 + lane] = (uint16_t)fin;
             __syncwarp();
           }
@@ -1121,12 +1122,13 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
         }
         __syncthreads();
         // literals: histogram, and the literal bytes written out in order for K-EMIT (position -> rank through the
-        // coverage bitmap)
+        // coverage bitmap).  A 4-byte aligned chunk reads whole words (a word that holds a valid byte never leaves its page).
+        const bool srcAligned = (reinterpret_cast<uintptr_t>(chunk0) & 3) == 0;
         for (int pos = tid * 4; pos < g.body; pos += 4 * kParseThreads) {
             const unsigned cword = cov[pos >> 5];
             const unsigned cw = (cword >> (pos & 31)) & 0xFu;
             if (cw == 0xFu) continue;                                   // four covered positions: nothing to count
-            const unsigned v = gload4(chunk0 + pos, strm.lo, strm.hi);
+            const unsigned v = srcAligned ? __ldg(reinterpret_cast<const unsigned*>(chunk0 + pos)) : gload4(chunk0 + pos, strm.lo, strm.hi);
             unsigned rank = litBase[pos >> 5] + (unsigned)__popc(~cword & ((1u << (pos & 31)) - 1u));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
