@@ -484,10 +484,9 @@ static_assert(2 * (kParseSmem + 1024 + 512) <= 228 * 1024, "two K-MATCH CTAs mus
 // 33..254 = first state beyond the tile at tileEnd + v - 33, 255 = further away (the reader follows F instead)
 __device__ __forceinline__ unsigned e1_pack(unsigned e, int tileStart)
 {
-    if (e == 0u) return 0u;
-    const int rel = (int)e - tileStart;
-    if (rel < 32) return 1u + (unsigned)rel;
-    return rel - 32 <= 221 ? 33u + (unsigned)(rel - 32) : 255u;
+    // both non-zero cases are rel + 1 (1..32 inside the tile, 33..254 beyond it), saturated at 255
+    const unsigned v = e - (unsigned)tileStart + 1u;
+    return e == 0u ? 0u : (v < 255u ? v : 255u);
 }
 
 struct ParseShared {
