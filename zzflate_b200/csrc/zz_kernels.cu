@@ -107,7 +107,7 @@ __device__ __forceinline__ int len_symbol(int len, int& extraBits, int& extraVal
 constexpr int kCandTile = 1024;
 constexpr int kEmptySlot = -(1 << 30);
 constexpr int kCandStage = kCandTile + 16;
-constexpr int kCandFlight = 16;           // steps of 32 positions whose table exchanges are in flight together
+constexpr int kCandFlight = 32;           // steps of 32 positions whose table exchanges are in flight together
 
 __device__ __forceinline__ void cp_async4(void* smemDst, const void* gsrc)
 {
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
         const int phase = (int)(reinterpret_cast<uintptr_t>(base0 + q0) & 3);
         const int tileEnd = min(q0 + kCandTile, qEnd);
         // Fast path: a full tile of positions that are all probed and inserted (no priming, no chunk start, no tail).
-        // kCandFlight steps (256 positions) are in flight at once: their hashes are independent, the exchanges are issued
+        // kCandFlight steps (a whole 1 KiB tile) are in flight at once: their hashes are independent, the exchanges are issued
         // back to back (shared-memory operations of one warp complete in program order, so step u+1 sees the slots as
         // step u left them) and the ascending-order check is made once for the group.  If any lane received a position
         // above its own, the slots the group touched are restored from the pre-group values the lanes hold (exactly one
@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
           int tLast = tFirst + kSuperTiles - 1; if (tLast >= ntiles) tLast = ntiles - 1;
           // pass A: F and the tile exits; the tiles of the super tile are independent, so their shared-memory
           // round trips overlap
-#pragma unroll 2
+#pragma unroll 8
           for (int t = tFirst; t <= tLast; ++t) {
             const int tileStart = base + t * 32, tileEnd = tileStart + 32;
             const int r = t * 32 + lane, b = tileStart + lane;
@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
                         if (w2 != kNone16) j = base + (int)w2 * 32 + __ffs(okbits[w2]) - 1;
                     }
                 }
-                if (b >= B0 && b < E && j >= 0) {
+                if ((unsigned)(b - B0) < (unsigned)(E - B0) && j >= 0) {
                     const unsigned fwd = (unsigned)info[j - base] - 1u;
                     f = needs_exact((int)fwd, j - b) ? 1u : (unsigned)j + fwd;
                 }
