@@ -1851,7 +1851,7 @@ __global__ void __launch_bounds__(kEmitThreads, 1) k_emit(Job job)
 //     match k   : header + (code bits of literals < l_k) + (bits of the matches < k)
 // so both are prefix sums over compact arrays, and every lane of a warp does the same work: no walk over positions,
 // no data-dependent mix of literals and matches per thread.
-//   pass A (tokens, 512 per step): match bits, l_k and the match-bit prefix M_k, kept in the chunk's candidate row
+//   pass A (tokens, 1024 per step): match bits, l_k and the match-bit prefix M_k, kept in the chunk's candidate row
 //   pass B (literals, 2048 per step): the matches that sit inside the step scatter their bits onto the literal index
 //           they precede (shared-memory D), one block scan of (literal bits, D) gives all offsets; literals are written,
 //           then the step's matches at header + literal-prefix(l_k) + M_k.
@@ -1957,20 +1957,31 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
     };
 
     // ---- pass A: per token l_k = start - (match bytes before) and M_k = match bits before ----
-    uint32_t tNext = 0; unsigned dNext = 0;
-    if (tid < ntok) { tNext = __ldg(tokA + tid); dNext = __ldg(tokD + tid); }
-    for (int k0 = 0; k0 < ntok; k0 += kEmit2Threads) {
-        const int k = k0 + tid;
-        const uint32_t t = tNext; const unsigned dist = dNext;
-        if (k + kEmit2Threads < ntok) { tNext = __ldg(tokA + k + kEmit2Threads); dNext = __ldg(tokD + k + kEmit2Threads); }   // next step's token
-        unsigned mb = 0, len = 0, ms = 0;
-        if (k < ntok) {
-            ms = t & 0xFFFFu; len = t >> 16;
-            unsigned lo, loN, hi, hiN; matchCode((int)len, dist, lo, loN, hi, hiN);
-            mb = loN + hiN;
-            MBs[k] = (uint8_t)mb;
+    // two consecutive tokens per thread and step (1024 per step): half as many block scans
+    auto load2 = [&](int k, uint2& t2, unsigned& d2) {
+        t2 = make_uint2(0u, 0u); d2 = 0;
+        if (k + 1 < ntok) { t2 = __ldg(reinterpret_cast<const uint2*>(tokA + k)); d2 = __ldg(reinterpret_cast<const unsigned*>(tokD + k)); }
+        else if (k < ntok) { t2.x = __ldg(tokA + k); d2 = __ldg(tokD + k); }
+    };
+    uint2 tNext; unsigned dNext;
+    load2(2 * tid, tNext, dNext);
+    for (int k0 = 0; k0 < ntok; k0 += 2 * kEmit2Threads) {
+        const int k = k0 + 2 * tid;
+        const uint2 t2 = tNext; const unsigned d2 = dNext;
+        load2(k + 2 * kEmit2Threads, tNext, dNext);                       // next step's tokens
+        unsigned mb[2] = { 0, 0 }, len[2] = { 0, 0 }, ms[2] = { 0, 0 };
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (k + u < ntok) {
+                const uint32_t t = u ? t2.y : t2.x;
+                ms[u] = t & 0xFFFFu; len[u] = t >> 16;
+                unsigned lo, loN, hi, hiN; matchCode((int)len[u], u ? d2 >> 16 : d2 & 0xFFFFu, lo, loN, hi, hiN);
+                mb[u] = loN + hiN;
+                MBs[k + u] = (uint8_t)mb[u];
+            }
         }
-        unsigned ia = mb, ib = len;
+        const unsigned sumA = mb[0] + mb[1], sumB = len[0] + len[1];
+        unsigned ia = sumA, ib = sumB;
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
             if (lane >= o) { ia += ta; ib += tb; }
@@ -1988,7 +1999,12 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
             const unsigned pa = __shfl_sync(0xffffffffu, va, (warp + 31) & 31), pb = __shfl_sync(0xffffffffu, vb, (warp + 31) & 31);
             if (warp) { beforeA += pa; beforeB += pb; }
         }
-        if (k < ntok) { TokInfo ti; ti.lit = ms - (beforeB + ib - len); ti.mbits = beforeA + ia - mb; tinfo[k] = ti; }
+        unsigned exA = beforeA + ia - sumA, exB = beforeB + ib - sumB;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (k + u < ntok) { TokInfo ti; ti.lit = ms[u] - exB; ti.mbits = exA; tinfo[k + u] = ti; }
+            exA += mb[u]; exB += len[u];
+        }
         __syncthreads();
         if (tid == 0) { sCarryA += totA; sCarryB += totB; }
     }
