@@ -175,12 +175,12 @@ def main():
         t = sum(times) / len(times)
         val = n / t / 1e9
         sample = f"first {n >> 20} MiB of the workload per step, Format=Deflate level 2, threaded=true"
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
+        emit_line({"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3), "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                           "ratio": round(out_len / n, 5),
                           "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
-                          "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ---------------------------------------------------------------- B200 arm
@@ -306,10 +306,40 @@ def main():
         line["cpu_baseline"] = {"value": round(n_s / best / 1e9, 4), "unit": UNIT, "cores": cores, "kind": kind,
                                 "sample": f"first {n_s >> 20} MiB of rank 0's shard, ZzFlateEncode Format=Deflate level 2 threaded=true, best of 3",
                                 "ratio": round(cpu_out / n_s, 5)}
-    print(json.dumps(line))
+    emit_line(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+class _StdoutToStderr:
+    """stdout carries exactly one JSON line: while the bench runs, file descriptor 1 points at stderr (NCCL and the
+    libraries under torch print version banners to it), and the real stdout comes back for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1); os.close(self.saved); self.saved = None
+
+    def __exit__(self, *exc):
+        self.restore()
+        return False
+
+
+_GUARD = None
+
+
+def emit_line(obj) -> None:
+    if _GUARD is not None:
+        _GUARD.restore()
+    print(json.dumps(obj), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    with _StdoutToStderr() as _GUARD:
+        main()
