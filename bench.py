@@ -152,13 +152,17 @@ def main():
     ap.add_argument("--cpu-sample-mib", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the output checks that run after the timed loops")
+    ap.add_argument("--format", default="zlib", choices=["zlib", "gzip", "deflate"], help="framing of the end-to-end leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload_name = {"text": "1 GiB order-2 Markov text per GPU (SURVEY 8d.2), 64 KiB chunks + 32 KiB dictionary, level 2 dynamic Huffman",
-                     "random": "splitmix64 random bytes, level 2 (stored fallback)", "zeros": "all-zero input, level 2",
-                     "pattern": "1000-byte pattern repeated, level 2"}[args.workload]
+    lvl = {0: "level 0 stored", 1: "level 1 fixed Huffman", 2: "level 2 dynamic Huffman", 3: "level 3 dynamic Huffman"}[args.level]
+    workload_name = {"text": "1 GiB order-2 Markov text per GPU (SURVEY 8d.2), 64 KiB chunks + 32 KiB dictionary, " + lvl,
+                     "random": "1 GiB splitmix64 random bytes per GPU (SURVEY 8d.3), " + lvl,
+                     "zeros": "1 GiB all-zero input per GPU (SURVEY 8d.4a), " + lvl,
+                     "pattern": "1 GiB of a 1000-byte pattern repeated per GPU (SURVEY 8d.4b), " + lvl}[args.workload]
     config = {"workload": workload_name if args.shard_mib == 1024 else workload_name.replace("1 GiB", f"{args.shard_mib} MiB"),
               "bytes_per_gpu": args.shard_mib << 20, "chunk": CHUNK, "dict": DICT, "level": args.level,
               "sharding": f"{world} contiguous shards, no collective" if world > 1 else "single GPU",
@@ -238,7 +242,7 @@ def main():
     # ---- end to end through the public API on pinned host buffers
     e2e_ms, e2e_out = None, 0
     if not args.no_e2e:
-        cfg = zz.Config(zz.Format.Deflate, args.level, False)
+        cfg = zz.Config({"zlib": zz.Format.Zlib, "gzip": zz.Format.Gzip, "deflate": zz.Format.Deflate}[args.format], args.level, False)
         src_ptr = pinned_src.data_ptr() + hist
         if hist:          # the public single-call API has no history argument: rank>0 encodes its shard as its own stream
             pass
@@ -251,6 +255,69 @@ def main():
             assert e2e_out is not None
         barrier()
         e2e_ms = (time.perf_counter() - t1) * 1e3
+
+
+    # ---- verification of the last timed outputs (outside the timed regions): a wrong stream must not print a number
+    verified = None
+    if not args.no_verify:
+        import zlib
+        out_len, a0, crc_v, _ = zz.deflate_device(d_src.data_ptr() + hist, nbytes, d_dst.data_ptr(), cap, level=args.level,
+                                                  history=hist, final=final, checksums=3)
+        got = d_dst[:out_len].cpu().numpy()
+        shard = host[hist:]
+        ok = {}
+        d = zlib.decompressobj(-15, zdict=host[max(0, hist - DICT): hist].tobytes()) if hist else zlib.decompressobj(-15)
+        pos, good = 0, True
+        for lo in range(0, out_len, 64 << 20):
+            piece = d.decompress(got[lo: lo + (64 << 20)].tobytes())
+            good = good and piece == shard[pos: pos + len(piece)].tobytes()
+            pos += len(piece)
+        ok["inflate_equals_input"] = bool(good and pos == nbytes and (d.eof or not final))
+        ok["adler32"] = bool(a0 == zlib.adler32(shard, 0))
+        ok["crc32"] = bool(crc_v == zlib.crc32(shard))
+        if rank == 0:
+            # rank 0's shard against the CPU restatement of the reference over the whole shard (the checker, not the product)
+            import oracle_lib
+            want, _ = oracle_lib.oracle().stream_chunked(shard, oracle_lib.DEFLATE, args.level, threads=os.cpu_count() or 1)
+            keep = len(want) if final else len(want) - (CHUNK + 64)       # the last chunk differs when the shard is not final
+            ok["rank0_bytes_equal_oracle"] = bool(out_len >= keep and got[:keep].tobytes() == want[:keep])
+            ok["oracle_compared_bytes"] = int(keep)
+        if e2e_ms is not None:
+            e2e_bytes = pinned_dst[:e2e_out].numpy()
+            wbits = {"zlib": 15, "gzip": 31, "deflate": -15}[args.format]
+            d2 = zlib.decompressobj(wbits)
+            pos2, good2 = 0, True
+            for lo in range(0, int(e2e_out), 64 << 20):
+                piece = d2.decompress(e2e_bytes[lo: lo + (64 << 20)].tobytes())
+                good2 = good2 and piece == shard[pos2: pos2 + len(piece)].tobytes()
+                pos2 += len(piece)
+            ok["e2e_inflate_equals_input"] = bool(good2 and pos2 == nbytes and d2.eof)       # includes zlib's own Adler-32 / CRC-32 check
+        meta = torch.tensor([out_len, a0, crc_v, nbytes, zlib.adler32(shard, 0), zlib.crc32(shard), int(all(v for v in ok.values() if isinstance(v, bool)))],
+                            dtype=torch.int64, device="cuda")
+        if dist is not None:
+            metas = [torch.zeros_like(meta) for _ in range(world)]
+            dist.all_gather(metas, meta)
+        else:
+            metas = [meta]
+        metas = [m.cpu().tolist() for m in metas]
+        # fold of the ranks' (checksum, length) pairs as the host driver does (zzgpu_adler32_combine / zzgpu_crc32_combine)
+        # against the same fold of zlib's per-shard values through the oracle's independent combine
+        if rank == 0:
+            import oracle_lib
+            o = oracle_lib.oracle()
+            fa, fc, wa, wc = 1, 0, 1, 0
+            for m in metas:
+                fa = zz.combine(fa, m[1], m[3]); fc = zz.crc32_combine(fc, m[2], m[3])
+                wa = o.combine(wa, m[4], m[3]); wc = o.crc32_combine(wc, m[5], m[3])
+            ok["folded_adler32"] = bool(fa == wa); ok["folded_crc32"] = bool(fc == wc)
+            ok["all_ranks_ok"] = bool(all(m[6] == 1 for m in metas))
+            ok["stream_bytes_all_ranks"] = int(sum(m[0] for m in metas))
+            verified = ok
+            if not all(v for v in ok.values() if isinstance(v, bool)):
+                print("VERIFICATION FAILED: " + json.dumps(ok), file=sys.stderr, flush=True)
+                if dist is not None:
+                    dist.destroy_process_group()
+                sys.exit(3)
 
     vals = torch.tensor([dev_ms, wall_ms, e2e_ms or 0.0, float(launches), float(out_len)], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -277,11 +344,14 @@ def main():
     chunks_per_launch = ((nbytes + CHUNK - 1) // CHUNK) / max(stage_n[dom] / args.steps, 1)
     alg_bytes = chunks_per_launch * CHUNK * (1.0 + ratio)            # 1 read + r written per input byte
     achieved = alg_bytes / (dom_avg_ms * 1e-3) / 1e9
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture (not
+    # measurable inside a plain run); the source of the number travels with it
+    traffic, traffic_src = None, None
     tp = ROOT / "profiles" / "traffic.json"
-    if tp.exists():
+    if tp.exists() and args.workload == "text" and args.level == 2 and args.shard_mib == 1024:
         try:
-            traffic = json.loads(tp.read_text()).get(names[dom])
+            tj = json.loads(tp.read_text())
+            traffic = tj.get(names[dom]); traffic_src = "profiles/traffic.json: " + str(tj.get("_source"))
         except Exception:
             traffic = None
     line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -291,14 +361,14 @@ def main():
             "stage_ms_per_step": {names[i]: round(stage_ms[i] / args.steps, 3) for i in range(len(_lib.STAGES)) if stage_n[i]},
 
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 5), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "avg_launch_ms": round(dom_avg_ms, 4),
                          "whole_path_frac": round(value * (1.0 + ratio) / peak, 5)},
-            "gpu_launches": launches, "clocks": clocks}
+            "gpu_launches": launches, "clocks": clocks, "verified": verified}
     if e2e_ms is not None:
         e2e_val = total_in / (e2e_ms_r / args.steps * 1e-3) / 1e9
         line["e2e"] = {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(e2e_out or 0),
-                       "ms_per_step": round(e2e_ms_r / args.steps, 3), "api": "ZzFlateEncode(Format=Deflate, level, threaded=false) on pinned host buffers"}
+                       "ms_per_step": round(e2e_ms_r / args.steps, 3), "api": f"ZzFlateEncode(Format={args.format}, level, threaded=false) on pinned host buffers (checksum of the trailer computed on the GPU inside the call)"}
     if not args.no_cpu_baseline:
         n_s = min(args.cpu_sample_mib << 20, nbytes)
         kind, cores, times, cpu_out = cpu_reference_run(host[hist: hist + n_s], 3, 1)

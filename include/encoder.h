@@ -9,6 +9,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <vector>
+#include "outputbitstream.h"      /* struct code, host bit writer */
 
 /* Adler-32 continuing from startValue (adler.cpp:17-43; true Adler-32, i.e. without the reference's
  * overflow above ~362 MiB). */
@@ -16,12 +17,6 @@ uint32_t adler32x(uint32_t startValue, const uint8_t* data, size_t len);
 
 /* Adler-32 of A||B from adler(A) and adler(B computed with start value 0) (adler.cpp:5-15). */
 uint32_t combine(uint32_t first, uint32_t second, size_t lenSecond);
-
-struct code          /* outputbitstream.h:14-24 : LSB-first bit string */
-{
-    int32_t length;
-    uint32_t bits;
-};
 
 /* Output side of an Encoder: what the reference exposes as `outputbitstream stream` (Flush,
  * byteswritten, streamStart).  Chunks always end byte-aligned here, so Flush has nothing left to pad. */
@@ -41,9 +36,12 @@ struct Encoder
 {
     Encoder(int level, uint8_t* outputBuffer = nullptr, int64_t bytes = 0);      /* encoder.cpp:527 */
 
-    /* Encodes [start,end) behind what was already written; `final` marks the last chunk BFINAL.  Data that
-     * directly follows the previous call in memory is primed with it as dictionary (the reference keeps
-     * its hash table across calls, encoder.cpp:248).  Returns false on error (encoder.cpp:539-551). */
+    /* Encodes [start,end) behind what was already written; `final` marks the last chunk BFINAL.  Successive calls
+     * continue one stream: each call is primed with the last 32 KiB (+288 bytes) the Encoder was fed, of which it
+     * keeps a private copy -- the caller's earlier buffers may be freed or reused (the reference keeps its hash table
+     * across calls, encoder.cpp:248,320-327, and silently requires the earlier bytes to stay in place in front of
+     * `start`).  Every call ends byte-aligned (E-mode, zzgpu.h), which the reference does not do between calls.
+     * Returns false on error (encoder.cpp:539-551). */
     bool AddData(const uint8_t* start, const uint8_t* end, bool final);
     void SetLevel(int newlevel) { level = newlevel; }
     bool AddDataGzip(const uint8_t* start, const uint8_t* end, uint32_t& adler, bool final);   /* encoder.cpp:554 */
@@ -56,8 +54,7 @@ struct Encoder
 
 private:
     int level;
-    const uint8_t* lastEnd = nullptr;
-    size_t contiguous = 0;           /* bytes before lastEnd that belong to this stream */
+    std::vector<uint8_t> tail;       /* the last <= 32 KiB + 288 bytes of the stream so far */
 };
 
 #endif

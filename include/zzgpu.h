@@ -81,10 +81,15 @@ ZZGPU_API int zzgpu_device_count(void);
 ZZGPU_API const char* zzgpu_strerror(int status);
 ZZGPU_API const char* zzgpu_last_error(void);
 
-/* Tuning knobs that do not change the produced bytes.  "overlap" (default 0): batches of 4096 chunks on two streams, so
- * that the candidate kernel of batch k+1 runs beside the Huffman / emit / checksum kernels of batch k.
- * "emit" (default 1): 1 = token-parallel bit emission, 0 = the position-range variant (same bytes, kept for A/B runs). */
+/* Tuning knobs that do not change the produced bytes (A/B switches of kernel variants; see zz_cabi.cu for the names).
+ * Unknown names return ZZGPU_E_ARG. */
 ZZGPU_API int zzgpu_set_option(const char* name, int value);
+
+/* Diagnostic counters of the calling thread's most recent streaming call (tests):
+ *   "sink_pieces"            pieces (H2D -> kernels -> D2H units) of the call
+ *   "sink_first_h2d_done"    pieces whose host-to-device copy had completed when the first data slice reached the sink
+ * Unknown names return -1. */
+ZZGPU_API long long zzgpu_get_counter(const char* name);
 
 /* Worst-case size of the raw deflate stream for n input bytes (A.6: 65 546 bytes per 65 536-byte chunk at
  * levels 0/2/3; 9 bits per literal at level 1). */
@@ -107,6 +112,39 @@ ZZGPU_API int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int
                                uint8_t* dst, size_t cap, int dst_mem,
                                int level, uint32_t chunk, uint32_t dict, int want_checksums,
                                size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats);
+
+/* Same as zzgpu_deflate_ex on host buffers, with the `hist_len` bytes of preceding stream given by their own pointer
+ * (they need not lie in front of src).  Used by Encoder::AddData, which keeps a private copy of the last
+ * 32 KiB + 288 bytes it was fed (the reference keeps its hash table across calls, encoder.cpp:248,320-327). */
+ZZGPU_API int zzgpu_deflate_hist(const uint8_t* src, size_t n, const uint8_t* hist, size_t hist_len, int final,
+                                 uint8_t* dst, size_t cap, int level, uint32_t chunk, uint32_t dict,
+                                 size_t* out_len);
+
+/* Streaming variant (replaces the growable-buffer mode of outputbitstream behind ZzFlateEncodeToCallback,
+ * zzflate/zzflate.cpp:197-222, outputbitstream.h:171-190): host input, the stream is handed to `sink` in order, in
+ * slices of at most `slice` bytes (0 = 1 000 000, the reference's buffer size), while later pieces are still being
+ * copied in and encoded.  Slice pointers are valid only during the sink call; its return value is ignored. */
+typedef int (*zzgpu_sink_fn)(const uint8_t* data, size_t len, void* user);
+ZZGPU_API int zzgpu_deflate_sink(const uint8_t* src, size_t n, size_t history, int final,
+                                 int level, uint32_t chunk, uint32_t dict, int want_checksums,
+                                 zzgpu_sink_fn sink, void* user, size_t slice,
+                                 size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats);
+
+/* Two-phase variant for shards whose place in the caller's buffer depends on earlier shards (stitch of
+ * zzflate.cpp:136-154 without a temporary and without a host-side memmove): zzgpu_deflate_hold encodes host input
+ * and keeps the stream in device memory, reporting its size; zzgpu_fetch then copies it to its final host address
+ * (dst != NULL) or hands it to a sink (dst == NULL), and releases the device's context.  Between the two calls the
+ * calling thread owns the device's context: other threads' calls on that device wait.  zzgpu_release drops a held
+ * stream without fetching it. */
+ZZGPU_API int zzgpu_deflate_hold(const uint8_t* src, size_t n, size_t history, int final,
+                                 int level, uint32_t chunk, uint32_t dict, int want_checksums,
+                                 size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats);
+ZZGPU_API int zzgpu_fetch(uint8_t* dst, size_t cap, zzgpu_sink_fn sink, void* user, size_t slice);
+ZZGPU_API void zzgpu_release(void);
+
+/* Size limits: host-buffer calls are processed in segments of at most 2 GiB of input (device staging is a ring of
+ * that size, so any input length works); device-resident calls use the caller's buffers in place; zzgpu_deflate_hold
+ * keeps zzgpu_bound(n) bytes of device memory until the fetch. */
 
 /* Adler-32 (continuing from adler_start, reference convention adler32x(start,...)) and CRC-32
  * (continuing from crc_start, reference convention crc32(buf,len,start)) of a buffer, on the GPU. */

@@ -86,6 +86,103 @@ def test_callback_api(zz, golden):
             assert len(pieces) >= 4
 
 
+def test_callback_api_streams(zz, oracle):
+    """N2 (zzflate.cpp:197-222 on the GPU): the callback receives the first data while later pieces of the input have
+    not even been copied to the device, and nothing of the size of the stream is buffered: 600 MiB of pageable input
+    are cut into 4 pieces (H2D -> kernels -> D2H), the first slice must arrive before the last piece's H2D is done."""
+    from zzflate_b200 import synth, _lib
+    n = 600 << 20
+    data = synth.markov_text(n, seg0=5)
+    lib = _lib.load()
+    state = {"first_at": None, "bytes": 0, "adler": 1, "crc": 0}
+    d = zlib.decompressobj(15)
+    pos = [0]
+    ok = [True]
+
+    def sink(b):
+        if len(b) > 4 and state["first_at"] is None and pos[0] == 0 and state["bytes"] >= 2:
+            state["first_at"] = (lib.zzgpu_get_counter(b"sink_first_h2d_done"), lib.zzgpu_get_counter(b"sink_pieces"))
+        state["bytes"] += len(b)
+        piece = d.decompress(b)
+        ok[0] = ok[0] and piece == data[pos[0]: pos[0] + len(piece)].tobytes()
+        pos[0] += len(piece)
+        assert len(b) <= 1000000
+        return False
+
+    zz.ZzFlateEncodeToCallback(data, zz.Config(zz.Format.Zlib, 2, False), sink)
+    assert ok[0] and pos[0] == n and d.eof
+    done, pieces = lib.zzgpu_get_counter(b"sink_first_h2d_done"), lib.zzgpu_get_counter(b"sink_pieces")
+    assert pieces == 4 and 1 <= done < pieces, (done, pieces)
+
+
+def test_hold_and_fetch(zz, oracle, golden):
+    """zzgpu_deflate_hold / zzgpu_fetch (the stitch of zzflate.cpp:136-154 without a temporary): same bytes as the
+    one-call path, to memory and to a sink; a second call of the holding thread is refused until the fetch."""
+    import ctypes as C
+    from zzflate_b200 import _lib
+    lib = _lib.load()
+    data = np.frombuffer(golden.input("markov"), dtype=np.uint8)
+    want, a0w, crcw, _ = zz.deflate_raw(data, level=2)
+    out_len = C.c_size_t(0); a0 = C.c_uint32(0); crc = C.c_uint32(0)
+    _lib.check(lib.zzgpu_deflate_hold(data.ctypes.data, data.size, 0, 1, 2, 0, 32768, 3, C.byref(out_len), C.byref(a0), C.byref(crc), None))
+    assert out_len.value == len(want) and a0.value == a0w and crc.value == crcw
+    dummy = C.c_size_t(0)
+    assert lib.zzgpu_deflate_ex(data.ctypes.data, 100, 0, 1, 0, None, 0, 0, 2, 0, 32768, 0, C.byref(dummy), None, None, None) == _lib.E_ARG
+    dst = np.zeros(out_len.value + 7, dtype=np.uint8)
+    _lib.check(lib.zzgpu_fetch(dst.ctypes.data + 3, out_len.value, _lib.SINK_FN(0), None, 0))
+    assert dst[3: 3 + out_len.value].tobytes() == want
+    assert lib.zzgpu_fetch(dst.ctypes.data, dst.size, _lib.SINK_FN(0), None, 0) == _lib.E_ARG      # nothing held any more
+    got = []
+    cb = _lib.SINK_FN(lambda p, n_, u: got.append(C.string_at(p, n_)) or 0)
+    _lib.check(lib.zzgpu_deflate_hold(data.ctypes.data, data.size, 0, 1, 2, 0, 32768, 0, C.byref(out_len), None, None, None))
+    _lib.check(lib.zzgpu_fetch(None, 0, cb, None, 50000))
+    assert b"".join(got) == want and max(map(len, got)) <= 50000
+    _lib.check(lib.zzgpu_deflate_hold(data.ctypes.data, data.size, 0, 1, 2, 0, 32768, 0, C.byref(out_len), None, None, None))
+    lib.zzgpu_release()
+    assert zz.deflate_raw(data, level=2)[0] == want
+
+
+def test_host_input_in_segments(zz, oracle):
+    """Host-buffer calls stage at most one segment (2 GiB by default) on the device; with 64 MiB segments a 200 MiB call
+    runs as four, each primed with the 32 KiB before it: same bytes and checksums as one segment."""
+    from zzflate_b200 import synth, _lib
+    lib = _lib.load()
+    n = (200 << 20) + 4321
+    data = synth.markov_text(n, seg0=9)
+    want, _ = oracle.stream_chunked(data, GZIP, 2, threads=8)
+    assert lib.zzgpu_set_option(b"segment_mib", 64) == 0
+    try:
+        assert zz.ZzFlateEncode(data, zz.Config(zz.Format.Gzip, 2, False)) == want
+        pieces = []
+        zz.ZzFlateEncodeToCallback(data, zz.Config(zz.Format.Gzip, 2, False), lambda b: pieces.append(b) or False)
+        assert b"".join(pieces) == want
+        assert zz.adler32x(1, data) == zlib.adler32(data)
+    finally:
+        assert lib.zzgpu_set_option(b"segment_mib", 2048) == 0
+
+
+@pytest.mark.parametrize("fmt,ofmt,wbits", [("Zlib", ZLIB, 15), ("Gzip", GZIP, 31)])
+def test_threaded_on_several_gpus(zz, oracle, fmt, ofmt, wbits):
+    """Config.threaded on a multi-GPU host (zzflate.cpp:97-154): contiguous chunk ranges per device, only the last shard
+    with data final, stitched in place, checksums folded -- byte-identical to the single-stream oracle.  Chunk counts
+    9, 12 and 17 used to leave trailing empty shards on 4 / 8 GPUs."""
+    ndev = zz.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    from zzflate_b200 import synth
+    for nchunks, tail in ((9, 0), (12, 5), (17, 60000), (8 * ndev, 0), (700, 123)):
+        data = synth.markov_text(nchunks * S - tail, seg0=3)
+        want, _ = oracle.stream_chunked(data, ofmt, 2, threads=8)
+        for level in (2, 1, 0):
+            w = want if level == 2 else oracle.stream_chunked(data, ofmt, level, threads=8)[0]
+            got = zz.ZzFlateEncode(data, zz.Config(zz.Format[fmt], level, True))
+            assert got == w, (nchunks, level)
+            assert zlib.decompress(got, wbits) == data.tobytes()
+        pieces = []
+        zz.ZzFlateEncodeToCallback(data, zz.Config(zz.Format[fmt], 2, True), lambda b: pieces.append(b) or False)
+        assert b"".join(pieces) == want, nchunks
+
+
 def test_error_behaviour(zz, golden):
     data = golden.input("alice29")
     assert zz.ZzFlateEncode(data, zz.Config(zz.Format.Zlib, 4, False)) is None            # zzflate.cpp:230
@@ -170,6 +267,32 @@ def test_encoder_object(zz, golden):
     out = C.string_at(lib.zz_c_encoder_data(e), n)
     lib.zz_c_encoder_free(e)
     assert zlib.decompress(out, -15) == data.tobytes()
+    # the dictionary is the Encoder's private copy of what it was fed: a second buffer anywhere in memory continues the
+    # stream exactly as if the data had been contiguous
+    e = lib.zz_c_encoder_new(2, None, 0)
+    cut = 2 * S
+    first = data[:cut].copy(); second = data[cut:].copy()
+    assert lib.zz_c_encoder_add_data(e, first.ctypes.data, cut, 0) == 1
+    first[:] = 0                                                     # the caller's earlier buffer is no longer needed
+    assert lib.zz_c_encoder_add_data(e, second.ctypes.data, second.size, 1) == 1
+    n = lib.zz_c_encoder_bytes(e)
+    out = C.string_at(lib.zz_c_encoder_data(e), n)
+    lib.zz_c_encoder_free(e)
+    from oracle_lib import oracle as get_oracle
+    assert out == get_oracle().stream_chunked(data, DEFLATE, 2)[0]
+
+
+def test_cpp_caller_against_the_headers(zz, golden, tmp_path):
+    """tests/cpp/boundary_test.cpp: a C++14 translation unit that includes include/zzflate.h, encoder.h, crc.h,
+    huffman.h, outputbitstream.h and links libzzflate_b200.so -- the reference's own tests (Test.cpp:202-338,
+    TestHuffman.cpp, TestBitOutput.cpp) re-hosted with plain checks."""
+    import subprocess
+    from zzflate_b200 import build
+    exe = build.build_boundary_test()
+    f = tmp_path / "adinsight.bin"
+    f.write_bytes(golden.input("adinsight"))
+    r = subprocess.run([str(exe), str(f)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "boundary ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_device_resident_buffers(zz, oracle):
@@ -224,7 +347,7 @@ def test_short_fuzz_run(zz):
 
 def test_host_buffers_pipelined_path(zz, oracle):
     """Inputs >= 32 MiB on host buffers go through the piece-wise path (H2D / kernels / D2H overlapped on three
-    streams); the bytes must not depend on how the call was cut into pieces, nor on the batch-overlap option."""
+    streams); the bytes must not depend on how the call was cut into pieces."""
     import ctypes as C
     from zzflate_b200 import synth, _lib
     n = (96 << 20) + 12345
@@ -236,11 +359,7 @@ def test_host_buffers_pipelined_path(zz, oracle):
         got = zz.ZzFlateEncode(data, zz.Config(zz.Format.Zlib, 2, threaded))
         assert got == want
     lib = _lib.load()
-    assert lib.zzgpu_set_option(b"overlap", 1) == 0
-    try:
-        out, a0, crc, st = zz.deflate_raw(data, level=2)
-    finally:
-        lib.zzgpu_set_option(b"overlap", 0)
+    out, a0, crc, st = zz.deflate_raw(data, level=2)
     assert out == want[2:-4]
     assert zz.combine(1, a0, n) == zlib.adler32(data) and crc == zlib.crc32(data)
     assert lib.zzgpu_set_option(b"no-such-option", 1) == _lib.E_ARG
@@ -249,45 +368,42 @@ def test_host_buffers_pipelined_path(zz, oracle):
 
 
 def test_kernel_variants_give_the_same_bytes(zz, oracle, golden):
-    """K-EMIT has two variants (symbol-parallel, the default, and the position-range walk behind the "emit" option) and
-    K-HUFF two (warp per chunk for launches of one wave, thread per chunk for full batches, picked by launch size):
-    every combination must give the oracle's bytes."""
-    from zzflate_b200 import synth, _lib
-    lib = _lib.load()
+    """K-HUFF has two variants (warp per chunk for launches of one wave, thread per chunk for full batches, picked by
+    launch size): both must give the oracle's bytes."""
+    from zzflate_b200 import synth
     small = golden.input("mixed")                                # a few chunks: warp-per-chunk K-HUFF
     n = 8000 * S + 777                                           # > 148 * 52 chunks: thread-per-chunk K-HUFF
     big = synth.markov_text(n, seg0=3)
     big[5 * S: 6 * S] = synth.random_bytes(S)                    # a stored chunk, a run of zeros and few-symbol data in between
     big[9 * S: 9 * S + 3000] = 0
     big[11 * S: 12 * S] = synth.random_bytes(S) % 7 + 48
-    want_small, _ = oracle.stream_chunked(small, DEFLATE, 2)
-    want_big, _ = oracle.stream_chunked(big, DEFLATE, 2, threads=8)
-    try:
-        for variant in (0, 1):
-            assert lib.zzgpu_set_option(b"emit", variant) == 0
-            assert zz.deflate_raw(small, level=2)[0] == want_small, variant
-            assert zz.deflate_raw(big, level=2)[0] == want_big, variant
-    finally:
-        lib.zzgpu_set_option(b"emit", 1)
+    assert zz.deflate_raw(small, level=2)[0] == oracle.stream_chunked(small, DEFLATE, 2)[0]
+    assert zz.deflate_raw(big, level=2)[0] == oracle.stream_chunked(big, DEFLATE, 2, threads=8)[0]
 
 
-@pytest.mark.parametrize("workload,size_mib", [("text", 1024), ("text", 1088), ("random", 256), ("zeros", 256), ("pattern", 256)])
-def test_baseline_sizes_round_trip(zz, workload, size_mib):
-    """BASELINE.json configs 2-4 at full size: every output inflates through zlib to the input and the
-    checksums agree with zlib's (size-independent properties; the oracle covers a 32 MiB prefix bit-exactly).
-    1088 MiB = 17 408 chunks crosses the 16 384-chunk scratch batch."""
+@pytest.mark.parametrize("workload,size_mib,level", [("text", 1024, 2), ("text", 1088, 2), ("random", 1024, 2), ("zeros", 1024, 2),
+                                                     ("pattern", 1024, 2), ("random", 1024, 1), ("text", 1024, 1), ("random", 1024, 0)])
+def test_baseline_sizes_bit_exact(zz, workload, size_mib, level):
+    """BASELINE.json configs 2-4 at full size (1 GiB; 1088 MiB = 17 408 chunks crosses the 16 384-chunk scratch batch):
+    the whole stream equals the (multi-threaded) oracle's byte for byte, inflates through zlib to the input, and the
+    checksums agree with zlib's."""
+    import os
     import torch
     from oracle_lib import oracle as get_oracle
     from zzflate_b200 import synth
     n = size_mib << 20
     data = synth.workload(workload, n)
     src = torch.from_numpy(data).cuda()
-    dst = torch.empty(zz.bound(n), dtype=torch.uint8, device="cuda")
+    dst = torch.empty(zz.bound(n, level), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
-    out_len, a0, crc, st = zz.deflate_device(src.data_ptr(), n, dst.data_ptr(), dst.numel(), level=2, checksums=3)
+    out_len, a0, crc, st = zz.deflate_device(src.data_ptr(), n, dst.data_ptr(), dst.numel(), level=level, checksums=3)
     out = dst[:out_len].cpu().numpy()
+    del src, dst
     assert zz.combine(1, a0, n) == zlib.adler32(data)
     assert crc == zlib.crc32(data)
+    want, _ = get_oracle().stream_chunked(data, DEFLATE, level, threads=os.cpu_count() or 8)
+    assert out_len == len(want)
+    assert out.tobytes() == want
     d = zlib.decompressobj(-15)
     pos = 0
     step = 64 << 20
@@ -296,8 +412,3 @@ def test_baseline_sizes_round_trip(zz, workload, size_mib):
         assert piece == data[pos: pos + len(piece)].tobytes()
         pos += len(piece)
     assert pos == n and d.eof
-    prefix = 32 << 20
-    want, _ = get_oracle().stream_chunked(data[:prefix], DEFLATE, 2, threads=8)
-    # all but the last chunk of the prefix are non-final in both streams
-    keep = len(want) - 70000
-    assert out[:keep].tobytes() == want[:keep]

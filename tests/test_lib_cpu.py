@@ -35,6 +35,14 @@ def test_cpp_api_symbols_present():
         assert sym in out, sym
 
 
+def test_cpp_caller_compiles_against_the_headers(lib):
+    """The boundary TU (tests/cpp/boundary_test.cpp) compiles as C++14 against include/*.h and links the library;
+    without a GPU only its host-only checks can pass, so it is just built here and run by the GPU tests."""
+    from zzflate_b200 import build
+    exe = build.build_boundary_test(force=True)
+    assert exe.exists()
+
+
 def test_kernels_are_sm100a(lib):
     import shutil, subprocess
     from zzflate_b200 import _lib
@@ -55,6 +63,35 @@ def test_no_cpu_fallback_without_device(lib):
         deflate_raw(b"hello hello hello", level=2)
     assert e.value.status == _lib.E_NO_DEVICE
     assert ZzFlateEncode(b"hello", Config(Format.Zlib, 2, False)) is None       # *destLen = ~0
+    from zzflate_b200 import ZzFlateEncodeToCallback
+    got = []
+    ZzFlateEncodeToCallback(b"hello", Config(Format.Zlib, 2, False), lambda b: got.append(b) or False)
+    assert got == []                                                            # nothing is delivered, not even the header
+    out_len = C.c_size_t(0)
+    assert lib.zzgpu_deflate_hold(None, 0, 0, 1, 2, 0, 0, 0, C.byref(out_len), None, None, None) == _lib.E_NO_DEVICE
+    assert lib.zzgpu_fetch(None, 0, _lib.SINK_FN(0), None, 0) == _lib.E_NO_DEVICE
+
+
+def test_shard_partition_of_the_multi_gpu_driver(lib):
+    """zz_host.cpp partition(): contiguous whole-chunk ranges that cover the input, no empty shard, exactly the last
+    shard final -- for every chunk count that used to leave trailing empty shards (5, 6, 9 chunks on 4 GPUs; 9-14,
+    17-21, ... on 8)."""
+    S = 65536
+    for ndev in (1, 2, 3, 4, 7, 8, 16):
+        for nchunks in list(range(0, 70)) + [16384, 16385]:
+            for tail in (0, 1, S - 1):
+                n = max(nchunks * S - tail, 0) if nchunks else 0
+                buf = (C.c_uint64 * (3 * 16))()
+                k = lib.zz_c_partition(n, ndev, S, buf, 16)
+                assert 1 <= k <= ndev
+                pos = 0
+                for g in range(k):
+                    off, ln, fin = buf[3 * g], buf[3 * g + 1], buf[3 * g + 2]
+                    assert off == pos and off % S == 0
+                    assert ln > 0 or n == 0
+                    assert fin == (1 if g == k - 1 else 0)
+                    pos += ln
+                assert pos == n
 
 
 def test_bound_matches_oracle(lib, oracle):

@@ -40,8 +40,11 @@ STAGES = ["cand", "parse", "huff", "offs", "emit", "cksum", "fixed", "gather", "
 SYMBOLS = [
     "zzgpu_init", "zzgpu_shutdown", "zzgpu_device_count", "zzgpu_strerror", "zzgpu_last_error", "zzgpu_bound",
     "zzgpu_deflate", "zzgpu_deflate_ex", "zzgpu_checksums", "zzgpu_adler32_combine", "zzgpu_crc32_combine",
-    "zzgpu_debug_chunk", "zzgpu_set_option",
+    "zzgpu_debug_chunk", "zzgpu_set_option", "zzgpu_get_counter", "zzgpu_deflate_hist", "zzgpu_deflate_sink",
+    "zzgpu_deflate_hold", "zzgpu_fetch", "zzgpu_release",
 ]
+
+SINK_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.c_void_p)
 
 _lib = None
 
@@ -78,6 +81,22 @@ def load() -> C.CDLL:
     lib.zzgpu_crc32_combine.restype = C.c_uint32
     lib.zzgpu_crc32_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
     lib.zzgpu_set_option.restype = C.c_int; lib.zzgpu_set_option.argtypes = [C.c_char_p, C.c_int]
+    lib.zzgpu_get_counter.restype = C.c_longlong; lib.zzgpu_get_counter.argtypes = [C.c_char_p]
+    lib.zzgpu_deflate_hist.restype = C.c_int
+    lib.zzgpu_deflate_hist.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
+                                       C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t)]
+    lib.zzgpu_deflate_sink.restype = C.c_int
+    lib.zzgpu_deflate_sink.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
+                                       SINK_FN, C.c_void_p, C.c_size_t,
+                                       C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(Stats)]
+    lib.zzgpu_deflate_hold.restype = C.c_int
+    lib.zzgpu_deflate_hold.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int,
+                                       C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(Stats)]
+    lib.zzgpu_fetch.restype = C.c_int
+    lib.zzgpu_fetch.argtypes = [C.c_void_p, C.c_size_t, SINK_FN, C.c_void_p, C.c_size_t]
+    lib.zzgpu_release.restype = None
+    lib.zz_c_partition.restype = C.c_int
+    lib.zz_c_partition.argtypes = [C.c_size_t, C.c_int, C.c_uint32, C.POINTER(C.c_uint64), C.c_int]
     lib.zzgpu_debug_chunk.restype = C.c_int
     lib.zzgpu_debug_chunk.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64,
                                       C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32),

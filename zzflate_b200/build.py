@@ -15,7 +15,7 @@ CSRC = PKG_DIR / "csrc"
 LIB = PKG_DIR / "libzzflate_b200.so"
 SOURCES = ["zz_kernels.cu", "zz_cabi.cu", "zz_host.cpp"]
 DEPS = SOURCES + ["zz_kernels.cuh", "../../include/zzgpu.h", "../../include/zzflate.h",
-                  "../../include/encoder.h", "../../include/crc.h"]
+                  "../../include/encoder.h", "../../include/crc.h", "../../include/outputbitstream.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
@@ -54,7 +54,25 @@ def build_synth(force: bool = False) -> Path:
     return SYNTH_LIB
 
 
+BOUNDARY_SRC = PKG_DIR.parent / "tests" / "cpp" / "boundary_test.cpp"
+BOUNDARY_BIN = PKG_DIR.parent / "tests" / "cpp" / "_build" / "boundary_test"
+
+
+def build_boundary_test(force: bool = False) -> Path:
+    """tests/cpp/boundary_test.cpp: a C++14 caller compiled against include/*.h and linked to the library (the
+    reference's own tests re-hosted); run by the GPU tests."""
+    build()
+    deps = [BOUNDARY_SRC, LIB] + [PKG_DIR.parent / "include" / h for h in ("zzflate.h", "encoder.h", "crc.h", "huffman.h", "outputbitstream.h")]
+    if force or not BOUNDARY_BIN.exists() or any(d.stat().st_mtime > BOUNDARY_BIN.stat().st_mtime for d in deps):
+        BOUNDARY_BIN.parent.mkdir(parents=True, exist_ok=True)
+        cxx = shutil.which("g++") or "c++"
+        subprocess.check_call([cxx, "-std=c++14", "-O1", "-Wall", "-o", str(BOUNDARY_BIN), str(BOUNDARY_SRC),
+                               "-L" + str(PKG_DIR), "-lzzflate_b200", "-lz", "-Wl,-rpath," + str(PKG_DIR)])
+    return BOUNDARY_BIN
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_synth(force="--force" in sys.argv))
+    print(build_boundary_test(force="--force" in sys.argv))

@@ -5,6 +5,7 @@
 #include "zz_kernels.cuh"
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -21,14 +22,24 @@ using namespace zz;
 
 constexpr uint32_t kMaxSlots = 16384;       // chunks per batch (scratch is sized for one batch)
 constexpr int kMaxDevices = 16;
+size_t g_segBytes = (size_t)2 << 30;             // host-buffer calls: input bytes staged on the device at a time ("segment_mib" option)
+constexpr size_t kPipelineMin = (size_t)32 << 20;   // host inputs from this size on are cut into overlapping pieces
+constexpr size_t kDefaultSlice = 1000000;   // outputbitstream.h:183
 
 thread_local std::string t_lastError;
 thread_local int t_device = -1;
+thread_local long long t_sinkPieces = 0, t_sinkFirstH2dDone = 0;
 
 struct Ctx {
     int device = -1;
     bool ready = false;
+    // one call at a time per device; a held stream (zzgpu_deflate_hold) keeps the context until the fetch
     std::mutex mu;
+    std::condition_variable cv;
+    bool busy = false;
+    bool held = false;
+    std::thread::id holder;
+    size_t heldLen = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     uint32_t slots = 0;
@@ -47,9 +58,6 @@ struct Ctx {
     cudaEvent_t stageInEv[2] = { nullptr, nullptr }, stageOutEv[2] = { nullptr, nullptr };
     std::vector<cudaEvent_t> pieceEv;
     uint64_t* hPiece = nullptr; size_t hPieceCap = 0;     // pinned: running totals after each piece
-    cudaStream_t lane[3] = { nullptr, nullptr, nullptr };  // overlap option: front-end and back-end streams
-    cudaEvent_t laneEv[3] = { nullptr, nullptr, nullptr };
-    std::vector<cudaEvent_t> offsEv;        // offsets scan of batch k (the next batch's scan continues its running total)
     std::vector<cudaEvent_t> stageEv;       // pool of events bracketing each stage launch
     std::vector<int> stageOf;               // stage id of the interval that ENDS at event i (-1: start marker)
     size_t stageUsed = 0;
@@ -67,11 +75,82 @@ int fail(int status, const char* what, cudaError_t e = cudaSuccess)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ZZGPU_E_CUDA, #call, e_); } while (0)
 
+// Exclusive use of a device context for the duration of one call (or until the fetch of a held stream).
+class Lease {
+public:
+    explicit Lease(Ctx& c) : c_(c)
+    {
+        std::unique_lock<std::mutex> lk(c.mu);
+        const std::thread::id me = std::this_thread::get_id();
+        if (c.busy && c.held && c.holder == me) { resumed_ = true; return; }       // the holder comes back (fetch / release)
+        c.cv.wait(lk, [&] { return !c.busy; });
+        c.busy = true; c.holder = me; c.held = false;
+    }
+    ~Lease()
+    {
+        std::lock_guard<std::mutex> lk(c_.mu);
+        if (resumed_ && !consume_) return;          // the hold goes on (the call was refused)
+        if (keep_) { c_.held = true; return; }
+        c_.busy = false; c_.held = false;
+        c_.cv.notify_all();
+    }
+    bool resumed() const { return resumed_; }       // this thread already held a stream on the context
+    void keep() { keep_ = true; }                   // the call leaves a held stream behind
+    void consume() { consume_ = true; }             // the call ends this thread's hold
+private:
+    Ctx& c_;
+    bool resumed_ = false, keep_ = false, consume_ = false;
+};
+
 void freeScratch(Ctx& c)
 {
     cudaFree(c.cand); cudaFree(c.info); cudaFree(c.tokA); cudaFree(c.tokD); cudaFree(c.hist); cudaFree(c.codes); cudaFree(c.state);
     c.cand = nullptr; c.info = nullptr; c.tokA = nullptr; c.tokD = nullptr; c.hist = nullptr; c.codes = nullptr; c.state = nullptr;
-    c.slots = 0;
+    c.slots = 0; c.slotChunk = 0;
+}
+
+// Releases everything a context owns and returns it to the default-constructed state (shutdown, failed set-up).
+void destroyCtx(Ctx& c)
+{
+    if (c.device >= 0) cudaSetDevice(c.device);
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    if (c.copyIn) cudaStreamSynchronize(c.copyIn);
+    if (c.copyOut) cudaStreamSynchronize(c.copyOut);
+    freeScratch(c);
+    cudaFree(c.total); cudaFreeHost(c.hTotal); cudaFree(c.ck); cudaFreeHost(c.hCk); cudaFree(c.dIn); cudaFree(c.dOut);
+    cudaFreeHost(c.hPiece);
+    for (auto& e : c.pieceEv) cudaEventDestroy(e);
+    for (auto& e : c.stageEv) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (c.stageIn[i]) cudaFreeHost(c.stageIn[i]);
+        if (c.stageOut[i]) cudaFreeHost(c.stageOut[i]);
+        if (c.stageInEv[i]) cudaEventDestroy(c.stageInEv[i]);
+        if (c.stageOutEv[i]) cudaEventDestroy(c.stageOutEv[i]);
+    }
+    if (c.copyIn) cudaStreamDestroy(c.copyIn);
+    if (c.copyOut) cudaStreamDestroy(c.copyOut);
+    for (auto& e : c.ev) if (e) cudaEventDestroy(e);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    (void)cudaGetLastError();
+    c.device = -1; c.ready = false; c.heldLen = 0;
+    c.stream = nullptr; for (auto& e : c.ev) e = nullptr;
+    c.total = nullptr; c.hTotal = nullptr; c.ck = nullptr; c.ckCap = 0; c.hCk = nullptr; c.hCkCap = 0;
+    c.dIn = nullptr; c.dInCap = 0; c.dOut = nullptr; c.dOutCap = 0; c.copyIn = nullptr; c.copyOut = nullptr;
+    for (int i = 0; i < 2; ++i) { c.stageIn[i] = c.stageOut[i] = nullptr; c.stageInEv[i] = c.stageOutEv[i] = nullptr; }
+    c.pieceEv.clear(); c.hPiece = nullptr; c.hPieceCap = 0;
+    c.stageEv.clear(); c.stageOf.clear(); c.stageUsed = 0;
+}
+
+int setUpCtx(Ctx& c, int dev)
+{
+    CK(cudaSetDevice(dev));
+    c.device = dev;
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (auto& e : c.ev) CK(cudaEventCreate(&e));
+    CK(cudaMalloc(&c.total, 4 * sizeof(uint64_t)));
+    CK(cudaMallocHost(&c.hTotal, 4 * sizeof(uint64_t)));
+    CK(configure_kernels());
+    return ZZGPU_OK;
 }
 
 int ensureCtx(Ctx*& out)
@@ -89,13 +168,8 @@ int ensureCtx(Ctx*& out)
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (!c.ready) {
-            CK(cudaSetDevice(dev));
-            CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-            for (auto& e : c.ev) CK(cudaEventCreate(&e));
-            CK(cudaMalloc(&c.total, 4 * sizeof(uint64_t)));
-            CK(cudaMallocHost(&c.hTotal, 4 * sizeof(uint64_t)));
-            CK(configure_kernels());
-            c.device = dev;
+            const int rc = setUpCtx(c, dev);
+            if (rc) { const std::string keep = t_lastError; destroyCtx(c); t_lastError = keep; return rc; }
             c.ready = true;
         }
     }
@@ -108,13 +182,16 @@ int ensureScratch(Ctx& c, uint32_t slots, uint32_t chunk)
 {
     if (c.slots >= slots && c.slotChunk >= chunk) return ZZGPU_OK;
     freeScratch(c);
-    CK(cudaMalloc(&c.cand, (size_t)slots * chunk * sizeof(uint16_t)));
-    CK(cudaMalloc(&c.info, (size_t)slots * chunk));
-    CK(cudaMalloc(&c.tokA, (size_t)slots * kMaxTokens * sizeof(uint32_t)));
-    CK(cudaMalloc(&c.tokD, (size_t)slots * kMaxTokens * sizeof(uint16_t)));
-    CK(cudaMalloc(&c.hist, (size_t)slots * kHistStride * sizeof(uint32_t)));
-    CK(cudaMalloc(&c.codes, (size_t)slots * sizeof(ChunkCodes)));
-    CK(cudaMalloc(&c.state, (size_t)slots * sizeof(ChunkState)));
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](auto& p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(&p, bytes); };
+    alloc(c.cand, (size_t)slots * chunk * sizeof(uint16_t));
+    alloc(c.info, (size_t)slots * chunk);
+    alloc(c.tokA, (size_t)slots * kMaxTokens * sizeof(uint32_t));
+    alloc(c.tokD, (size_t)slots * kMaxTokens * sizeof(uint16_t));
+    alloc(c.hist, (size_t)slots * kHistStride * sizeof(uint32_t));
+    alloc(c.codes, (size_t)slots * sizeof(ChunkCodes));
+    alloc(c.state, (size_t)slots * sizeof(ChunkState));
+    if (e != cudaSuccess) { freeScratch(c); (void)cudaGetLastError(); return fail(ZZGPU_E_NOMEM, "scratch allocation failed", e); }
     c.slots = slots; c.slotChunk = chunk;
     return ZZGPU_OK;
 }
@@ -126,7 +203,7 @@ int ensureBuf(T*& p, size_t& cap, size_t need, bool pinned = false)
     if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
     size_t bytes = std::max<size_t>(need, 256) * sizeof(T);
     cudaError_t e = pinned ? cudaMallocHost(&p, bytes) : cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) return fail(ZZGPU_E_NOMEM, "allocation failed", e);
+    if (e != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); return fail(ZZGPU_E_NOMEM, "allocation failed", e); }
     cap = std::max<size_t>(need, 256);
     return ZZGPU_OK;
 }
@@ -159,6 +236,7 @@ void collectStages(Ctx& c, zzgpu_stats* stats)
         float ms = 0;
         if (cudaEventElapsedTime(&ms, c.stageEv[i - 1], c.stageEv[i]) == cudaSuccess) { stats->stage_ms[st] += ms; stats->stage_launches[st]++; }
     }
+    (void)cudaGetLastError();                    // timing queries must never poison the next call
 }
 
 // Parallel memcpy between pageable caller memory and the pinned staging blocks (a single host thread moves
@@ -238,94 +316,45 @@ int preparePipeline(Ctx& c, size_t n, uint32_t chunk, int wantCk)
     return ZZGPU_OK;
 }
 
-constexpr uint32_t kLaneChunks = 4096;      // chunks per batch when batches overlap
-int g_overlap = 0;                          // zzgpu_set_option("overlap", 0/1)
-
 Job makeJob(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap, int level,
-            uint32_t chunk, uint32_t dict, int wantCk, uint64_t first, uint32_t count, size_t so)
+            uint32_t chunk, uint32_t dict, int wantCk, uint64_t first, uint32_t count)
 {
     Job job{};
     job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
     job.first_chunk = first; job.nchunks = count;
     job.final_stream = final; job.level = level; job.want_checksums = wantCk;
-    job.cand = c.cand + so * chunk; job.info = c.info + so * chunk; job.tokA = c.tokA + so * kMaxTokens; job.tokD = c.tokD + so * kMaxTokens;
-    job.hist = c.hist + so * kHistStride; job.codes = c.codes + so; job.state = c.state + so;
+    job.cand = c.cand; job.info = c.info; job.tokA = c.tokA; job.tokD = c.tokD;
+    job.hist = c.hist; job.codes = c.codes; job.state = c.state;
     job.dst = d_dst; job.cap = cap; job.total = c.total; job.ck = c.ck;
     return job;
 }
 
-// Kernel pipeline over chunks [firstChunk, lastChunk) of the call (geometry is always that of the whole call).
-//
-// Default: batches of up to 16 384 chunks, kernels back to back on one stream.
-// "overlap" option: batches of 4096 chunks on two streams with two scratch slices.  Stream A runs K-CAND and K-MATCH,
-// stream B runs K-HUFF, K-OFFS, K-EMIT, K-CKSUM.  K-MATCH needs whole SMs (its CTA takes all shared memory), so it
-// is ordered after the previous batch's K-EMIT; what overlaps is K-CAND of batch k+1 (one warp + 34 KiB per CTA) with
-// the back end of batch k.
+// Kernel pipeline over chunks [firstChunk, lastChunk) of the call (geometry is always that of the whole call):
+// batches of up to 16 384 chunks, kernels back to back on one stream.
 int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap,
               int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t firstChunk, uint64_t lastChunk, uint64_t& launches)
 {
     int rc;
-    const uint64_t count = lastChunk - firstChunk;
-    const bool overlap = g_overlap && level >= 2 && count >= 2 * kLaneChunks && c.slots >= 2 * kLaneChunks;
-    if (!overlap) {
-        for (uint64_t first = firstChunk; first < lastChunk; first += c.slots) {
-            const Job job = makeJob(c, d_src, n, history, final, d_dst, cap, level, chunk, dict, wantCk, first,
-                                    (uint32_t)std::min<uint64_t>(c.slots, lastChunk - first), 0);
-            cudaStream_t st = c.stream;
-            rc = markStage(c, -1, st); if (rc) return rc;
-            if (level >= 2) {
-                launches += launch_candidates(job, st); rc = markStage(c, ZZGPU_STAGE_CAND, st); if (rc) return rc;
-                launches += launch_info(job, st); rc = markStage(c, ZZGPU_STAGE_INFO, st); if (rc) return rc;
-                launches += launch_parse(job, st); rc = markStage(c, ZZGPU_STAGE_PARSE, st); if (rc) return rc;
-            }
-            if (level == 1) {
-                launches += launch_fixed(job, st); rc = markStage(c, ZZGPU_STAGE_FIXED, st); if (rc) return rc;
-            } else {
-                launches += launch_huffman(job, st); rc = markStage(c, ZZGPU_STAGE_HUFF, st); if (rc) return rc;
-            }
-            launches += launch_offsets(job, st); rc = markStage(c, ZZGPU_STAGE_OFFS, st); if (rc) return rc;
-            if (level == 1) { launches += launch_gather(job, st); rc = markStage(c, ZZGPU_STAGE_GATHER, st); if (rc) return rc; }
-            else { launches += launch_emit(job, st); rc = markStage(c, ZZGPU_STAGE_EMIT, st); if (rc) return rc; }
-            if (wantCk) { launches += launch_checksums(job, st); rc = markStage(c, ZZGPU_STAGE_CKSUM, st); if (rc) return rc; }
-        }
-        CK(cudaGetLastError());
-        return ZZGPU_OK;
-    }
-
-    for (int i = 0; i < 2; ++i)
-        if (!c.lane[i]) { CK(cudaStreamCreateWithFlags(&c.lane[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c.laneEv[i], cudaEventDisableTiming)); }
-    const size_t nb = (size_t)((count + kLaneChunks - 1) / kLaneChunks);
-    while (c.offsEv.size() < 2 * nb + 1) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.offsEv.push_back(e); }
-    cudaStream_t sA = c.lane[0], sB = c.lane[1];
-    CK(cudaEventRecord(c.offsEv[2 * nb], c.stream));               // everything queued so far on the main stream
-    CK(cudaStreamWaitEvent(sA, c.offsEv[2 * nb], 0));
-    CK(cudaStreamWaitEvent(sB, c.offsEv[2 * nb], 0));
-    auto evParse = [&](size_t k) { return c.offsEv[2 * k]; };
-    auto evEmit = [&](size_t k) { return c.offsEv[2 * k + 1]; };
-    size_t k = 0;
-    for (uint64_t first = firstChunk; first < lastChunk; first += kLaneChunks, ++k) {
+    for (uint64_t first = firstChunk; first < lastChunk; first += c.slots) {
         const Job job = makeJob(c, d_src, n, history, final, d_dst, cap, level, chunk, dict, wantCk, first,
-                                (uint32_t)std::min<uint64_t>(kLaneChunks, lastChunk - first), (k & 1) * (size_t)kLaneChunks);
-        // stream A: candidates as soon as the scratch slice is free, the match kernel once the SMs are
-        if (k >= 2) CK(cudaStreamWaitEvent(sA, evEmit(k - 2), 0));
-        rc = markStage(c, -1, sA); if (rc) return rc;
-        launches += launch_candidates(job, sA); rc = markStage(c, ZZGPU_STAGE_CAND, sA); if (rc) return rc;
-        launches += launch_info(job, sA); rc = markStage(c, ZZGPU_STAGE_INFO, sA); if (rc) return rc;
-        if (k >= 1) CK(cudaStreamWaitEvent(sA, evEmit(k - 1), 0));
-        rc = markStage(c, -1, sA); if (rc) return rc;
-        launches += launch_parse(job, sA); rc = markStage(c, ZZGPU_STAGE_PARSE, sA); if (rc) return rc;
-        CK(cudaEventRecord(evParse(k), sA));
-        // stream B: back end of the batch
-        CK(cudaStreamWaitEvent(sB, evParse(k), 0));
-        rc = markStage(c, -1, sB); if (rc) return rc;
-        launches += launch_huffman(job, sB); rc = markStage(c, ZZGPU_STAGE_HUFF, sB); if (rc) return rc;
-        launches += launch_offsets(job, sB); rc = markStage(c, ZZGPU_STAGE_OFFS, sB); if (rc) return rc;
-        launches += launch_emit(job, sB); rc = markStage(c, ZZGPU_STAGE_EMIT, sB); if (rc) return rc;
-        if (wantCk) { launches += launch_checksums(job, sB); rc = markStage(c, ZZGPU_STAGE_CKSUM, sB); if (rc) return rc; }
-        CK(cudaEventRecord(evEmit(k), sB));
+                                (uint32_t)std::min<uint64_t>(c.slots, lastChunk - first));
+        cudaStream_t st = c.stream;
+        rc = markStage(c, -1, st); if (rc) return rc;
+        if (level >= 2) {
+            launches += launch_candidates(job, st); rc = markStage(c, ZZGPU_STAGE_CAND, st); if (rc) return rc;
+            launches += launch_info(job, st); rc = markStage(c, ZZGPU_STAGE_INFO, st); if (rc) return rc;
+            launches += launch_parse(job, st); rc = markStage(c, ZZGPU_STAGE_PARSE, st); if (rc) return rc;
+        }
+        if (level == 1) {
+            launches += launch_fixed(job, st); rc = markStage(c, ZZGPU_STAGE_FIXED, st); if (rc) return rc;
+        } else {
+            launches += launch_huffman(job, st); rc = markStage(c, ZZGPU_STAGE_HUFF, st); if (rc) return rc;
+        }
+        launches += launch_offsets(job, st); rc = markStage(c, ZZGPU_STAGE_OFFS, st); if (rc) return rc;
+        if (level == 1) { launches += launch_gather(job, st); rc = markStage(c, ZZGPU_STAGE_GATHER, st); if (rc) return rc; }
+        else { launches += launch_emit(job, st); rc = markStage(c, ZZGPU_STAGE_EMIT, st); if (rc) return rc; }
+        if (wantCk) { launches += launch_checksums(job, st); rc = markStage(c, ZZGPU_STAGE_CKSUM, st); if (rc) return rc; }
     }
-    CK(cudaStreamWaitEvent(c.stream, evEmit(k - 1), 0));
-    CK(cudaStreamWaitEvent(c.stream, evParse(k - 1), 0));
     CK(cudaGetLastError());
     return ZZGPU_OK;
 }
@@ -341,13 +370,14 @@ int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int fina
 
 // Piece schedule of the host-buffer path: small pieces first (the kernels start after one short H2D), large in
 // the middle (full occupancy, one dictionary-priming pass per long run of chunks), small at the end (short drain).
-std::vector<uint64_t> pieceSchedule(uint64_t nchunks)
+std::vector<uint64_t> pieceSchedule(uint64_t nchunks, uint32_t chunk)
 {
     // Every piece costs one launch of each kernel (the Huffman kernel alone is ~0.4 ms however few chunks it gets), so
     // pieces are few.  Their sizes are multiples of 888 chunks = 148 SMs x 6 resident K-CAND warps, which is also a
     // whole number of waves of K-MATCH / K-EMIT (296 CTAs) and K-INFO (148 chunks): 888, 1776, 3552, then 4440 chunks,
     // and the last <= 7104 chunks in two pieces (about 60/40) so that the final D2H is short.
     std::vector<uint64_t> ends;
+    if (nchunks * chunk < kPipelineMin) { ends.push_back(nchunks); return ends; }
     const uint64_t unit = 888, big = 5 * unit;
     uint64_t pos = 0, size = unit;
     while (nchunks - pos > big + 3 * unit) {
@@ -360,92 +390,157 @@ std::vector<uint64_t> pieceSchedule(uint64_t nchunks)
     return ends;
 }
 
-// Host buffers on both sides: H2D copies, kernels and D2H copies of successive pieces overlap on three streams.
-int runHostPipelined(Ctx& c, const uint8_t* src, size_t n, size_t hist, int final, uint8_t* dst, size_t cap,
-                     int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t& launches, size_t& total, size_t& d2h)
+// Where the stream of a host-buffer call goes.
+struct HostOut {
+    enum Kind { Direct, Sink, Hold } kind = Direct;
+    uint8_t* dst = nullptr; size_t cap = 0; bool pinned = false;        // Direct: caller's buffer
+    zzgpu_sink_fn sink = nullptr; void* user = nullptr; size_t slice = kDefaultSlice;   // Sink: slices in order
+    size_t written = 0;         // bytes of the stream delivered (Direct, Sink) or held on the device (Hold) so far
+    size_t d2h = 0;
+    bool firstSlice = true;
+};
+
+int ensureStaging(Ctx& c)
+{
+    if (!c.copyIn) { CK(cudaStreamCreateWithFlags(&c.copyIn, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c.copyOut, cudaStreamNonBlocking)); }
+    for (int i = 0; i < 2; ++i) {
+        if (!c.stageIn[i]) CK(cudaMallocHost(&c.stageIn[i], kStageBlock));
+        if (!c.stageOut[i]) CK(cudaMallocHost(&c.stageOut[i], kStageBlock));
+        if (!c.stageInEv[i]) CK(cudaEventCreateWithFlags(&c.stageInEv[i], cudaEventDisableTiming));
+        if (!c.stageOutEv[i]) CK(cudaEventCreateWithFlags(&c.stageOutEv[i], cudaEventDisableTiming));
+    }
+    return ZZGPU_OK;
+}
+
+// Moves d_from[0, len) (device) to the call's destination.  Direct + pinned: one asynchronous copy on the copy-out
+// stream.  Direct + pageable / Sink: through the two pinned staging blocks, the D2H of block k+1 running while block k
+// is copied out (or handed to the sink in slices).  `probe`: the segment's H2D-complete events (diagnostic counter).
+struct PieceProbe { const std::vector<cudaEvent_t>* ev; size_t issued, total; };
+
+int deliver(Ctx& c, HostOut& out, const uint8_t* d_from, size_t len, const PieceProbe* probe)
+{
+    if (len == 0) return ZZGPU_OK;
+    if (out.kind == HostOut::Hold) { out.written += len; return ZZGPU_OK; }
+    if (out.kind == HostOut::Direct && out.pinned) {
+        CK(cudaMemcpyAsync(out.dst + out.written, d_from, len, cudaMemcpyDeviceToHost, c.copyOut));
+        out.written += len; out.d2h += len;
+        return ZZGPU_OK;
+    }
+    size_t blocks = 0;
+    size_t pendLen = 0; int pendSb = 0;
+    for (size_t off = 0; off < len || pendLen; ) {
+        size_t cur = 0; int sb = 0;
+        if (off < len) {
+            cur = std::min(kStageBlock, len - off); sb = (int)(blocks++ & 1);
+            CK(cudaMemcpyAsync(c.stageOut[sb], d_from + off, cur, cudaMemcpyDeviceToHost, c.copyOut));
+            CK(cudaEventRecord(c.stageOutEv[sb], c.copyOut));
+        }
+        if (pendLen) {
+            CK(cudaEventSynchronize(c.stageOutEv[pendSb]));
+            if (out.kind == HostOut::Direct) {
+                CopyPool::get().copy(out.dst + out.written, c.stageOut[pendSb], pendLen);
+            } else {
+                if (out.firstSlice) {
+                    out.firstSlice = false;
+                    long long doneH2d = 0;
+                    if (probe) for (size_t q = 0; q < probe->issued; ++q) if (cudaEventQuery((*probe->ev)[2 * q]) == cudaSuccess) ++doneH2d;
+                    (void)cudaGetLastError();
+                    t_sinkFirstH2dDone = doneH2d; t_sinkPieces = probe ? (long long)probe->total : 0;
+                }
+                for (size_t s = 0; s < pendLen; s += out.slice) out.sink(c.stageOut[pendSb] + s, std::min(out.slice, pendLen - s), out.user);
+            }
+            out.written += pendLen; out.d2h += pendLen;
+        }
+        pendLen = cur; pendSb = sb;
+        off += cur;
+    }
+    return ZZGPU_OK;
+}
+
+// One segment (<= g_segBytes of input) of a host-buffer call: H2D copies, kernels and D2H copies of successive pieces
+// overlap on three streams.  `histSrc` holds the `hist` bytes of stream before src.  d_out/d_cap: device buffer that
+// receives the segment's stream.
+int runHostSegment(Ctx& c, const uint8_t* src, size_t n, const uint8_t* histSrc, size_t hist, int final,
+                   HostOut& out, uint8_t* d_out, size_t d_cap, int level, uint32_t chunk, uint32_t dict, int wantCk,
+                   uint64_t& launches)
 {
     const uint64_t nchunks = (n + chunk - 1) / chunk;
     int rc = ensureBuf(c.dIn, c.dInCap, hist + n + 64); if (rc) return rc;
-    const size_t d_cap = std::min(cap, zzgpu_bound(n, level, chunk));
-    rc = ensureBuf(c.dOut, c.dOutCap, d_cap + 64); if (rc) return rc;
-    if (!c.copyIn) { CK(cudaStreamCreateWithFlags(&c.copyIn, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c.copyOut, cudaStreamNonBlocking)); }
-    const bool srcPinned = isPinnedHost(src), dstPinned = isPinnedHost(dst);
-    if (!srcPinned || !dstPinned) {
-        for (int i = 0; i < 2; ++i) {
-            if (!c.stageIn[i]) { CK(cudaMallocHost(&c.stageIn[i], kStageBlock)); CK(cudaMallocHost(&c.stageOut[i], kStageBlock));
-                                 CK(cudaEventCreateWithFlags(&c.stageInEv[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c.stageOutEv[i], cudaEventDisableTiming)); }
-        }
-    }
-    size_t inBlocks = 0, outBlocks = 0;
-    const std::vector<uint64_t> ends = pieceSchedule(nchunks);
+    rc = ensureStaging(c); if (rc) return rc;
+    const bool srcPinned = isPinnedHost(src);
+    const std::vector<uint64_t> ends = pieceSchedule(nchunks, chunk);
     const size_t np = ends.size();
     while (c.pieceEv.size() < 2 * np) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.pieceEv.push_back(e); }
     rc = ensureBuf(c.hPiece, c.hPieceCap, 4 * np, true); if (rc) return rc;
     rc = preparePipeline(c, n, chunk, wantCk); if (rc) return rc;
-    cudaEvent_t start = c.pieceEv[0];                   // copies must not start before earlier work on the main stream is done
+    // the copy streams must not touch the staging buffers before earlier work on the main stream is done with them
     CK(cudaEventRecord(c.ev[0], c.stream));
     CK(cudaStreamWaitEvent(c.copyIn, c.ev[0], 0));
     CK(cudaStreamWaitEvent(c.copyOut, c.ev[0], 0));
-    (void)start;
+    if (hist) CK(cudaMemcpyAsync(c.dIn, histSrc, hist, cudaMemcpyHostToDevice, c.copyIn));
     const uint8_t* d_src = c.dIn + hist;
+    size_t inBlocks = 0, done = 0, nextDrain = 0, issued = 0;
     uint64_t firstChunk = 0;
-    for (size_t p = 0; p < np; ++p) {
+
+    auto issue = [&](size_t p) -> int {
         const size_t lo = (size_t)(firstChunk * chunk), hi = (size_t)std::min<uint64_t>(n, ends[p] * chunk);
-        const size_t from = p == 0 ? 0 : hist + lo, to = hist + hi;          // piece 0 also carries the history
         if (srcPinned) {
-            CK(cudaMemcpyAsync(c.dIn + from, src - hist + from, to - from, cudaMemcpyHostToDevice, c.copyIn));
+            CK(cudaMemcpyAsync(c.dIn + hist + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, c.copyIn));
         } else {
-            for (size_t off = from; off < to; off += kStageBlock, ++inBlocks) {
-                const size_t len = std::min(kStageBlock, to - off);
+            for (size_t off = lo; off < hi; off += kStageBlock, ++inBlocks) {
+                const size_t len = std::min(kStageBlock, hi - off);
                 const int sb = (int)(inBlocks & 1);
                 CK(cudaEventSynchronize(c.stageInEv[sb]));                   // the block's previous H2D has drained
-                CopyPool::get().copy(c.stageIn[sb], src - hist + off, len);
-                CK(cudaMemcpyAsync(c.dIn + off, c.stageIn[sb], len, cudaMemcpyHostToDevice, c.copyIn));
+                CopyPool::get().copy(c.stageIn[sb], src + off, len);
+                CK(cudaMemcpyAsync(c.dIn + hist + off, c.stageIn[sb], len, cudaMemcpyHostToDevice, c.copyIn));
                 CK(cudaEventRecord(c.stageInEv[sb], c.copyIn));
             }
         }
         CK(cudaEventRecord(c.pieceEv[2 * p], c.copyIn));
         CK(cudaStreamWaitEvent(c.stream, c.pieceEv[2 * p], 0));
-        rc = runChunks(c, d_src, n, hist, final, c.dOut, d_cap, level, chunk, dict, wantCk, firstChunk, ends[p], launches);
-        if (rc) return rc;
+        int r = runChunks(c, d_src, n, hist, final, d_out, d_cap, level, chunk, dict, wantCk, firstChunk, ends[p], launches);
+        if (r) return r;
         CK(cudaMemcpyAsync(c.hPiece + 4 * p, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
         CK(cudaEventRecord(c.pieceEv[2 * p + 1], c.stream));
         firstChunk = ends[p];
-    }
-    CK(cudaEventRecord(c.ev[2], c.stream));
-    size_t done = 0;
-    for (size_t p = 0; p < np; ++p) {
-        CK(cudaEventSynchronize(c.pieceEv[2 * p + 1]));
+        issued = p + 1;
+        return ZZGPU_OK;
+    };
+    // returns 0 when piece p was delivered, 1 when it is not ready yet (non-blocking mode), < 0 = -status
+    auto drain = [&](size_t p, bool blocking) -> int {
+        if (!blocking) {
+            const cudaError_t q = cudaEventQuery(c.pieceEv[2 * p + 1]);
+            if (q == cudaErrorNotReady) { (void)cudaGetLastError(); return 1; }
+            if (q != cudaSuccess) return -fail(ZZGPU_E_CUDA, "cudaEventQuery", q);
+        } else {
+            const cudaError_t q = cudaEventSynchronize(c.pieceEv[2 * p + 1]);
+            if (q != cudaSuccess) return -fail(ZZGPU_E_CUDA, "cudaEventSynchronize", q);
+        }
         const uint64_t upto = c.hPiece[4 * p], flags = c.hPiece[4 * p + 1];
-        if (flags & 1) return fail(ZZGPU_E_CAPACITY, "destination too small");
-        if (flags & ~1ull) return fail(ZZGPU_E_CUDA, "internal consistency check failed (emit size mismatch)");
-        if (upto > cap) return fail(ZZGPU_E_CAPACITY, "destination too small");
+        if (flags & 1) return -fail(ZZGPU_E_CAPACITY, "destination too small");
+        if (flags & ~1ull) return -fail(ZZGPU_E_CUDA, "internal consistency check failed (emit size mismatch)");
+        if (upto > d_cap) return -fail(ZZGPU_E_CAPACITY, "destination too small");
         if (upto > done) {
-            if (dstPinned) {
-                CK(cudaMemcpyAsync(dst + done, c.dOut + done, upto - done, cudaMemcpyDeviceToHost, c.copyOut));
-            } else {
-                // D2H of block k+1 runs while block k is copied out of its pinned stage
-                size_t pendOff = 0, pendLen = 0; int pendSb = 0;
-                for (size_t off = done; off < upto || pendLen; ) {
-                    size_t len = 0; int sb = 0;
-                    if (off < upto) {
-                        len = std::min(kStageBlock, (size_t)upto - off); sb = (int)(outBlocks++ & 1);
-                        CK(cudaMemcpyAsync(c.stageOut[sb], c.dOut + off, len, cudaMemcpyDeviceToHost, c.copyOut));
-                        CK(cudaEventRecord(c.stageOutEv[sb], c.copyOut));
-                    }
-                    if (pendLen) { CK(cudaEventSynchronize(c.stageOutEv[pendSb])); CopyPool::get().copy(dst + pendOff, c.stageOut[pendSb], pendLen); }
-                    pendOff = off; pendLen = len; pendSb = sb;
-                    off += len;
-                }
-            }
+            const PieceProbe probe = { &c.pieceEv, issued, np };
+            const int r = deliver(c, out, d_out + done, (size_t)upto - done, &probe);
+            if (r) return -r;
         }
         done = (size_t)upto;
+        return 0;
+    };
+
+    for (size_t p = 0; p < np; ++p) {
+        rc = issue(p); if (rc) return rc;
+        while (nextDrain < p) {                  // hand over what has finished meanwhile (pageable input: the issue above took a while)
+            const int r = drain(nextDrain, false);
+            if (r < 0) return -r;
+            if (r) break;
+            ++nextDrain;
+        }
     }
-    CK(cudaEventRecord(c.ev[3], c.copyOut));
-    CK(cudaStreamWaitEvent(c.stream, c.ev[3], 0));
-    CK(cudaStreamSynchronize(c.copyOut));
+    for (; nextDrain < np; ++nextDrain) { const int r = drain(nextDrain, true); if (r < 0) return -r; }
+    CK(cudaStreamSynchronize(c.copyOut));        // the device output buffer is reused by the next segment / call
     for (int i = 0; i < 4; ++i) c.hTotal[i] = c.hPiece[4 * (np - 1) + i];
-    total = done; d2h = done;
     return ZZGPU_OK;
 }
 
@@ -468,7 +563,164 @@ int foldChecksums(Ctx& c, size_t n, uint32_t chunk, int wantCk, uint32_t* adler0
     return ZZGPU_OK;
 }
 
+void drainStreams(Ctx& c)
+{
+    if (c.copyIn) cudaStreamSynchronize(c.copyIn);
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    if (c.copyOut) cudaStreamSynchronize(c.copyOut);
+    (void)cudaGetLastError();
+}
+
+// Host-buffer call: segments of <= g_segBytes, each pipelined in pieces.  Checksums of the segments are folded here.
+int deflateHost(Ctx& c, const uint8_t* src, size_t n, const uint8_t* histSrc, size_t hist, int final, HostOut& out,
+                int level, uint32_t chunk, uint32_t dict, int wantCk, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t segBytes = std::max<size_t>(1, g_segBytes / chunk) * chunk;
+    if (out.kind == HostOut::Hold) { int rc = ensureBuf(c.dOut, c.dOutCap, zzgpu_bound(n, level, chunk) + 64); if (rc) return rc; }
+    uint32_t a = 0, r = 0;
+    uint64_t launches = 0, matches = 0, stored = 0;
+    size_t h2d = 0;
+    for (size_t off = 0; off < n; off += segBytes) {
+        const size_t len = std::min(segBytes, n - off);
+        const int segFinal = final && off + len == n;
+        const size_t h = off == 0 ? hist : std::min<size_t>(off + hist, (size_t)dict + kPreExtra);
+        const uint8_t* hs = off == 0 ? histSrc : src + off - h;
+        uint8_t* d_out; size_t d_cap;
+        const size_t bound = zzgpu_bound(len, level, chunk);
+        if (out.kind == HostOut::Hold) { d_out = c.dOut + out.written; d_cap = bound; }
+        else {
+            d_cap = out.kind == HostOut::Direct ? std::min(out.cap - out.written, bound) : bound;
+            int rc = ensureBuf(c.dOut, c.dOutCap, d_cap + 64); if (rc) return rc;
+            d_out = c.dOut;
+        }
+        int rc = runHostSegment(c, src + off, len, hs, h, segFinal, out, d_out, d_cap, level, chunk, dict, wantCk, launches);
+        if (rc) { drainStreams(c); return rc; }
+        uint32_t sa = 0, sr = 0;
+        rc = foldChecksums(c, len, chunk, wantCk, &sa, &sr); if (rc) return rc;
+        a = adler32_combine(a, sa, len); r = crc32_combine(r, sr, len);
+        matches += c.hTotal[2]; stored += c.hTotal[3];
+        h2d += h + len;
+        collectStages(c, stats);
+    }
+    if (adler0) *adler0 = a;
+    if (crc) *crc = r;
+    if (stats) {
+        stats->chunks = (n + chunk - 1) / chunk;
+        stats->matches = matches; stats->stored_chunks = stored; stats->kernel_launches = launches;
+        stats->device_ms = 0;                        // kernels interleave with copies: the stages' sum
+        for (int i = 0; i < ZZGPU_NSTAGES; ++i) stats->device_ms += stats->stage_ms[i];
+        stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        stats->h2d_bytes = h2d; stats->d2h_bytes = out.d2h;
+    }
+    return ZZGPU_OK;
+}
+
 const uint8_t kEmptyFinalStored[5] = { 0x01, 0x00, 0x00, 0xFF, 0xFF };     // R7: empty input still gets one final block
+
+struct CallArgs {
+    const uint8_t* src; size_t n; const uint8_t* histSrc; size_t history; int final; int src_mem;
+    uint8_t* dst; size_t cap; int dst_mem;
+    int level; uint32_t chunk; uint32_t dict; int want;
+    HostOut::Kind kind; zzgpu_sink_fn sink; void* user; size_t slice;
+};
+
+int deflateCall(const CallArgs& a, size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats)
+{
+    const uint32_t chunk = a.chunk ? a.chunk : ZZGPU_DEFAULT_CHUNK;
+    if (!validParams(a.level, chunk, a.dict) || !out_len || (!a.src && a.n)) return fail(ZZGPU_E_ARG, "invalid argument");
+    if (a.kind == HostOut::Direct && !a.dst && a.cap) return fail(ZZGPU_E_ARG, "invalid argument");
+    if (a.kind == HostOut::Sink && !a.sink) return fail(ZZGPU_E_ARG, "invalid argument");
+    Ctx* cp = nullptr;
+    int rc = ensureCtx(cp); if (rc) return rc;
+    Ctx& c = *cp;
+    Lease lease(c);
+    if (lease.resumed()) return fail(ZZGPU_E_ARG, "this thread holds a stream on the device: fetch or release it first");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (adler0) *adler0 = 0;
+    if (crc) *crc = 0;
+    *out_len = 0;
+    const bool hostBoth = a.src_mem == ZZGPU_MEM_HOST && a.dst_mem == ZZGPU_MEM_HOST;
+
+    if (a.n == 0) {
+        if (a.final) {
+            if (a.kind == HostOut::Sink) { a.sink(kEmptyFinalStored, 5, a.user); }
+            else if (a.kind == HostOut::Hold) {
+                rc = ensureBuf(c.dOut, c.dOutCap, 64); if (rc) return rc;
+                CK(cudaMemcpyAsync(c.dOut, kEmptyFinalStored, 5, cudaMemcpyHostToDevice, c.stream)); CK(cudaStreamSynchronize(c.stream));
+            } else {
+                if (a.cap < 5) return fail(ZZGPU_E_CAPACITY, "destination too small");
+                if (a.dst_mem == ZZGPU_MEM_HOST) memcpy(a.dst, kEmptyFinalStored, 5);
+                else { CK(cudaMemcpyAsync(a.dst, kEmptyFinalStored, 5, cudaMemcpyHostToDevice, c.stream)); CK(cudaStreamSynchronize(c.stream)); }
+            }
+            *out_len = 5;
+        }
+        if (a.kind == HostOut::Hold) { c.heldLen = *out_len; lease.keep(); }
+        return ZZGPU_OK;
+    }
+
+    const size_t hist = std::min<size_t>(a.history, (size_t)a.dict + kPreExtra);    // bytes the kernels may look at
+    if (hostBoth) {
+        HostOut out;
+        out.kind = a.kind; out.dst = a.dst; out.cap = a.cap; out.pinned = a.kind == HostOut::Direct && isPinnedHost(a.dst);
+        out.sink = a.sink; out.user = a.user; out.slice = a.slice ? a.slice : kDefaultSlice;
+        const uint8_t* hs = a.histSrc ? a.histSrc + (a.history - hist) : a.src - hist;
+        rc = deflateHost(c, a.src, a.n, hs, hist, a.final, out, a.level, chunk, a.dict, a.want, adler0, crc, stats);
+        if (rc) return rc;
+        *out_len = out.written;
+        if (a.kind == HostOut::Hold) { c.heldLen = out.written; lease.keep(); }
+        return ZZGPU_OK;
+    }
+
+    // device-resident (or mixed) buffers: the caller's device memory is used in place
+    uint64_t launches = 0;
+    size_t h2d = 0, d2h = 0;
+    CK(cudaEventRecord(c.ev[0], c.stream));
+    const uint8_t* d_src = a.src;
+    if (a.src_mem == ZZGPU_MEM_HOST) {
+        rc = ensureBuf(c.dIn, c.dInCap, hist + a.n + 64); if (rc) return rc;
+        CK(cudaMemcpyAsync(c.dIn, a.src - hist, hist + a.n, cudaMemcpyHostToDevice, c.stream));
+        d_src = c.dIn + hist;
+        h2d = hist + a.n;
+    }
+    uint8_t* d_dst = a.dst;
+    size_t d_cap = a.cap;
+    if (a.dst_mem == ZZGPU_MEM_HOST) {
+        d_cap = std::min(a.cap, zzgpu_bound(a.n, a.level, chunk));
+        rc = ensureBuf(c.dOut, c.dOutCap, d_cap + 64); if (rc) return rc;
+        d_dst = c.dOut;
+    }
+    CK(cudaEventRecord(c.ev[1], c.stream));
+    rc = runPipeline(c, d_src, a.n, hist, a.final, d_dst, d_cap, a.level, chunk, a.dict, a.want, launches);
+    if (rc) return rc;
+    CK(cudaEventRecord(c.ev[2], c.stream));
+    CK(cudaMemcpyAsync(c.hTotal, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    const uint64_t total = c.hTotal[0], flags = c.hTotal[1];
+    if (flags & 1) return fail(ZZGPU_E_CAPACITY, "destination too small");
+    if (flags & ~1ull) return fail(ZZGPU_E_CUDA, "internal consistency check failed (emit size mismatch)");
+    if (total > a.cap) return fail(ZZGPU_E_CAPACITY, "destination too small");
+    if (a.dst_mem == ZZGPU_MEM_HOST) {
+        CK(cudaMemcpyAsync(a.dst, c.dOut, total, cudaMemcpyDeviceToHost, c.stream));
+        d2h = total;
+    }
+    CK(cudaEventRecord(c.ev[3], c.stream));
+    rc = foldChecksums(c, a.n, chunk, a.want, adler0, crc); if (rc) return rc;
+    CK(cudaStreamSynchronize(c.stream));
+    *out_len = (size_t)total;
+    if (stats) {
+        stats->chunks = (a.n + chunk - 1) / chunk;
+        stats->matches = c.hTotal[2];
+        stats->stored_chunks = c.hTotal[3];
+        stats->kernel_launches = launches;
+        collectStages(c, stats);
+        cudaEventElapsedTime(&stats->total_ms, c.ev[0], c.ev[3]);
+        cudaEventElapsedTime(&stats->device_ms, c.ev[1], c.ev[2]);
+        (void)cudaGetLastError();
+        stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
+    }
+    return ZZGPU_OK;
+}
 
 }  // namespace
 
@@ -490,29 +742,24 @@ void zzgpu_shutdown(void)
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& c : g_ctx) {
         if (!c.ready) continue;
-        cudaSetDevice(c.device);
-        cudaStreamSynchronize(c.stream);
-        freeScratch(c);
-        cudaFree(c.total); cudaFreeHost(c.hTotal); cudaFree(c.ck); cudaFreeHost(c.hCk); cudaFree(c.dIn); cudaFree(c.dOut);
-        cudaFreeHost(c.hPiece); c.hPiece = nullptr; c.hPieceCap = 0;
-        for (auto& e : c.pieceEv) cudaEventDestroy(e);
-        c.pieceEv.clear();
-        for (auto& e : c.stageEv) cudaEventDestroy(e);
-        c.stageEv.clear(); c.stageOf.clear(); c.stageUsed = 0;
-        if (c.copyIn) { cudaStreamDestroy(c.copyIn); cudaStreamDestroy(c.copyOut); c.copyIn = nullptr; c.copyOut = nullptr; }
-        for (int i = 0; i < 2; ++i) if (c.stageIn[i]) { cudaFreeHost(c.stageIn[i]); cudaFreeHost(c.stageOut[i]); cudaEventDestroy(c.stageInEv[i]); cudaEventDestroy(c.stageOutEv[i]); c.stageIn[i] = c.stageOut[i] = nullptr; }
-        for (auto& e : c.ev) cudaEventDestroy(e);
-        cudaStreamDestroy(c.stream);
-        c.total = nullptr; c.hTotal = nullptr; c.ck = nullptr; c.hCk = nullptr; c.dIn = nullptr; c.dOut = nullptr;
-        c.ckCap = c.hCkCap = c.dInCap = c.dOutCap = 0;
-        c.ready = false;
+        {   // wait for a running call on this context (a stream somebody still holds is dropped with it)
+            std::unique_lock<std::mutex> cl(c.mu);
+            c.cv.wait(cl, [&] { return !c.busy || c.held; });
+            c.busy = true; c.held = false;
+        }
+        destroyCtx(c);
+        {
+            std::lock_guard<std::mutex> cl(c.mu);
+            c.busy = false; c.held = false;
+        }
+        c.cv.notify_all();
     }
 }
 
 int zzgpu_device_count(void)
 {
     int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
     return count;
 }
 
@@ -544,89 +791,70 @@ int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int final, in
                      int level, uint32_t chunk, uint32_t dict, int want_checksums,
                      size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats)
 {
-    if (chunk == 0) chunk = ZZGPU_DEFAULT_CHUNK;
-    if (!validParams(level, chunk, dict) || !out_len || (!src && n) || (!dst && cap)) return fail(ZZGPU_E_ARG, "invalid argument");
+    const CallArgs a = { src, n, nullptr, history, final, src_mem, dst, cap, dst_mem, level, chunk, dict, want_checksums,
+                         HostOut::Direct, nullptr, nullptr, 0 };
+    return deflateCall(a, out_len, adler0, crc, stats);
+}
+
+int zzgpu_deflate_hist(const uint8_t* src, size_t n, const uint8_t* hist, size_t hist_len, int final,
+                       uint8_t* dst, size_t cap, int level, uint32_t chunk, uint32_t dict, size_t* out_len)
+{
+    if (hist_len && !hist) return fail(ZZGPU_E_ARG, "invalid argument");
+    const CallArgs a = { src, n, hist, hist_len, final, ZZGPU_MEM_HOST, dst, cap, ZZGPU_MEM_HOST, level, chunk, dict, 0,
+                         HostOut::Direct, nullptr, nullptr, 0 };
+    return deflateCall(a, out_len, nullptr, nullptr, nullptr);
+}
+
+int zzgpu_deflate_sink(const uint8_t* src, size_t n, size_t history, int final,
+                       int level, uint32_t chunk, uint32_t dict, int want_checksums,
+                       zzgpu_sink_fn sink, void* user, size_t slice,
+                       size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats)
+{
+    t_sinkPieces = 0; t_sinkFirstH2dDone = 0;
+    const CallArgs a = { src, n, nullptr, history, final, ZZGPU_MEM_HOST, nullptr, 0, ZZGPU_MEM_HOST, level, chunk, dict,
+                         want_checksums, HostOut::Sink, sink, user, slice };
+    return deflateCall(a, out_len, adler0, crc, stats);
+}
+
+int zzgpu_deflate_hold(const uint8_t* src, size_t n, size_t history, int final,
+                       int level, uint32_t chunk, uint32_t dict, int want_checksums,
+                       size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats)
+{
+    const CallArgs a = { src, n, nullptr, history, final, ZZGPU_MEM_HOST, nullptr, 0, ZZGPU_MEM_HOST, level, chunk, dict,
+                         want_checksums, HostOut::Hold, nullptr, nullptr, 0 };
+    return deflateCall(a, out_len, adler0, crc, stats);
+}
+
+int zzgpu_fetch(uint8_t* dst, size_t cap, zzgpu_sink_fn sink, void* user, size_t slice)
+{
     Ctx* cp = nullptr;
     int rc = ensureCtx(cp); if (rc) return rc;
     Ctx& c = *cp;
-    std::lock_guard<std::mutex> lk(c.mu);
-    if (stats) memset(stats, 0, sizeof *stats);
-    if (adler0) *adler0 = 0;
-    if (crc) *crc = 0;
-
-    if (n == 0) {
-        *out_len = 0;
-        if (final) {
-            if (cap < 5) return fail(ZZGPU_E_CAPACITY, "destination too small");
-            if (dst_mem == ZZGPU_MEM_HOST) memcpy(dst, kEmptyFinalStored, 5);
-            else { CK(cudaMemcpyAsync(dst, kEmptyFinalStored, 5, cudaMemcpyHostToDevice, c.stream)); CK(cudaStreamSynchronize(c.stream)); }
-            *out_len = 5;
-        }
-        return ZZGPU_OK;
-    }
-
-    uint64_t launches = 0;
-    const size_t hist = std::min<size_t>(history, (size_t)dict + kPreExtra);    // bytes the kernels may look at
-    size_t h2d = 0, d2h = 0;
-    uint64_t total = 0;
-    if (src_mem == ZZGPU_MEM_HOST && dst_mem == ZZGPU_MEM_HOST && n >= ((size_t)32 << 20)) {
-        size_t tot = 0;
-        rc = runHostPipelined(c, src, n, hist, final, dst, cap, level, chunk, dict, want_checksums, launches, tot, d2h);
-        if (rc) { cudaStreamSynchronize(c.copyIn); cudaStreamSynchronize(c.stream); cudaStreamSynchronize(c.copyOut); return rc; }
-        total = tot; h2d = hist + n;
-    } else {
-        CK(cudaEventRecord(c.ev[0], c.stream));
-        const uint8_t* d_src = src;
-        if (src_mem == ZZGPU_MEM_HOST) {
-            rc = ensureBuf(c.dIn, c.dInCap, hist + n + 64); if (rc) return rc;
-            CK(cudaMemcpyAsync(c.dIn, src - hist, hist + n, cudaMemcpyHostToDevice, c.stream));
-            d_src = c.dIn + hist;
-            h2d = hist + n;
-        }
-        uint8_t* d_dst = dst;
-        size_t d_cap = cap;
-        if (dst_mem == ZZGPU_MEM_HOST) {
-            d_cap = std::min(cap, zzgpu_bound(n, level, chunk));
-            rc = ensureBuf(c.dOut, c.dOutCap, d_cap + 64); if (rc) return rc;
-            d_dst = c.dOut;
-        }
-        CK(cudaEventRecord(c.ev[1], c.stream));
-        rc = runPipeline(c, d_src, n, hist, final, d_dst, d_cap, level, chunk, dict, want_checksums, launches);
-        if (rc) return rc;
-        CK(cudaEventRecord(c.ev[2], c.stream));
-        CK(cudaMemcpyAsync(c.hTotal, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
-        CK(cudaStreamSynchronize(c.stream));
-        total = c.hTotal[0];
-        const uint64_t flags = c.hTotal[1];
-        if (flags & 1) return fail(ZZGPU_E_CAPACITY, "destination too small");
-        if (flags & ~1ull) return fail(ZZGPU_E_CUDA, "internal consistency check failed (emit size mismatch)");
-        if (total > cap) return fail(ZZGPU_E_CAPACITY, "destination too small");
-        if (dst_mem == ZZGPU_MEM_HOST) {
-            CK(cudaMemcpyAsync(dst, c.dOut, total, cudaMemcpyDeviceToHost, c.stream));
-            d2h = total;
-        }
-        CK(cudaEventRecord(c.ev[3], c.stream));
-    }
-    rc = foldChecksums(c, n, chunk, want_checksums, adler0, crc); if (rc) return rc;
-    CK(cudaStreamSynchronize(c.stream));
-    *out_len = (size_t)total;
-    if (stats) {
-        stats->chunks = (n + chunk - 1) / chunk;
-        stats->matches = c.hTotal[2];
-        stats->stored_chunks = c.hTotal[3];
-        stats->kernel_launches = launches;
-        collectStages(c, stats);
-        cudaEventElapsedTime(&stats->total_ms, c.ev[0], c.ev[3]);
-        if (h2d + d2h > 0) {
-            stats->device_ms = 0;                    // host buffers: kernels interleave with copies; sum the stages
-            for (int i = 0; i < ZZGPU_NSTAGES; ++i) stats->device_ms += stats->stage_ms[i];
-        } else {
-            cudaEventElapsedTime(&stats->device_ms, c.ev[1], c.ev[2]);
-        }
-        (void)cudaGetLastError();                    // timing queries must never poison the next call
-        stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
-    }
+    Lease lease(c);                                  // ends the hold when it goes out of scope
+    if (!lease.resumed()) return fail(ZZGPU_E_ARG, "no held stream on this device for the calling thread");
+    if ((dst != nullptr) == (sink != nullptr)) return fail(ZZGPU_E_ARG, "exactly one of dst / sink");
+    lease.consume();
+    const size_t len = c.heldLen;
+    c.heldLen = 0;
+    if (dst && len > cap) return fail(ZZGPU_E_CAPACITY, "destination too small");
+    rc = ensureStaging(c); if (rc) return rc;
+    HostOut out;
+    out.kind = dst ? HostOut::Direct : HostOut::Sink;
+    out.dst = dst; out.cap = cap; out.pinned = dst && isPinnedHost(dst);
+    out.sink = sink; out.user = user; out.slice = slice ? slice : kDefaultSlice; out.firstSlice = false;
+    rc = deliver(c, out, c.dOut, len, nullptr);
+    if (rc) { drainStreams(c); return rc; }
+    CK(cudaStreamSynchronize(c.copyOut));
     return ZZGPU_OK;
+}
+
+void zzgpu_release(void)
+{
+    Ctx* cp = nullptr;
+    if (ensureCtx(cp)) return;
+    Lease lease(*cp);
+    lease.consume();
+    cp->heldLen = 0;
 }
 
 int zzgpu_deflate(const uint8_t* src, size_t n, int src_mem, uint8_t* dst, size_t cap, int dst_mem,
@@ -649,38 +877,51 @@ int zzgpu_checksums(const uint8_t* src, size_t n, int src_mem, uint32_t adler_st
     Ctx* cp = nullptr;
     int rc = ensureCtx(cp); if (rc) return rc;
     Ctx& c = *cp;
-    std::lock_guard<std::mutex> lk(c.mu);
-    uint32_t a0 = 0, r = 0;
-    if (n) {
-        const uint8_t* d_src = src;
+    Lease lease(c);
+    if (lease.resumed()) return fail(ZZGPU_E_ARG, "this thread holds a stream on the device: fetch or release it first");
+    uint32_t a = adler_start, r = crc_start;
+    const uint32_t chunk = ZZGPU_MAX_CHUNK;
+    const size_t slice = src_mem == ZZGPU_MEM_HOST ? (size_t)1 << 30 : n;      // host input: bounded device staging
+    for (size_t off = 0; off < n; off += slice) {
+        const size_t len = std::min(slice, n - off);
+        const uint8_t* d_src = src + off;
         if (src_mem == ZZGPU_MEM_HOST) {
-            rc = ensureBuf(c.dIn, c.dInCap, n + 64); if (rc) return rc;
-            CK(cudaMemcpyAsync(c.dIn, src, n, cudaMemcpyHostToDevice, c.stream));
+            rc = ensureBuf(c.dIn, c.dInCap, len + 64); if (rc) return rc;
+            CK(cudaMemcpyAsync(c.dIn, src + off, len, cudaMemcpyHostToDevice, c.stream));
             d_src = c.dIn;
         }
-        const uint32_t chunk = ZZGPU_MAX_CHUNK;
-        const uint64_t nchunks = (n + chunk - 1) / chunk;
+        const uint64_t nchunks = (len + chunk - 1) / chunk;
         rc = ensureBuf(c.ck, c.ckCap, 2 * nchunks); if (rc) return rc;
         for (uint64_t first = 0; first < nchunks; first += 32768) {
             Job job{};
-            job.src = d_src; job.n = n; job.chunk = chunk; job.dict = 0; job.first_chunk = first;
+            job.src = d_src; job.n = len; job.chunk = chunk; job.dict = 0; job.first_chunk = first;
             job.nchunks = (uint32_t)std::min<uint64_t>(32768, nchunks - first);
             job.final_stream = 1; job.ck = c.ck;
             launch_checksums(job, c.stream);
         }
         CK(cudaGetLastError());
-        rc = foldChecksums(c, n, chunk, 3, &a0, &r); if (rc) return rc;
+        uint32_t a0 = 0, r0 = 0;
+        rc = foldChecksums(c, len, chunk, 3, &a0, &r0); if (rc) return rc;
+        a = zz::adler32_combine(a, a0, len);
+        r = zz::crc32_combine(r, r0, len);
     }
-    if (adler) *adler = zz::adler32_combine(adler_start, a0, n);
-    if (crc) *crc = zz::crc32_combine(crc_start, r, n);
+    if (adler) *adler = a;
+    if (crc) *crc = r;
     return ZZGPU_OK;
 }
 
 int zzgpu_set_option(const char* name, int value)
 {
-    if (name && !strcmp(name, "overlap")) { g_overlap = value ? 1 : 0; return ZZGPU_OK; }
-    if (name && !strcmp(name, "emit")) { set_emit_variant(value ? 1 : 0); return ZZGPU_OK; }       // 0: position-range K-EMIT, 1: token-parallel (default)
+    if (name && !strcmp(name, "segment_mib") && value >= 1 && value <= 65536) { g_segBytes = (size_t)value << 20; return ZZGPU_OK; }
+    if (name && set_kernel_option(name, value)) return ZZGPU_OK;
     return fail(ZZGPU_E_ARG, "unknown option");
+}
+
+long long zzgpu_get_counter(const char* name)
+{
+    if (name && !strcmp(name, "sink_pieces")) return t_sinkPieces;
+    if (name && !strcmp(name, "sink_first_h2d_done")) return t_sinkFirstH2dDone;
+    return -1;
 }
 
 uint32_t zzgpu_adler32_combine(uint32_t first, uint32_t second_start0, size_t len_second)
@@ -704,7 +945,8 @@ int zzgpu_debug_chunk(const uint8_t* src, size_t n, int src_mem, int level, uint
     Ctx* cp = nullptr;
     int rc = ensureCtx(cp); if (rc) return rc;
     Ctx& c = *cp;
-    std::lock_guard<std::mutex> lk(c.mu);
+    Lease lease(c);
+    if (lease.resumed()) return fail(ZZGPU_E_ARG, "this thread holds a stream on the device: fetch or release it first");
     const uint8_t* d_src = src;
     if (src_mem == ZZGPU_MEM_HOST) {
         rc = ensureBuf(c.dIn, c.dInCap, n + 64); if (rc) return rc;
@@ -721,7 +963,7 @@ int zzgpu_debug_chunk(const uint8_t* src, size_t n, int src_mem, int level, uint
     CK(cudaMemcpy(&st, c.state + slot, sizeof st, cudaMemcpyDeviceToHost));
     if (cand) {
         // K-EMIT reuses the candidate rows as scratch: run K-CAND again for the tap
-        const Job job = makeJob(c, d_src, n, 0, 1, c.dOut, cap, level, chunk, dict, 0, 0, (uint32_t)nchunks, 0);
+        const Job job = makeJob(c, d_src, n, 0, 1, c.dOut, cap, level, chunk, dict, 0, 0, (uint32_t)nchunks);
         launch_candidates(job, c.stream);
         CK(cudaStreamSynchronize(c.stream));
         CK(cudaMemcpy(cand, c.cand + slot * chunk, (size_t)chunk * 2, cudaMemcpyDeviceToHost));

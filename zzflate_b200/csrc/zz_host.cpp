@@ -7,7 +7,9 @@
 #include "../../include/zzgpu.h"
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -56,49 +58,119 @@ struct Shard {
     size_t off = 0, len = 0;
     int device = 0;
     bool final = false;
-    std::vector<uint8_t> out;
     size_t outLen = 0;
     uint32_t adler0 = 0, crc = 0;
     int status = ZZGPU_OK;
 };
 
-// Raw deflate of source[0,n) into dest (capacity cap).  threaded => one contiguous range of chunks per
-// visible GPU, each primed with the bytes before it, stitched in order (zzflate.cpp:97-154).
-int deflateStream(uint8_t* dest, size_t cap, const uint8_t* source, size_t n, int level, bool threaded,
+// Contiguous ranges of whole chunks, one per device that gets any (zzflate.cpp:67-78 divideInRanges at chunk
+// granularity).  Only shards with data exist, so exactly the last one carries BFINAL.
+std::vector<Shard> partition(size_t n, int ndevAvail, uint32_t chunk)
+{
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    size_t ndev = (size_t)std::max(ndevAvail, 1);
+    if (ndev > nchunks) ndev = std::max<size_t>(nchunks, 1);
+    const size_t per = std::max<size_t>((nchunks + ndev - 1) / ndev, 1);
+    ndev = std::max<size_t>((nchunks + per - 1) / per, 1);          // devices that actually receive chunks
+    std::vector<Shard> shards(ndev);
+    for (size_t g = 0; g < ndev; ++g) {
+        Shard& s = shards[g];
+        const size_t c0 = std::min(nchunks, per * g), c1 = std::min(nchunks, per * (g + 1));
+        s.off = std::min(n, c0 * chunk); s.len = std::min(n, c1 * chunk) - s.off;
+        s.device = (int)g; s.final = (g + 1 == ndev);
+    }
+    return shards;
+}
+
+struct SinkCtx { const std::function<bool(const uint8_t*, size_t)>* cb; };
+
+int sinkTrampoline(const uint8_t* p, size_t len, void* user)
+{
+    (*static_cast<SinkCtx*>(user)->cb)(p, len);
+    return 0;
+}
+
+// Raw deflate of source[0,n).  Output goes either to dest (capacity cap) or, when `cb` is given, to the callback in
+// order, in pieces of at most kCallbackPiece bytes.  threaded => one contiguous range of chunks per visible GPU, each
+// primed with the bytes before it (zzflate.cpp:97-132).  Shard 0 streams straight to its destination while it is
+// encoded; the other shards stay in their GPU's memory until the sizes of the shards before them are known and are
+// then copied to their final place (no temporary, no host-side memmove as in zzflate.cpp:136-154).
+int deflateStream(uint8_t* dest, size_t cap, const std::function<bool(const uint8_t*, size_t)>* cb,
+                  const uint8_t* source, size_t n, int level, bool threaded,
                   Format format, size_t* outLen, uint32_t* adler, uint32_t* crc)
 {
     const int want = (format == Zlib ? 1 : 0) | (format == Gzip ? 2 : 0);
     const uint32_t chunk = ZZGPU_DEFAULT_CHUNK, dict = ZZGPU_DEFAULT_DICT;
-    const size_t nchunks = (n + chunk - 1) / chunk;
-    int ndev = threaded ? zzgpu_device_count() : 1;
-    if ((size_t)ndev > nchunks) ndev = (int)std::max<size_t>(nchunks, 1);
-    if (ndev <= 1) {
+    SinkCtx sctx = { cb };
+    std::vector<Shard> shards = partition(n, threaded ? zzgpu_device_count() : 1, chunk);
+    if (shards.size() <= 1) {
         uint32_t a0 = 0, c = 0;
-        int rc = zzgpu_deflate_ex(source, n, 0, 1, ZZGPU_MEM_HOST, dest, cap, ZZGPU_MEM_HOST, level, chunk, dict, want,
-                                  outLen, &a0, &c, nullptr);
+        int rc;
+        if (cb) rc = zzgpu_deflate_sink(source, n, 0, 1, level, chunk, dict, want, sinkTrampoline, &sctx, kCallbackPiece, outLen, &a0, &c, nullptr);
+        else rc = zzgpu_deflate_ex(source, n, 0, 1, ZZGPU_MEM_HOST, dest, cap, ZZGPU_MEM_HOST, level, chunk, dict, want,
+                                   outLen, &a0, &c, nullptr);
         if (rc) return rc;
         *adler = zzgpu_adler32_combine(1, a0, n);
         *crc = c;
         return ZZGPU_OK;
     }
-    std::vector<Shard> shards((size_t)ndev);
-    const size_t per = (nchunks + ndev - 1) / ndev;
-    for (int g = 0; g < ndev; ++g) {
-        Shard& s = shards[(size_t)g];
-        const size_t c0 = std::min(nchunks, per * g), c1 = std::min(nchunks, per * (g + 1));
-        s.off = std::min(n, c0 * chunk); s.len = std::min(n, c1 * chunk) - s.off;
-        s.device = g; s.final = (c1 == nchunks);
-    }
+    // one host thread per device; each keeps its device context until its stream has been fetched
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> sized(shards.size(), 0);          // shard g's size is known (or it failed)
+    std::vector<size_t> place(shards.size(), 0);        // final offset of shard g
+    bool abortAll = false;
+    size_t emitted = 0;                                  // callback mode: shards handed over so far
     std::vector<std::thread> threads;
-    for (auto& s : shards) {
-        threads.emplace_back([&s, source, level, want]() {
-            if (s.len == 0 && !s.final) return;
+    for (size_t g = 0; g < shards.size(); ++g) {
+        threads.emplace_back([&, g]() {
+            Shard& s = shards[g];
+            auto publish = [&](bool ok) {
+                std::lock_guard<std::mutex> lk(mu);
+                sized[g] = 1; if (!ok) abortAll = true;
+                cv.notify_all();
+            };
             s.status = zzgpu_init(s.device);
+            if (s.status) { publish(false); return; }
+            if (g == 0) {
+                // the first shard's place is known: it goes out while it is being encoded
+                if (cb) s.status = zzgpu_deflate_sink(source, s.len, 0, 0, level, chunk, dict, want, sinkTrampoline, &sctx, kCallbackPiece,
+                                                      &s.outLen, &s.adler0, &s.crc, nullptr);
+                else s.status = zzgpu_deflate_ex(source, s.len, 0, 0, ZZGPU_MEM_HOST, dest, cap, ZZGPU_MEM_HOST, level, chunk, dict, want,
+                                                 &s.outLen, &s.adler0, &s.crc, nullptr);
+                { std::lock_guard<std::mutex> lk(mu); emitted = 1; }
+                publish(s.status == ZZGPU_OK);
+                return;
+            }
+            s.status = zzgpu_deflate_hold(source + s.off, s.len, s.off, s.final ? 1 : 0, level, chunk, dict, want,
+                                          &s.outLen, &s.adler0, &s.crc, nullptr);
+            publish(s.status == ZZGPU_OK);
             if (s.status) return;
-            s.out.resize(zzgpu_bound(s.len, level, ZZGPU_DEFAULT_CHUNK));
-            s.status = zzgpu_deflate_ex(source + s.off, s.len, s.off, s.final ? 1 : 0, ZZGPU_MEM_HOST,
-                                        s.out.data(), s.out.size(), ZZGPU_MEM_HOST, level,
-                                        ZZGPU_DEFAULT_CHUNK, ZZGPU_DEFAULT_DICT, want, &s.outLen, &s.adler0, &s.crc, nullptr);
+            size_t at = 0;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                // direct mode: the sizes of all earlier shards; callback mode: all earlier shards handed over
+                cv.wait(lk, [&] {
+                    if (abortAll) return true;
+                    if (cb) return emitted == g;
+                    for (size_t k = 0; k < g; ++k) if (!sized[k]) return false;
+                    return true;
+                });
+                if (abortAll) { lk.unlock(); zzgpu_release(); return; }
+                for (size_t k = 0; k < g; ++k) at += shards[k].outLen;
+                place[g] = at;
+            }
+            if (cb) {
+                s.status = zzgpu_fetch(nullptr, 0, sinkTrampoline, &sctx, kCallbackPiece);
+                std::lock_guard<std::mutex> lk(mu);
+                emitted = g + 1; if (s.status) abortAll = true;
+                cv.notify_all();
+            } else if (at + s.outLen > cap) {
+                zzgpu_release();
+                s.status = ZZGPU_E_CAPACITY;
+            } else {
+                s.status = zzgpu_fetch(dest + at, cap - at, nullptr, nullptr, 0);
+            }
         });
     }
     for (auto& t : threads) t.join();
@@ -106,8 +178,6 @@ int deflateStream(uint8_t* dest, size_t cap, const uint8_t* source, size_t n, in
     uint32_t a = 1, c = 0;
     for (auto& s : shards) {
         if (s.status) return s.status;
-        if (pos + s.outLen > cap) return ZZGPU_E_CAPACITY;
-        memcpy(dest + pos, s.out.data(), s.outLen);
         pos += s.outLen;
         a = zzgpu_adler32_combine(a, s.adler0, s.len);
         c = zzgpu_crc32_combine(c, s.crc, s.len);
@@ -135,7 +205,7 @@ void ZzFlateEncode(uint8_t* dest, size_t* destLen, const uint8_t* source, size_t
     if (config->level > 3 || *destLen < hl + tl) { *destLen = ~(size_t)0; return; }     // zzflate.cpp:230-234
     memcpy(dest, h, hl);
     size_t body = 0; uint32_t adler = 1, crc = 0;
-    const int rc = deflateStream(dest + hl, *destLen - hl - tl, source, sourceLen, config->level, config->threaded,
+    const int rc = deflateStream(dest + hl, *destLen - hl - tl, nullptr, source, sourceLen, config->level, config->threaded,
                                  config->format, &body, &adler, &crc);
     if (rc != ZZGPU_OK) { *destLen = ~(size_t)0; return; }
     trailerBytes(config->format, adler, crc, sourceLen, t);
@@ -143,20 +213,20 @@ void ZzFlateEncode(uint8_t* dest, size_t* destLen, const uint8_t* source, size_t
     *destLen = hl + body + tl;
 }
 
+// Header, the stream in pieces of <= 1 000 000 bytes as they leave the GPU (the first piece arrives while later
+// input is still being copied in and encoded), trailer.  Nothing of the size of the whole stream is ever allocated.
 void ZzFlateEncodeToCallback(const uint8_t* source, size_t sourceLen, const Config* config,
                              std::function<bool(const uint8_t*, size_t)> callback)
 {
     if (config->level > 3) return;                                                     // zzflate.cpp:201-202
-    std::vector<uint8_t> buf(zzgpu_bound(sourceLen, config->level, ZZGPU_DEFAULT_CHUNK));
-    size_t body = 0; uint32_t adler = 1, crc = 0;
-    const int rc = deflateStream(buf.data(), buf.size(), source, sourceLen, config->level, config->threaded,
-                                 config->format, &body, &adler, &crc);
-    if (rc != ZZGPU_OK) return;
+    if (zzgpu_device_count() <= 0) return;                                             // no CPU fallback: nothing is delivered
     uint8_t h[10], t[8];
     const size_t hl = headerBytes(config->format, h);
     callback(h, hl);
-    for (size_t pos = 0; pos < body; pos += kCallbackPiece)
-        callback(buf.data() + pos, std::min(kCallbackPiece, body - pos));
+    size_t body = 0; uint32_t adler = 1, crc = 0;
+    const int rc = deflateStream(nullptr, 0, &callback, source, sourceLen, config->level, config->threaded,
+                                 config->format, &body, &adler, &crc);
+    if (rc != ZZGPU_OK) return;                       // a failed stream gets no trailer, so no inflater accepts it
     const size_t tl = trailerBytes(config->format, adler, crc, sourceLen, t);
     callback(t, tl);
 }
@@ -188,7 +258,6 @@ bool Encoder::AddData(const uint8_t* start, const uint8_t* end, bool final)
     if (level < 0 || level > 3) return false;
     const size_t n = (size_t)(end - start);
     if (n == 0 && !final) return true;
-    const size_t history = (start == lastEnd) ? contiguous : 0;
     const size_t need = zzgpu_bound(n, level, ZZGPU_DEFAULT_CHUNK);
     uint8_t* out; size_t cap;
     if (stream.start && stream.owned.empty()) {
@@ -198,13 +267,20 @@ bool Encoder::AddData(const uint8_t* start, const uint8_t* end, bool final)
         stream.start = stream.owned.data();
         out = stream.start + stream.written; cap = need;
     }
+    // The dictionary of this call is the private copy of what the previous calls were fed (the reference keeps its hash
+    // table across calls, encoder.cpp:248,320-327): the caller's earlier buffers are never read again.
     size_t outLen = 0;
-    const int rc = zzgpu_deflate_ex(start, n, history, final ? 1 : 0, ZZGPU_MEM_HOST, out, cap, ZZGPU_MEM_HOST, level,
-                                    ZZGPU_DEFAULT_CHUNK, ZZGPU_DEFAULT_DICT, 0, &outLen, nullptr, nullptr, nullptr);
+    const int rc = zzgpu_deflate_hist(start, n, tail.data(), tail.size(), final ? 1 : 0, out, cap, level,
+                                      ZZGPU_DEFAULT_CHUNK, ZZGPU_DEFAULT_DICT, &outLen);
     if (rc != ZZGPU_OK) return false;
     stream.written += outLen;
-    contiguous = history + n;
-    lastEnd = end;
+    const size_t keep = (size_t)ZZGPU_DEFAULT_DICT + 288;
+    if (n >= keep) tail.assign(end - keep, end);
+    else {
+        const size_t old = std::min(tail.size(), keep - n);
+        tail.erase(tail.begin(), tail.end() - (std::ptrdiff_t)old);
+        tail.insert(tail.end(), start, end);
+    }
     return true;
 }
 
@@ -266,6 +342,14 @@ ZZGPU_API void zz_c_merged_length_codes(const int32_t* symbolCodes286x2, int32_t
     for (int i = 0; i < 286; ++i) { sym[i].length = symbolCodes286x2[2 * i]; sym[i].bits = (uint32_t)symbolCodes286x2[2 * i + 1]; }
     Encoder::CreateMergedLengthCodes(l, sym);
     for (int i = 0; i < 259; ++i) { lcodes259x2[2 * i] = l[i].length; lcodes259x2[2 * i + 1] = (int32_t)l[i].bits; }
+}
+
+// shard partition of the multi-GPU driver: writes (offset, length, final) triples, returns the number of shards
+ZZGPU_API int zz_c_partition(size_t n, int ndev, uint32_t chunk, uint64_t* triples, int maxShards)
+{
+    const std::vector<Shard> sh = partition(n, ndev, chunk ? chunk : ZZGPU_DEFAULT_CHUNK);
+    for (size_t g = 0; g < sh.size() && (int)g < maxShards; ++g) { triples[3 * g] = sh[g].off; triples[3 * g + 1] = sh[g].len; triples[3 * g + 2] = sh[g].final ? 1 : 0; }
+    return (int)sh.size();
 }
 
 ZZGPU_API void* zz_c_encoder_new(int level, uint8_t* out, int64_t cap) { return new Encoder(level, out, cap); }

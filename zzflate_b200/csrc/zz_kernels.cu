@@ -16,9 +16,8 @@
 //                          small launches, thread per chunk for full batches
 //   K-OFFS   k_offsets     exclusive scan of chunk sizes -> output offsets (stitch of zzflate.cpp:136-154)
 //   K-EMIT   k_emit2       bit emission of header, records, EOB and the aligning stored block
-//            (k_emit)      (WriteRecords / WriteDistance / StartBlock / outputbitstream; encoder.cpp:135-169,
-//                           UncompressedFallback / WriteUncompressedBlock; encoder.cpp:305-317,482-502);
-//                          symbol-parallel, k_emit = the older position-range walk kept for A/B runs
+//                          (WriteRecords / WriteDistance / StartBlock / outputbitstream; encoder.cpp:135-169,
+//                           UncompressedFallback / WriteUncompressedBlock; encoder.cpp:305-317,482-502), symbol-parallel
 //   K-FIXED  k_fixed, k_gather   level 1: WriteBlockFixedHuff (encoder.cpp:329-373)
 //   K-CKSUM  k_checksums   per-chunk Adler-32 / CRC-32 partials (adler.cpp:17, crc.cpp:24)
 //
@@ -651,29 +650,6 @@ __device__ __forceinline__ int probe_next(const uint8_t* info, const unsigned* o
     const unsigned w2 = nzw[w + 1];
     if (w2 == kNone16) return -1;
     return base + (int)w2 * 32 + __ffs(okbits[w2]) - 1;
-}
-
-// Walks positions [a,b) of a chunk against its sorted match list; calls lit(pos) for every literal and
-// match(k, start, len) for every match that starts inside [a,b).
-template <class Lit, class Match>
-__device__ __forceinline__ void walk_positions(const uint32_t* tokA, int ntok, int a, int b, Lit lit, Match match)
-{
-    int lo = 0, hi = ntok;                              // first match whose end is > a
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        uint32_t t = tokA[mid];
-        int end = (int)(t & 0xFFFF) + (int)(t >> 16);
-        if (end > a) hi = mid; else lo = mid + 1;
-    }
-    int k = lo, pos = a;
-    while (pos < b) {
-        int ms = 0x7fffffff, ln = 0;
-        if (k < ntok) { uint32_t t = tokA[k]; ms = (int)(t & 0xFFFF); ln = (int)(t >> 16); }
-        if (ms < pos) { pos = ms + ln; ++k; continue; }           // inside a match that started before a
-        const int litEnd = ms < b ? ms : b;
-        for (; pos < litEnd; ++pos) lit(pos);
-        if (pos == ms && pos < b) { match(k, ms, ln); pos += ln; ++k; }
-    }
 }
 
 __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
@@ -1683,20 +1659,7 @@ __global__ void __launch_bounds__(1024) k_offsets(Job job)
 // ------------------------------------------------------------------------------------------------
 // K-EMIT : one CTA per chunk
 // ------------------------------------------------------------------------------------------------
-constexpr int kEmitThreads = 1024;
 constexpr int kOutWords = (kMaxChunk + 64) / 4;
-constexpr int kEmitWinBytes = 16 + kMaxChunk + 64;
-constexpr int kEmitSmem = kEmitWinBytes + kOutWords * 4 + (286 + 259 + 30) * 4;
-
-struct BitWriter {
-    unsigned* out; unsigned long long acc; int used; int word;
-    __device__ __forceinline__ void init(unsigned* o, unsigned bitOffset) { out = o; acc = 0; word = (int)(bitOffset >> 5); used = (int)(bitOffset & 31); }
-    __device__ __forceinline__ void put(unsigned bits, int n) {          // n <= 32
-        acc |= (unsigned long long)bits << used; used += n;
-        if (used >= 32) { atomicOr(&out[word], (unsigned)acc); acc >>= 32; used -= 32; ++word; }
-    }
-    __device__ __forceinline__ void flush() { if (used > 0) atomicOr(&out[word], (unsigned)acc); }
-};
 
 __device__ __forceinline__ void copy_out(uint8_t* D, const unsigned* out32, unsigned bytes)
 {
@@ -1713,138 +1676,8 @@ __device__ __forceinline__ void copy_out(uint8_t* D, const unsigned* out32, unsi
     if ((unsigned)tid < bytes - done) D[done + tid] = out8[done + tid];
 }
 
-__global__ void __launch_bounds__(kEmitThreads, 1) k_emit(Job job)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* win = smem;
-    unsigned* out = reinterpret_cast<unsigned*>(smem + kEmitWinBytes);
-    unsigned* litc = out + kOutWords;        // bits | len << 24
-    unsigned* lenc = litc + 286;             // merged length codes (CreateMergedLengthCodes, encoder.cpp:126-133)
-    unsigned* dstc = lenc + 259;
-    __shared__ unsigned wsum[32];
-    __shared__ unsigned sTotalBits;
-
-    const unsigned slot = blockIdx.x;
-    const Geom g = chunk_geom(job, slot);
-    const ChunkState st = job.state[slot];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint8_t* chunk0 = job.src + g.off;
-    if (st.out_off + st.out_bytes > job.cap) {                        // never write past the caller's buffer
-        if (tid == 0) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 1ull);
-        return;
-    }
-    uint8_t* D = job.dst + st.out_off;
-
-    if (st.block_type == 0) {
-        // stored blocks of <= 65535 bytes (encoder.cpp:482-502), then the aligning block for non-final chunks
-        int written = 0; unsigned o = 0;
-        while (written < g.body) {
-            const int len = min(g.body - written, 0xFFFF);
-            if (tid == 0) {
-                D[o] = (uint8_t)((g.final && written + len == g.body) ? 1 : 0);
-                D[o + 1] = (uint8_t)len; D[o + 2] = (uint8_t)(len >> 8);
-                D[o + 3] = (uint8_t)~len; D[o + 4] = (uint8_t)((~len) >> 8);
-            }
-            for (int i = tid; i < len; i += kEmitThreads) D[o + 5 + i] = chunk0[written + i];
-            o += 5 + len; written += len;
-        }
-        if (!g.final && tid == 0) {
-            D[o] = 0; D[o + 1] = 1; D[o + 2] = 0; D[o + 3] = 0xFE; D[o + 4] = 0xFF; D[o + 5] = chunk0[g.n - 1];
-        }
-        return;
-    }
-
-    const int wb = (int)(reinterpret_cast<uintptr_t>(chunk0) & 15);   // phase-preserving base (0..15)
-    load_window(win, wb, chunk0, 0, g.n, g.n + 16);
-    for (int i = tid; i < kOutWords; i += kEmitThreads) out[i] = 0;
-    const ChunkCodes& cc = job.codes[slot];
-    for (int i = tid; i < 286; i += kEmitThreads) { uint32_t c = cc.lit[i]; litc[i] = (c & 0xFFFF) | ((c >> 16) << 24); }
-    for (int i = tid; i < 30; i += kEmitThreads) { uint32_t c = cc.dist[i]; dstc[i] = (c & 0xFFFF) | ((c >> 16) << 24); }
-    __syncthreads();
-    for (int i = tid; i < 259; i += kEmitThreads) {
-        unsigned v = 0;
-        if (i >= 3) {
-            int eb, ev; const int sym = len_symbol(i, eb, ev);
-            const unsigned c = litc[sym]; const unsigned cl = c >> 24;
-            v = ((c & 0xFFFFFF) | ((unsigned)ev << cl)) | ((cl + eb) << 24);
-        }
-        lenc[i] = v;
-    }
-    const uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
-    const uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
-    const int ntok = (int)st.ntok;
-    __syncthreads();
-
-    const int per = (g.body + kEmitThreads - 1) / kEmitThreads;
-    int a = tid * per, b = a + per; if (b > g.body) b = g.body; if (a > b) a = b;
-
-    // pass 1: bits produced by this thread's positions
-    unsigned mybits = 0;
-    walk_positions(tokA, ntok, a, b,
-        [&](int pos) { mybits += litc[win[wb + pos]] >> 24; },
-        [&](int k, int, int ln) {
-            int eb, ev; const int ds = dist_symbol(tokD[k], eb, ev);
-            mybits += (lenc[ln] >> 24) + (dstc[ds] >> 24) + eb;
-        });
-    unsigned inc = mybits;
-    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned s = wsum[lane];
-        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
-        wsum[lane] = s;
-    }
-    __syncthreads();
-    const unsigned start = st.hdr_bits + (warp ? wsum[warp - 1] : 0) + inc - mybits;
-    if (tid == kEmitThreads - 1) sTotalBits = start + mybits;
-
-    // header bit string
-    for (unsigned i = tid; i < (st.hdr_bits + 31) / 32; i += kEmitThreads) {
-        const uint8_t* h = cc.hdr + i * 4;
-        unsigned v = h[0] | (h[1] << 8) | (h[2] << 16) | ((unsigned)h[3] << 24);
-        const unsigned rem = st.hdr_bits - i * 32;
-        if (rem < 32) v &= (1u << rem) - 1u;
-        atomicOr(&out[i], v);
-    }
-
-    // pass 2: write
-    BitWriter bw; bw.init(out, start);
-    walk_positions(tokA, ntok, a, b,
-        [&](int pos) { const unsigned c = litc[win[wb + pos]]; bw.put(c & 0xFFFFFF, (int)(c >> 24)); },
-        [&](int k, int, int ln) {
-            const unsigned lc = lenc[ln];
-            bw.put(lc & 0xFFFFFF, (int)(lc >> 24));
-            const int d = tokD[k];
-            int eb, ev; const int ds = dist_symbol(d, eb, ev);
-            const unsigned dc = dstc[ds]; const int dl = (int)(dc >> 24);
-            bw.put((dc & 0xFFFFFF) | ((unsigned)ev << dl), dl + eb);
-        });
-    bw.flush();
-    __syncthreads();
-
-    if (tid == 0) {
-        unsigned q = sTotalBits;
-        const unsigned eob = litc[256];
-        BitWriter e; e.init(out, q); e.put(eob & 0xFFFFFF, (int)(eob >> 24)); e.flush();
-        q += eob >> 24;
-        if ((unsigned long long)q != st.total_bits)                 // K-HUFF's exact size and K-EMIT must agree
-            atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 2ull);
-        unsigned bytes = (q + 7) >> 3;
-        if (!g.final) {
-            const unsigned bp = (q + 3 + 7) >> 3;                   // 3 header bits of the stored block, then pad
-            uint8_t* o8 = reinterpret_cast<uint8_t*>(out);
-            o8[bp] = 1; o8[bp + 1] = 0; o8[bp + 2] = 0xFE; o8[bp + 3] = 0xFF; o8[bp + 4] = win[wb + g.n - 1];
-            bytes = bp + 5;
-        }
-        if (bytes != st.out_bytes) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 4ull);
-    }
-    __syncthreads();
-    copy_out(D, out, st.out_bytes);
-}
-
 // ------------------------------------------------------------------------------------------------
-// K-EMIT, symbol-parallel variant.  The bit stream interleaves two sequences that are each compact in memory: the
+// K-EMIT, symbol-parallel.  The bit stream interleaves two sequences that are each compact in memory: the
 // literals (K-MATCH leaves the literal bytes of the block in order in the chunk's info row) and the matches (the token
 // list).  With l_k = number of literals before match k, the write offsets are
 //     literal i : header + (code bits of literals < i) + (bits of the matches k with l_k <= i)
@@ -2392,7 +2225,6 @@ cudaError_t configure_kernels()
 {
     cudaError_t e;
     e = cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kParseSmem); if (e) return e;
-    e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmitSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_huffman_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffLSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_emit2, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmit2Smem); if (e) return e;
     e = cudaFuncSetAttribute(k_info, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfoSmem); if (e) return e;
@@ -2461,13 +2293,16 @@ int launch_offsets(const Job& job, cudaStream_t s)
     return 1;
 }
 
-static int g_emitVariant = 1;        // 0: position-range walk (k_emit), 1: symbol-parallel (k_emit2)
-void set_emit_variant(int v) { g_emitVariant = v; }
+// A/B switches of kernel variants (zzgpu_set_option); none changes the produced bytes.
+bool set_kernel_option(const char* name, int value)
+{
+    (void)name; (void)value;
+    return false;
+}
 
 int launch_emit(const Job& job, cudaStream_t s)
 {
-    if (g_emitVariant == 0) k_emit<<<job.nchunks, kEmitThreads, kEmitSmem, s>>>(job);
-    else k_emit2<<<job.nchunks, kEmit2Threads, kEmit2Smem, s>>>(job);
+    k_emit2<<<job.nchunks, kEmit2Threads, kEmit2Smem, s>>>(job);
     return 1;
 }
 

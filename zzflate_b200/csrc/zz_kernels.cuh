@@ -71,7 +71,7 @@ int launch_checksums(const Job& job, cudaStream_t s);
 int launch_fixed(const Job& job, cudaStream_t s);     // level 1: bits into the scratch slot
 int launch_gather(const Job& job, cudaStream_t s);    // level 1: scratch slot -> stream
 cudaError_t configure_kernels();
-void set_emit_variant(int v);
+bool set_kernel_option(const char* name, int value);   // true if the name is known
 
 // host-side checksum folds
 uint32_t adler32_combine(uint32_t first, uint32_t second, size_t lenSecond);
