@@ -1676,6 +1676,31 @@ __device__ __forceinline__ void copy_out(uint8_t* D, const unsigned* out32, unsi
     if ((unsigned)tid < bytes - done) D[done + tid] = out8[done + tid];
 }
 
+// global -> global copy of `bytes` bytes at arbitrary alignments (stored blocks): whole destination words, each from two
+// aligned source words (a source word that holds a needed byte never leaves the buffer's pages)
+__device__ __forceinline__ void copy_g2g(uint8_t* D, const uint8_t* S, unsigned bytes)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(D) & 3);
+    unsigned head = mis ? 4 - mis : 0; if (head > bytes) head = bytes;
+    if ((unsigned)tid < head) D[tid] = S[tid];
+    const unsigned nfull = (bytes - head) >> 2;
+    unsigned* Dw = reinterpret_cast<unsigned*>(D + head);
+    const uint8_t* S2 = S + head;
+    const unsigned smis = (unsigned)(reinterpret_cast<uintptr_t>(S2) & 3);
+    const unsigned* Sw = reinterpret_cast<const unsigned*>(S2 - smis);
+    if (smis == 0) {
+#pragma unroll 4
+        for (unsigned i = tid; i < nfull; i += nt) Dw[i] = __ldg(Sw + i);
+    } else {
+        const int sh = (int)smis * 8;
+#pragma unroll 4
+        for (unsigned i = tid; i < nfull; i += nt) Dw[i] = __funnelshift_r(__ldg(Sw + i), __ldg(Sw + i + 1), sh);
+    }
+    const unsigned done = head + nfull * 4;
+    if ((unsigned)tid < bytes - done) D[done + tid] = S[done + tid];
+}
+
 // ------------------------------------------------------------------------------------------------
 // K-EMIT, symbol-parallel.  The bit stream interleaves two sequences that are each compact in memory: the
 // literals (K-MATCH leaves the literal bytes of the block in order in the chunk's info row) and the matches (the token
@@ -1741,7 +1766,7 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
                 Dst[o + 1] = (uint8_t)len; Dst[o + 2] = (uint8_t)(len >> 8);
                 Dst[o + 3] = (uint8_t)~len; Dst[o + 4] = (uint8_t)((~len) >> 8);
             }
-            for (int i = tid; i < len; i += kEmit2Threads) Dst[o + 5 + i] = chunk0[written + i];
+            copy_g2g(Dst + o + 5, chunk0 + written, (unsigned)len);
             o += 5 + len; written += len;
         }
         if (!g.final && tid == 0) {
