@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the output checks that run after the timed loops")
+    ap.add_argument("--opt", action="append", default=[], help="name=value passed to zzgpu_set_option (A/B of kernel variants)")
     ap.add_argument("--format", default="zlib", choices=["zlib", "gzip", "deflate"], help="framing of the end-to-end leg")
     args = ap.parse_args()
 
@@ -200,6 +201,10 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     _lib.check(_lib.load().zzgpu_init(local_rank))
+    for kv in args.opt:
+        k, v = kv.split("=")
+        _lib.check(_lib.load().zzgpu_set_option(k.encode(), int(v)))
+        config.setdefault("options", {})[k] = int(v)
 
     nbytes = args.shard_mib << 20
     host, hist = make_shard(args.workload, rank, nbytes)

@@ -71,7 +71,7 @@ typedef struct zzgpu_stats {
 } zzgpu_stats;
 
 enum { ZZGPU_STAGE_CAND = 0, ZZGPU_STAGE_PARSE = 1, ZZGPU_STAGE_HUFF = 2, ZZGPU_STAGE_OFFS = 3, ZZGPU_STAGE_EMIT = 4,
-       ZZGPU_STAGE_CKSUM = 5, ZZGPU_STAGE_FIXED = 6, ZZGPU_STAGE_GATHER = 7, ZZGPU_STAGE_INFO = 8 };
+       ZZGPU_STAGE_CKSUM = 5, ZZGPU_STAGE_FIXED = 6, ZZGPU_STAGE_GATHER = 7, ZZGPU_STAGE_INFO = 8, ZZGPU_STAGE_LZ = 9 };
 
 /* Select the device used by the calling thread's subsequent calls (default: current CUDA device).
  * Creates the per-device context (stream, scratch) lazily.  Returns ZZGPU_E_NO_DEVICE without a GPU. */

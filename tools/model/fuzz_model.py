@@ -9,8 +9,9 @@ lib = C.CDLL('tools/model/liblzmodel.so')
 lib.lzm_chunk.restype = C.c_int
 lib.lzm_chunk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
 o = oracle()
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 30
-seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+_main = __name__ == "__main__"
+budget = float(sys.argv[1]) if _main and len(sys.argv) > 1 else 30
+seed = int(sys.argv[2]) if _main and len(sys.argv) > 2 else 1
 rng = np.random.default_rng(seed)
 text = synth.markov_text(1 << 20, seg0=11, threads=1).tobytes()
 

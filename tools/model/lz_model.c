@@ -61,7 +61,7 @@ typedef struct {
     uint8_t info[SUBCAP + 64];
     uint16_t F[SUBCAP];
     uint16_t dist[SUBCAP + 64];
-    uint8_t S[SUBCAP], T[SUBCAP];
+    uint8_t S[SUBCAP], T[SUBCAP], L[SUBCAP];
 } Sub;
 
 /* first position the walk takes from state b, or -1 (positions outside [s0,s1) are masked) */
@@ -117,7 +117,7 @@ int lzm_chunk(const uint8_t* c, int n, int body, int pre, const uint16_t* cand, 
             int lowb = b > s0 - 64 ? b : s0 - 64; if (lowb > s0) lowb = s0;
             s->base = lowb & ~31; s->s0 = s0; s->s1 = s1;
             s->lim = ((s1 - s->base + 31) >> 5) * 32;
-            memset(s->info, 0, sizeof s->info); memset(s->S, 0, sizeof s->S); memset(s->T, 0, sizeof s->T);
+            memset(s->info, 0, sizeof s->info); memset(s->S, 0, sizeof s->S); memset(s->T, 0, sizeof s->T); memset(s->L, 0, sizeof s->L);
             for (int j = s0; j < s1; ++j) {
                 int d = cand_of(cand, &ps, j);
                 s->dist[j - s->base] = (uint16_t)d;
@@ -131,67 +131,96 @@ int lzm_chunk(const uint8_t* c, int n, int body, int pre, const uint16_t* cand, 
                 b = exact_token(c, pre, b, j, d, &ms, &m); EMIT(ms, m, d);
                 if (b >= s1) { s0 = s1; continue; }
             }
-            /* F over the states of the sub-batch */
-            for (int x = s->base; x < s->base + s->lim; ++x) {
-                unsigned f = 0;
-                if (x >= B0 && x < s1) {
-                    int j = probe_next(s, x);
-                    if (j >= 0) { int fwd = s->info[j - s->base] - 1; f = needs_exact(fwd, j - x) ? 1u : (unsigned)(j + fwd); }
+            /* exact next states of long matches measured so far in this sub-batch */
+            int exN = 0; static int exX[4096], exNb[4096];
+#define SUCC(x, out) do { unsigned f_ = 0; if ((x) >= B0 && (x) < s1) { int j_ = probe_next(s, (x)); if (j_ >= 0) { int fw_ = s->info[j_ - s->base] - 1; f_ = needs_exact(fw_, j_ - (x)) ? 1u : (unsigned)(j_ + fw_); } } (out) = f_; } while (0)
+#define LOOKUP(x, out) do { (out) = 0; for (int q_ = 0; q_ < exN; ++q_) if (exX[q_] == (x)) (out) = (unsigned)exNb[q_]; } while (0)
+#define EXACT(x, out) do { int j_ = probe_next(s, (x)); int d_ = s->dist[j_ - s->base], ms_, m_; int nb_ = exact_token(c, pre, (x), j_, d_, &ms_, &m_); \
+                           exX[exN] = (x); exNb[exN] = nb_; ++exN; (out) = nb_; } while (0)
+            /* speculative chains: 128 lanes (4 warps), lane i owns states [base + 64 i, base + 64 (i+1)) (the last lane also the tail) */
+            enum { NL = 128, SEG = 64 };
+            int stopState[NL], stopKind[NL], stopTgt[NL], chX[NL];      /* kind: 0 none, 1 ends, 2 breaker, 3 leaves the segment */
+            for (int i = 0; i < NL; ++i) { stopKind[i] = 0; chX[i] = s->base + SEG * i; }
+            for (int round = 0; g_spec; ++round) {
+                int any = 0;
+                for (int i = 0; i < NL; ++i) {
+                    int segLo = s->base + SEG * i, segHi = i == NL - 1 ? s->base + s->lim : segLo + SEG;
+                    if (segLo >= s1 || stopKind[i] != 0) continue;
+                    int x = chX[i];
+                    for (;;) {
+                        s->S[x - s->base] = 1; g_stat_spec++;
+                        unsigned f; SUCC(x, f);
+                        if (f == 0) { stopKind[i] = 1; stopState[i] = x; break; }
+                        if (f == 1) { stopKind[i] = 2; stopState[i] = x; break; }
+                        if ((int)f >= segHi || (int)f >= s1) { stopKind[i] = 3; stopState[i] = x; stopTgt[i] = (int)f; break; }
+                        x = (int)f;
+                    }
                 }
-                s->F[x - s->base] = (uint16_t)f;
+                /* per warp: breakers are measured speculatively only while they are few */
+                for (int w = 0; w < NL / 32; ++w) {
+                    int cnt = 0;
+                    for (int l = 0; l < 32; ++l) cnt += stopKind[32 * w + l] == 2 && chX[32 * w + l] >= 0;
+                    if (cnt == 0 || cnt > 8) { for (int l = 0; l < 32; ++l) if (stopKind[32 * w + l] == 2) chX[32 * w + l] = -1; continue; }
+                    for (int l = 0; l < 32; ++l) {
+                        int i = 32 * w + l;
+                        if (stopKind[i] != 2 || chX[i] < 0) continue;
+                        int segLo = s->base + SEG * i, segHi = i == NL - 1 ? s->base + s->lim : segLo + SEG;
+                        unsigned nb; LOOKUP(stopState[i], nb);
+                        if (!nb) EXACT(stopState[i], nb);
+                        if ((int)nb >= segHi || (int)nb >= s1) { stopKind[i] = 3; stopTgt[i] = (int)nb; }
+                        else { stopKind[i] = 0; chX[i] = (int)nb; any = 1; }
+                    }
+                }
+                if (!any) break;
             }
-            /* speculative chains: lane i owns states [base + 256 i, base + 256 (i+1)) (the last lane also the tail) */
-            int stopState[32], stopKind[32], stopTgt[32];      /* kind: 0 none, 1 ends (F==0), 2 breaker (F==1), 3 leaves the segment */
-            for (int i = 0; i < 32; ++i) {
-                stopKind[i] = 0;
-                if (!g_spec) continue;
-                int segLo = s->base + 256 * i, segHi = i == 31 ? s->base + s->lim : segLo + 256;
-                if (segLo >= s1) continue;
-                int x = segLo;
+            /* links */
+            int linkMp[NL];
+            for (int i = 0; i < NL; ++i) {
+                linkMp[i] = -1;
+                if (!g_spec || i == 0 || stopKind[i - 1] != 3 || stopKind[i] == 0) continue;
+                int segLo = s->base + SEG * i, segHi = i == NL - 1 ? s->base + s->lim : segLo + SEG;
+                int x = stopTgt[i - 1];
+                if (x < segLo || x >= segHi || x >= s1) continue;
                 for (;;) {
-                    s->S[x - s->base] = 1; g_stat_spec++;
-                    unsigned f = s->F[x - s->base];
-                    if (f == 0) { stopKind[i] = 1; stopState[i] = x; break; }
-                    if (f == 1) { stopKind[i] = 2; stopState[i] = x; break; }
-                    if ((int)f >= segHi || (int)f >= s1) { stopKind[i] = 3; stopState[i] = x; stopTgt[i] = (int)f; break; }
+                    if (s->S[x - s->base]) { linkMp[i] = x; break; }
+                    s->L[x - s->base] = 1;
+                    unsigned f; SUCC(x, f);
+                    if (f == 1) LOOKUP(x, f);
+                    if (f == 0 || (int)f >= segHi || (int)f >= s1) break;
                     x = (int)f;
                 }
             }
             /* the true walk */
-            int mp[32]; for (int i = 0; i < 32; ++i) mp[i] = -1;
+            int mp[NL], linked[NL]; for (int i = 0; i < NL; ++i) { mp[i] = -1; linked[i] = 0; }
             int cur = b, bout = -1;
             for (;;) {
                 if (cur >= s1) { bout = cur; break; }
-                int i = (cur - s->base) >> 8; if (i > 31) i = 31;
+                int i = (cur - s->base) / SEG; if (i > NL - 1) i = NL - 1;
                 int x;
                 if (s->S[cur - s->base] && stopKind[i] && mp[i] < 0) {
                     mp[i] = cur; g_stat_merged++;
+                    while (stopKind[i] == 3 && i + 1 < NL && linkMp[i + 1] >= 0) { ++i; linked[i] = 1; mp[i] = linkMp[i]; }
                     if (stopKind[i] == 1) { bout = stopState[i]; break; }
                     if (stopKind[i] == 3) { cur = stopTgt[i]; continue; }
-                    x = stopState[i];                       /* breaker: resolved below */
+                    x = stopState[i];                       /* breaker left unmeasured: resolved below */
                 } else {
                     x = cur; s->T[x - s->base] = 1; g_stat_truewalk++;
-                    unsigned f = s->F[x - s->base];
+                    unsigned f; SUCC(x, f);
                     if (f == 0) { bout = x; break; }
                     if (f != 1) { cur = (int)f; continue; }
                 }
-                {   /* exact resolution of the long match at state x */
-                    int j = probe_next(s, x);
-                    int d = s->dist[j - s->base], ms, m;
-                    int nb = exact_token(c, pre, x, j, d, &ms, &m);
-                    s->F[x - s->base] = (uint16_t)(nb < 65535 ? nb : 65535);
-                    cur = nb;
-                }
+                { unsigned nb; LOOKUP(x, nb); if (!nb) EXACT(x, nb); cur = (int)nb; }
             }
-            for (int i = 0; i < 32; ++i) if (mp[i] >= 0) {
-                int segLo = s->base + 256 * i, segHi = i == 31 ? s->base + s->lim : segLo + 256;
-                (void)segLo;
+            for (int i = 0; i < NL; ++i) if (mp[i] >= 0) {
+                int segLo = s->base + SEG * i, segHi = i == NL - 1 ? s->base + s->lim : segLo + SEG;
                 for (int x = mp[i]; x < segHi; ++x) if (s->S[x - s->base]) s->T[x - s->base] = 1;
+                if (linked[i]) for (int x = segLo; x < segHi; ++x) if (s->L[x - s->base]) s->T[x - s->base] = 1;
             }
             /* tokens of the sub-batch */
             for (int x = s->base; x < s->base + s->lim; ++x) if (s->T[x - s->base]) {
-                unsigned f = s->F[x - s->base];
+                unsigned f; SUCC(x, f);
                 if (f == 0) continue;                      /* the orbit's last state: no token */
+                if (f == 1) LOOKUP(x, f);
                 int j = probe_next(s, x);
                 int d = s->dist[j - s->base];
                 int fwd = s->info[j - s->base] - 1;

@@ -33,7 +33,7 @@ class Stats(C.Structure):
         ("stage_ms", C.c_float * 10), ("stage_launches", C.c_uint32 * 10),
     ]
 
-STAGES = ["cand", "parse", "huff", "offs", "emit", "cksum", "fixed", "gather", "info", "spare"]
+STAGES = ["cand", "parse", "huff", "offs", "emit", "cksum", "fixed", "gather", "info", "lz"]
 
 
 # every symbol include/zzgpu.h declares; tests check that the library exports all of them

@@ -342,8 +342,12 @@ int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final,
         rc = markStage(c, -1, st); if (rc) return rc;
         if (level >= 2) {
             launches += launch_candidates(job, st); rc = markStage(c, ZZGPU_STAGE_CAND, st); if (rc) return rc;
-            launches += launch_info(job, st); rc = markStage(c, ZZGPU_STAGE_INFO, st); if (rc) return rc;
-            launches += launch_parse(job, st); rc = markStage(c, ZZGPU_STAGE_PARSE, st); if (rc) return rc;
+            if (use_fused_lz()) {
+                launches += launch_lz(job, st); rc = markStage(c, ZZGPU_STAGE_LZ, st); if (rc) return rc;
+            } else {
+                launches += launch_info(job, st); rc = markStage(c, ZZGPU_STAGE_INFO, st); if (rc) return rc;
+                launches += launch_parse(job, st); rc = markStage(c, ZZGPU_STAGE_PARSE, st); if (rc) return rc;
+            }
         }
         if (level == 1) {
             launches += launch_fixed(job, st); rc = markStage(c, ZZGPU_STAGE_FIXED, st); if (rc) return rc;

@@ -1122,6 +1122,873 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K-LZ : match info and greedy parse fused, one CTA per chunk (replaces K-INFO + K-MATCH; FirstPass, countMatchBackward,
+// remain, GetFrequencies; encoder.cpp:81-102,375-471).
+//
+// The CTA walks the chunk in the reference's batches of 16 384 positions (WriteBlock2Pass, encoder.cpp:225-234).  For
+// each batch the window [batch start - 33 056, batch end + 304) is brought into shared memory with one-dimensional
+// bulk copies (cp.async.bulk + mbarrier: the TMA engine moves the aligned interior, threads patch the ragged edges), and
+// everything the parse needs is read from there: candidate compares, exact lengths of long matches, backward extension.
+// A batch is processed in sub-batches of up to 8192 positions:
+//   A  info[j] = 0 / 1 + min(forward match length, 32) for every position (the compare part of FirstPass, as in the
+//      former K-INFO: four positions per thread, long compares queued per warp)
+//   C  A state b is the end of the previous match; from b the walk takes the first position j > b that is usable and far
+//      enough (j - b >= 4 - min(fwd, 4)) and moves to succ(b) = j + fwd.  The parse is the orbit of succ from the
+//      entry state.  succ is evaluated on the fly from info and a bitmap of usable positions, only for states that are
+//      visited.  Orbits that start at different states merge after a few matches (the walk re-synchronises), so 128
+//      lanes first follow succ speculatively, each through its own 64-state segment from the segment's first state,
+//      marking what they visit (chains); each lane then follows succ from the state where its left neighbour's chain entered
+//      its segment until it steps on its own chain (links).  One walk from the true entry state follows succ only until it
+//      steps on a chain; from there the chains are the orbit as far as the links connect them, so the walk continues behind
+//      the last connected segment.  Matches of 32 bytes or more (or behind a literal gap so long that the backward extension
+//      could hit the 258 cap) end a chain; while they are few they are measured exactly by the chain's warp (all lanes
+//      compare, up to 258 bytes forwards and backwards) and the chain goes on, otherwise the true walk measures them as it
+//      meets them, runs of equal 258-byte matches 32 at a time.
+//   D  the visited states are compacted and expanded to tokens in parallel (backward extension bounded by the pending
+//      literals, encoder.cpp:404-416).
+// After the last batch: histograms and the literal stream for K-EMIT, as before.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLzThreads = 512;
+constexpr int kLzWarps = kLzThreads / 32;
+constexpr int kLzBack = kPreCap;                          // bytes kept before the batch's first probed position
+constexpr int kLzAhead = 304;                             // bytes kept behind its last one (258 + 8-byte loads + slack)
+constexpr int kLzWin = 32 + kLzBack + kBatch + kLzAhead + 16;
+static_assert(kLzWin % 16 == 0 && kLzWin < 65536, "window offsets are kept in 16 bits");
+constexpr int kSub = 8192;                                // states per sub-batch (tile-aligned base up to 95 below its first position)
+constexpr int kSubTiles = kSub / 32;
+constexpr int kSubWords = kSubTiles + 5;
+constexpr int kSegStates = 64;                            // states per lane in the speculative pass
+constexpr int kChains = kSub / kSegStates;
+constexpr int kChaseWarps = kChains / 32;
+static_assert(kChains % 32 == 0 && kChaseWarps <= kLzWarps && kSubTiles <= kLzThreads && kSub % (4 * kLzThreads) == 0, "geometry");
+constexpr int kLzQueue = 32 + 128;
+constexpr int kExCap = 256;                               // exactly measured long matches remembered per sub-batch
+constexpr int kLzScratch = kLzWarps * kLzQueue * 4;       // phase A: long-compare queues; afterwards: bitmaps, nzw, state list
+static_assert(4 * kSubWords * 4 + 544 + (kSub / 4 + 40) * 2 <= kLzScratch, "bitmaps + nzw + state list fit the queue space");
+constexpr int kLzSmem = kLzWin + (kSub + 64) + kLzScratch;
+static_assert(3 * (kLzSmem + 4096) <= 228 * 1024, "K-LZ leaves a third of the SM's shared memory to its neighbours");
+
+struct LzShared {
+    int pos;            // start of the next FirstPass batch
+    int ntok;
+    int nexcl;          // batch starts that were never inserted into the hash table
+    int excl[4];
+    int npatch;         // positions whose candidate changes because of an excluded batch start
+    int patchJ[4];
+    int patchD[4];
+    int npend;          // positions found in phase A whose candidate is an excluded batch start
+    int pendJ[8];
+    int b;              // current state of the walk
+    int npre;           // tokens written directly by warp 0 in this sub-batch (first probe / far entry)
+    int exN;            // entries of the exact list
+    int endsAt;         // orbit state without successor in the sub-batch (it yields no token), or -1
+    int err;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// one-dimensional bulk copy global -> shared through the TMA engine; all three of dst, src, bytes are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void chase_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kChaseWarps * 32) : "memory"); }
+
+// info of one position from the window (same definition as phase A); oj = window offset of the position
+__device__ int info_of_w(const uint8_t* win, int oj, int d, int room)
+{
+    if (d == 0) return 0;
+    const int op = oj - d;
+    int fwd = 0;
+    while (fwd < kCapLen) {
+        const unsigned x = ld4(win, oj + fwd) ^ ld4(win, op + fwd);
+        if (x) { fwd += (__ffs(x) - 1) >> 3; break; }
+        fwd += 4;
+    }
+    bool ok = fwd >= 4;
+    if (!ok) {
+        const unsigned y = ld4(win, oj - 4) ^ ld4(win, op - 4);
+        int back = y ? (__clz(y) >> 3) : 4;
+        if (back > room) back = room;                    // bytes of real history before the candidate (R4 clamp)
+        ok = fwd + back >= 4;
+    }
+    return ok ? fwd + 1 : 0;
+}
+
+// exact forward and backward match lengths (<= 258 each), all 32 lanes cooperate (remain(), countMatchBackward;
+// encoder.cpp:81-102); window offsets
+__device__ __forceinline__ void coop_lengths_w(const uint8_t* win, int oj, int op, int lane, bool wantBack, int& fwd, int& lb)
+{
+    const unsigned long long xa = ld8(win, oj + lane * 8) ^ ld8(win, op + lane * 8);
+    unsigned long long xb = 0;
+    unsigned ta = 1, tb = 1;
+    if (wantBack) xb = ld8(win, oj - 8 - lane * 8) ^ ld8(win, op - 8 - lane * 8);
+    if (lane < 2) ta = (unsigned)(win[oj + 256 + lane] ^ win[op + 256 + lane]);
+    if (wantBack && lane < 2) tb = (unsigned)(win[oj - 257 - lane] ^ win[op - 257 - lane]);
+    const unsigned ma = __ballot_sync(0xffffffffu, xa != 0);
+    const unsigned mta = __ballot_sync(0xffffffffu, ta == 0);       // bit 0: byte 256 equal, bit 1: byte 257 equal
+    if (ma) {
+        const int src = __ffs(ma) - 1;
+        const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src);
+        fwd = src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
+    } else {
+        fwd = 256 + ((mta & 1u) ? ((mta & 2u) ? 2 : 1) : 0);
+    }
+    lb = 0;
+    if (wantBack) {
+        const unsigned mb = __ballot_sync(0xffffffffu, xb != 0);
+        const unsigned mtb = __ballot_sync(0xffffffffu, tb == 0);
+        if (mb) {
+            const int src = __ffs(mb) - 1;
+            const unsigned long long xs = __shfl_sync(0xffffffffu, xb, src);
+            lb = src * 8 + (__clzll((long long)xs) >> 3);
+        } else {
+            lb = 256 + ((mtb & 1u) ? ((mtb & 2u) ? 2 : 1) : 0);
+        }
+    }
+}
+
+// single-thread backward match length from the window, at most `limit` bytes
+__device__ __forceinline__ int back_upto_w(const uint8_t* win, int oj, int op, int limit)
+{
+    int lb = 0;
+    while (lb < limit) {
+        const unsigned y = ld4(win, oj - 4 - lb) ^ ld4(win, op - 4 - lb);
+        const int c = y ? (__clz(y) >> 3) : 4;
+        lb += c;
+        if (c < 4) break;
+    }
+    return lb < limit ? lb : limit;
+}
+
+// single-thread forward match length from the window, at most 258 bytes
+__device__ __forceinline__ int fwd_upto_w(const uint8_t* win, int oj, int op)
+{
+    int fwd = 0;
+    while (fwd < kMaxMatch) {
+        const unsigned x = ld4(win, oj + fwd) ^ ld4(win, op + fwd);
+        if (x) { fwd += (__ffs(x) - 1) >> 3; break; }
+        fwd += 4;
+    }
+    return fwd < kMaxMatch ? fwd : kMaxMatch;
+}
+
+// candidate of j (raw distance d) with the never-inserted batch starts removed from the hash chain (encoder.cpp:384: a
+// FirstPass batch never inserts its first position unless a match of the previous batch covers it)
+__device__ int lz_effective_cand(const uint16_t* cand, const LzShared* ps, int j, int d)
+{
+    for (;;) {
+        if (d == 0) return 0;
+        const int p = j - d;
+        bool hit = false;
+        for (int k = 0; k < ps->nexcl; ++k) hit |= (ps->excl[k] == p);
+        if (!hit) return d;
+        const int dd = p > 0 ? (int)__ldg(cand + p) : 0;
+        if (dd == 0) return 0;
+        d += dd;
+        if (d >= kMaxDistance) return 0;
+    }
+}
+
+// candidate distance of j as the parse sees it
+__device__ __forceinline__ int lz_cand(const uint16_t* cand, const LzShared* ps, int npatch, int j)
+{
+    int d = __ldg(cand + j);
+    if (npatch) for (int k = 0; k < npatch; ++k) if (ps->patchJ[k] == j) d = ps->patchD[k];
+    return d;
+}
+
+// the arrays of a sub-batch
+struct LzSub {
+    const uint8_t* info; const unsigned* okbits; const uint16_t* nzw;
+    int ntiles, base, B0, s1;
+};
+
+// succ(b): 0 = no position of the sub-batch is taken from b any more, 1 = the match must be measured exactly, else the next state
+__device__ __forceinline__ unsigned lz_succ(const LzSub& s, int b, int& j)
+{
+    j = -1;
+    if ((unsigned)(b - s.B0) >= (unsigned)(s.s1 - s.B0)) return 0u;
+    j = probe_next(s.info, s.okbits, s.nzw, s.ntiles, s.base, b);
+    if (j < 0) return 0u;
+    const int fwd = (int)s.info[j - s.base] - 1;
+    return needs_exact(fwd, j - b) ? 1u : (unsigned)(j + fwd);
+}
+
+// exact match taken at position j (candidate distance d) from state x, all lanes of the warp cooperate: returns the next state
+__device__ __forceinline__ int lz_exact(const uint8_t* win, int wb, int pre, int x, int j, int d, int lane, int& fwdOut, int& lbOut)
+{
+    const int p = j - d;
+    int maxBack = j - x;
+    { const int room = p + pre; if (room < maxBack) maxBack = room; }     // R4: clamp at stream start
+    if (maxBack > kMaxMatch) maxBack = kMaxMatch;                          // R6: cap (reference breaks at 259)
+    int fwd, lb;
+    coop_lengths_w(win, wb + j, wb + p, lane, maxBack > 0, fwd, lb);
+    if (lb > maxBack) lb = maxBack;
+    int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
+    fwdOut = fwd; lbOut = lb;
+    return j - lb + m;
+}
+
+__device__ __forceinline__ unsigned lz_lookup(const unsigned* exList, int exN, int x)
+{
+    unsigned nb = 0;
+    if (exN > kExCap) exN = kExCap;
+    for (int q = 0; q < exN; ++q) { const unsigned e = exList[q]; if ((int)(e >> 16) == x) nb = e & 0xFFFFu; }
+    return nb;
+}
+
+__global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int useSpec)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t* win = smem;
+    uint8_t* info = win + kLzWin;
+    uint8_t* scratch = info + kSub + 64;
+    unsigned* okbits = reinterpret_cast<unsigned*>(scratch);
+    unsigned* Sb = okbits + kSubWords;               // states visited by the speculative chains
+    unsigned* Tb = Sb + kSubWords;                   // states of the orbit
+    unsigned* Lb = Tb + kSubWords;                   // states visited by the links between chains
+    uint16_t* nzw = reinterpret_cast<uint16_t*>(Lb + kSubWords);
+    uint16_t* stateList = nzw + 272;
+    __shared__ LzShared ps;
+    __shared__ unsigned wsum[32];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ unsigned exList[kExCap];              // state << 16 | exact next state
+    __shared__ unsigned stopKS[kChains];             // kind << 16 | last state of the chain
+    __shared__ uint16_t stopT[kChains];              // where the chain left its segment (kind 3)
+    __shared__ uint16_t linkArr[kChains];            // state where the link joined the chain, 0xFFFF = it did not
+    __shared__ uint16_t segMp[kChains];              // first state of the chain that belongs to the orbit, 0xFFFF = none
+    __shared__ unsigned k3Mask[kChaseWarps], lkMask[kChaseWarps], linkedW[kChaseWarps];
+    __shared__ unsigned grpMin[kSubWords / 32 + 2];
+
+    const unsigned slot = blockIdx.x;
+    const Geom g = chunk_geom(job, slot);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const uint8_t* chunk0 = job.src + g.off;
+    const Stream strm = { job.src - job.history, job.src + job.n };
+    const uint16_t* cand = job.cand + (size_t)slot * job.chunk;
+    uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
+    uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
+    const int phase = (int)(reinterpret_cast<uintptr_t>(chunk0) & 15);
+
+    if (tid == 0) {
+        ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npatch = 0; ps.npend = 0; ps.exN = 0; ps.err = 0;
+        mbar_init(&mbar, 1);
+    }
+    __syncthreads();
+    unsigned parity = 0;
+#ifdef ZZ_PHASE_TIMING
+    long long tPhase = clock64();
+#endif
+
+    const int t0 = g.t0;
+    // ---- batches of the reference's WriteBlock2Pass loop (encoder.cpp:225-234) ----
+    for (;;) {
+        const int pos = ps.pos;
+        if (pos >= t0) break;
+        int E = pos + kBatch; if (E > t0) E = t0;
+        const int B0 = pos + 1;                          // FirstPass: backRefEnd = j = startPos + 1
+        // ---- window of the batch: position i lives at win[wb + i]; shared and global 16-byte phases agree ----
+        const int off0 = B0 - kLzBack;
+        const int wb = 16 + ((phase + off0) & 15) - off0;
+        int lo = off0; if (lo < -g.pre) lo = -g.pre;
+        int hi = E + kLzAhead - 16; if (hi > g.n) hi = g.n;
+        bool tmaIssued = false;
+        {
+            const int s_lo = wb + lo, s_hi = wb + hi;
+            const int a_lo = (s_lo + 15) & ~15, a_hi = s_hi & ~15;
+            tmaIssued = useTma && a_lo < a_hi;
+            if (tmaIssued) {
+                if (tid == 0) {
+                    // the window was read through the generic proxy by the previous batch: order those accesses before
+                    // the asynchronous writes
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const unsigned bytes = (unsigned)(a_hi - a_lo);
+                    mbar_expect_tx(&mbar, bytes);
+                    const uint8_t* gsrc = chunk0 + (a_lo - wb);
+                    for (unsigned o = 0; o < bytes; o += 16384u) {
+                        const unsigned len = bytes - o < 16384u ? bytes - o : 16384u;
+                        bulk_g2s(win + a_lo + o, gsrc + o, len, &mbar);
+                    }
+                }
+                for (int s = s_lo + tid; s < a_lo; s += kLzThreads) win[s] = chunk0[s - wb];
+                for (int s = a_hi + tid; s < s_hi; s += kLzThreads) win[s] = chunk0[s - wb];
+                for (int s = s_hi + tid; s < s_hi + 16; s += kLzThreads) win[s] = 0;
+            } else {
+                load_window(win, wb, chunk0, lo, hi, hi + 16);
+            }
+        }
+        if (tmaIssued) {
+            unsigned spins = 0;
+            while (!mbar_try_wait(&mbar, parity)) { if (++spins > (1u << 18)) { ps.err = 1; break; } }
+            parity ^= 1u;
+        }
+        __syncthreads();
+        PHASE_MARK(0);
+        const int nexcl = ps.nexcl;
+        const int ex0 = nexcl > 0 ? ps.excl[0] : -1, ex1 = nexcl > 1 ? ps.excl[1] : -1, ex2 = nexcl > 2 ? ps.excl[2] : -1;
+
+        // ---- first probe of the batch: j == backRefEnd, no backward room (encoder.cpp:384-386) ----
+        if (warp == 0) {
+            int b = B0;
+            if (B0 < E) {
+                const int d = lz_effective_cand(cand, &ps, B0, (int)__ldg(cand + B0));     // the excluded start may be B0's own candidate
+                const int inf = info_of_w(win, wb + B0, d, B0 - d + g.pre);
+                if (inf >= 5) {
+                    int fwd = inf - 1, lbNone;
+                    if (fwd >= kCapLen) coop_lengths_w(win, wb + B0, wb + B0 - d, lane, false, fwd, lbNone);
+                    const int tk = ps.ntok;
+                    if (lane == 0) { tokA[tk] = (uint32_t)B0 | ((uint32_t)fwd << 16); tokD[tk] = (uint16_t)d; ps.ntok = tk + 1; }
+                    b = B0 + fwd;
+                }
+            }
+            if (lane == 0) ps.b = b;
+        }
+        __syncthreads();
+        PHASE_MARK(1);
+
+        // ---- sub-batches ----
+        for (int s0 = B0; s0 < E; ) {
+            const int bIn = ps.b;
+            {
+                int s1n = s0 + kSub; if (s1n > E) s1n = E;
+                if (bIn >= s1n) { s0 = s1n; continue; }            // a long match jumped over the whole sub-batch
+            }
+            int lowb = bIn > s0 - 64 ? bIn : s0 - 64; if (lowb > s0) lowb = s0;
+            const int base = lowb & ~31;
+            int s1 = base + kSub; if (s1 > E) s1 = E;               // the arrays hold kSub states from the tile-aligned base
+            const int ntiles = (s1 - base + 31) >> 5;
+            const int lim = ntiles * 32;
+
+            // ---- A: match info of the positions [s0, s1); everything else in the array reads as "no match" ----
+            {
+                unsigned* queue = reinterpret_cast<unsigned*>(scratch) + warp * kLzQueue;
+                int queued = 0;
+                const unsigned* w32 = reinterpret_cast<const unsigned*>(win);
+                const int iters = (lim + 4 * kLzThreads - 1) / (4 * kLzThreads);
+                uint2 ddNext = make_uint2(0u, 0u);
+                {
+                    const int j0 = base + 4 * tid;
+                    if (j0 + 3 >= s0 && j0 < s1) ddNext = __ldg(reinterpret_cast<const uint2*>(cand + j0));
+                }
+                for (int it = 0; it < iters; ++it) {
+                    const int idx = 4 * tid + it * 4 * kLzThreads;
+                    const int j0 = base + idx;
+                    const bool inArr = idx < lim;
+                    const bool live = inArr && j0 + 3 >= s0 && j0 < s1;
+                    const uint2 dd = ddNext;
+                    ddNext = make_uint2(0u, 0u);
+                    {
+                        const int jn = j0 + 4 * kLzThreads;
+                        if (idx + 4 * kLzThreads < lim && jn + 3 >= s0 && jn < s1) ddNext = __ldg(reinterpret_cast<const uint2*>(cand + jn));
+                    }
+                    int d[4] = { (int)(dd.x & 0xFFFFu), (int)(dd.x >> 16), (int)(dd.y & 0xFFFFu), (int)(dd.y >> 16) };
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (!live || j0 + k < s0 || j0 + k >= s1) d[k] = 0;
+                    if (nexcl) {
+                        // a position whose candidate is a never-inserted batch start must look one entry further down the chain:
+                        // noted here, recomputed after the pass (at most three such positions per chunk)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int p = j0 + k - d[k];
+                            if (d[k] != 0 && (p == ex0 || p == ex1 || p == ex2)) { const int q = atomicAdd(&ps.npend, 1); if (q < 8) ps.pendJ[q] = j0 + k; }
+                        }
+                    }
+                    const int oj0 = wb + (live ? j0 : s0);
+                    const unsigned* wj = w32 + (oj0 >> 2);
+                    unsigned packed = 0, longMask = 0;
+                    int op[4] = { 0, 0, 0, 0 };
+                    if (live) {
+                        const unsigned W0 = wj[-1], W1 = wj[0], W2 = wj[1], W3 = wj[2];
+                        const int ph = (oj0 & 3) * 8;
+                        const unsigned V0 = __funnelshift_r(W0, W1, ph), V1 = __funnelshift_r(W1, W2, ph), V2 = __funnelshift_r(W2, W3, ph);
+                        unsigned pw0[4], pw1[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            op[k] = oj0 + k - d[k];
+                            const unsigned* wp = w32 + (op[k] >> 2);
+                            pw0[k] = wp[0]; pw1[k] = wp[1];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const unsigned x = __funnelshift_r(V1, V2, 8 * k) ^ __funnelshift_r(pw0[k], pw1[k], op[k] * 8);
+                            if (d[k] != 0) {
+                                if (x == 0) longMask |= 1u << k;         // >= 4 bytes forwards: usable whatever lies behind; length from the queue
+                                else {
+                                    const int fwd = (__ffs(x) - 1) >> 3;
+                                    const unsigned y = __funnelshift_r(V0, V1, 8 * k) ^ __funnelshift_r(w32[(op[k] >> 2) - 1], pw0[k], op[k] * 8);
+                                    int back = y ? (__clz(y) >> 3) : 4;
+                                    const int room = j0 + k - d[k] + g.pre;   // bytes of real history before the candidate (R4 clamp)
+                                    if (back > room) back = room;
+                                    if (fwd + back >= 4) packed |= (unsigned)(fwd + 1) << (8 * k);
+                                }
+                            }
+                        }
+                    }
+                    // queued bytes are stored as 0 here and overwritten when the queue is drained: the drain comes after a
+                    // __syncwarp(), which orders the two stores of the warp
+                    if (inArr) *reinterpret_cast<unsigned*>(info + idx) = packed;
+                    {   // append: a lane queues 0..4 positions; its slot = positions queued by lower lanes (three votes on the count's bits)
+                        const unsigned cnt = (unsigned)__popc(longMask);
+                        const unsigned b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u), b2 = __ballot_sync(0xffffffffu, cnt & 4u);
+                        int slotq = queued + __popc(b0 & ltMask) + 2 * __popc(b1 & ltMask) + 4 * __popc(b2 & ltMask);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if ((longMask >> k) & 1u) queue[slotq++] = (unsigned)(oj0 + k) | ((unsigned)op[k] << 16);
+                        queued += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                    }
+                    __syncwarp();
+                    int head = 0;
+                    while (queued - head >= 32) {
+                        const unsigned e = queue[head + lane]; const int oj = (int)(e & 0xFFFFu), opq = (int)(e >> 16);
+                        info[oj - wb - base] = (uint8_t)(4 + fwd_more(win, oj + 4, opq + 4) + 1);
+                        head += 32;
+                    }
+                    if (head) {                                      // keep the remainder (< 32 entries) at the front
+                        const int rem = queued - head;
+                        unsigned e = 0;
+                        if (lane < rem) e = queue[head + lane];
+                        __syncwarp();
+                        if (lane < rem) queue[lane] = e;
+                        queued = rem;
+                    }
+                    __syncwarp();
+                }
+                if (lane < queued) {
+                    const unsigned e = queue[lane];
+                    const int oj = (int)(e & 0xFFFFu), opq = (int)(e >> 16);
+                    info[oj - wb - base] = (uint8_t)(4 + fwd_more(win, oj + 4, opq + 4) + 1);
+                }
+                if (tid < 16) *reinterpret_cast<unsigned*>(info + lim + 4 * tid) = 0u;      // look-ahead of the last states
+            }
+            __syncthreads();
+            PHASE_MARK(2);
+            // the queues are drained: their space now holds the bitmaps, nzw and the state list
+            for (int t = tid; t < kSubWords; t += kLzThreads) { Sb[t] = 0; Tb[t] = 0; Lb[t] = 0; }
+            if (tid < kChains) segMp[tid] = 0xFFFFu;
+            if (tid < kChaseWarps) linkedW[tid] = 0;
+            if (tid < ps.npend && tid < 8) {                      // positions whose candidate changes with the parse
+                const int pj = ps.pendJ[tid];
+                const int pd = lz_effective_cand(cand, &ps, pj, (int)__ldg(cand + pj));
+                const int q = atomicAdd(&ps.npatch, 1);
+                if (q < 4) { ps.patchJ[q] = pj; ps.patchD[q] = pd; }
+                info[pj - base] = (uint8_t)info_of_w(win, wb + pj, pd, pj - pd + g.pre);
+            }
+            __syncthreads();
+            if (tid == 0) { ps.npend = 0; ps.exN = 0; if (ps.npatch > 4) { ps.npatch = 4; ps.err = 1; } }
+            for (int idx = tid; idx < lim + 64; idx += kLzThreads) {
+                const unsigned m4 = __ballot_sync(0xffffffffu, info[idx] != 0);
+                if (lane == 0) okbits[idx >> 5] = m4;
+            }
+            __syncthreads();
+            {   // nzw[w] = next non-empty bitmap word at or after w (suffix minimum: within groups of 32 words by shuffles, then across)
+                const int w = tid;
+                unsigned v = (w < ntiles && okbits[w] != 0) ? (unsigned)w : kNone16;
+                if (w < kSubWords + 27) {
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_down_sync(0xffffffffu, v, o); if (lane + o < 32 && u < v) v = u; }
+                    if (lane == 0) grpMin[warp] = v;
+                }
+                __syncthreads();
+                if (w <= ntiles) {
+                    if (v == kNone16) for (int gq = warp + 1; gq <= (ntiles >> 5) && v == kNone16; ++gq) v = grpMin[gq];
+                    nzw[w] = (uint16_t)v;
+                }
+            }
+            __syncthreads();
+            const int npatch = ps.npatch;
+            PHASE_MARK(3);
+            PHASE_MARK(4);
+
+            // ---- C: the orbit of succ from the entry state ----
+            if (warp < kChaseWarps) {
+                const LzSub sub = { info, okbits, nzw, ntiles, base, B0, s1 };
+                // speculative chains: lane i follows succ from the first state of its segment and marks what it visits
+                const int ci = tid;
+                const int segLo = base + kSegStates * ci;
+                const int segHi = ci == kChains - 1 ? base + lim : segLo + kSegStates;
+                int kind = 0, state = 0, tgt = 0;                   // 1: succ == 0, 2: long match, 3: left the segment (tgt = next state)
+                {
+                    int x = segLo;
+                    bool go = useSpec && segLo < s1;
+                    bool givenUp = false;
+                    for (;;) {
+                        if (go) {
+                            for (;;) {
+                                atomicOr(&Sb[(x - base) >> 5], 1u << (x & 31));
+                                int j;
+                                const unsigned f = lz_succ(sub, x, j);
+                                if (f == 0u) { kind = 1; state = x; break; }
+                                if (f == 1u) { kind = 2; state = x; break; }
+                                if ((int)f >= segHi || (int)f >= s1) { kind = 3; state = x; tgt = (int)f; break; }
+                                x = (int)f;
+                            }
+                            go = false;
+                        }
+                        // long matches that stopped chains: measured here while they are few (text), left to the true walk otherwise
+                        unsigned brk = __ballot_sync(0xffffffffu, kind == 2 && !givenUp);
+                        if (!brk) break;
+                        if (__popc(brk) > 8) { givenUp = true; break; }
+                        int myJ = 0, myD = 0;
+                        if ((brk >> lane) & 1u) { myJ = probe_next(info, okbits, nzw, ntiles, base, state); myD = lz_cand(cand, &ps, npatch, myJ); }
+                        while (brk) {
+                            const int L = __ffs(brk) - 1; brk &= brk - 1;
+                            const int xs = __shfl_sync(0xffffffffu, state, L), js = __shfl_sync(0xffffffffu, myJ, L), ds = __shfl_sync(0xffffffffu, myD, L);
+                            int fw, lb;
+                            const int nb = lz_exact(win, wb, g.pre, xs, js, ds, lane, fw, lb);
+                            if (lane == L) {
+                                const int q = atomicAdd(&ps.exN, 1);
+                                if (q < kExCap) exList[q] = ((unsigned)xs << 16) | (unsigned)(nb < 65535 ? nb : 65535);
+                                if (nb >= segHi || nb >= s1) { kind = 3; tgt = nb; }
+                                else { kind = 0; x = nb; go = true; }
+                            }
+                        }
+                    }
+                }
+                PHASE_MARK(9);
+                stopKS[ci] = ((unsigned)kind << 16) | (unsigned)state;
+                stopT[ci] = (uint16_t)(tgt < 65535 ? tgt : 65535);
+                chase_barrier();
+                PHASE_MARK(10);
+                // links: lane i follows succ from the state where lane i-1's chain entered segment i until it steps on its own
+                // chain.  If lane i-1's chain turns out to be the orbit, so is lane i's from that state on.
+                int linkMp = -1;
+                if (ci > 0 && kind != 0) {
+                    const unsigned pks = stopKS[ci - 1];
+                    const int pt = stopT[ci - 1];
+                    if ((pks >> 16) == 3u && pt >= segLo && pt < segHi && pt < s1) {
+                        const int exN = ps.exN;
+                        int x = pt;
+                        for (;;) {
+                            if ((Sb[(x - base) >> 5] >> (x & 31)) & 1u) { linkMp = x; break; }
+                            atomicOr(&Lb[(x - base) >> 5], 1u << (x & 31));
+                            int j;
+                            unsigned f = lz_succ(sub, x, j);
+                            if (f == 1u) f = lz_lookup(exList, exN, x);
+                            if (f == 0u || (int)f >= segHi || (int)f >= s1) break;
+                            x = (int)f;
+                        }
+                    }
+                }
+                PHASE_MARK(11);
+                linkArr[ci] = (uint16_t)(linkMp >= 0 ? linkMp : 0xFFFF);
+                {
+                    const unsigned m1 = __ballot_sync(0xffffffffu, kind == 3), m2 = __ballot_sync(0xffffffffu, linkMp >= 0);
+                    if (lane == 0) { k3Mask[warp] = m1; lkMask[warp] = m2; }
+                }
+                chase_barrier();
+                PHASE_MARK(12);
+                if (warp == 0) {
+                    int cur = bIn, npre = 0;
+                    const int tokBase = ps.ntok;
+                    bool alive = true;
+                    if (cur < base) {
+                        // entry state far behind the arrays: every usable position of the sub-batch is far enough, the first one is taken
+                        const unsigned w0 = nzw[0];
+                        if (w0 == kNone16) alive = false;                 // nothing to take: the state stays
+                        else {
+                            const int j = base + (int)w0 * 32 + __ffs(okbits[w0]) - 1;
+                            const int d = lz_cand(cand, &ps, npatch, j);
+                            int fw, lb;
+                            const int nb = lz_exact(win, wb, g.pre, cur, j, d, lane, fw, lb);
+                            int m = fw + lb; if (m > kMaxMatch) m = kMaxMatch;
+                            if (lane == 0) { tokA[tokBase] = (uint32_t)(j - lb) | ((uint32_t)m << 16); tokD[tokBase] = (uint16_t)d; }
+                            npre = 1;
+                            cur = nb;
+                        }
+                    }
+                    int endsAt = -1;                                       // orbit state with succ == 0 that ended the walk (it yields no token)
+                    if (alive && cur < s1) {
+                        // bit t of okRun: segment t is entered through its link provided segment t-1's chain is the orbit and leaves into it
+                        static_assert(kChaseWarps == 4, "okRun is kept as two 64-bit words");
+                        const unsigned long long k3lo = k3Mask[0] | ((unsigned long long)k3Mask[1] << 32), k3hi = k3Mask[2] | ((unsigned long long)k3Mask[3] << 32);
+                        const unsigned long long lklo = lkMask[0] | ((unsigned long long)lkMask[1] << 32), lkhi = lkMask[2] | ((unsigned long long)lkMask[3] << 32);
+                        const unsigned long long okLo = (k3lo << 1) & lklo, okHi = ((k3hi << 1) | (k3lo >> 63)) & lkhi;
+                        for (;;) {
+                            if (cur >= s1) break;
+                            const int r = cur - base;
+                            int j;
+                            const unsigned f0 = lz_succ(sub, cur, j);
+                            const bool marked = (Sb[r >> 5] >> (r & 31)) & 1u;
+                            int x = cur;
+                            bool joined = false;
+                            if (marked) {
+                                int i = r / kSegStates; if (i > kChains - 1) i = kChains - 1;
+                                const unsigned iKS = stopKS[i];
+                                if ((iKS >> 16) != 0u && segMp[i] == 0xFFFFu) {
+                                    // the walk stepped on chain i: the chain is the orbit from here on, and so are the chains of the
+                                    // following segments as long as each one's link joined it
+                                    joined = true;
+                                    // run of ones in okRun from bit i+1 on
+                                    int last = i;
+                                    if (i + 1 < kChains) {
+                                        const int t = i + 1;                          // 1 <= t <= 127
+                                        const unsigned long long v0 = t < 64 ? ((okLo >> t) | (okHi << (64 - t))) : (okHi >> (t - 64));
+                                        const unsigned long long v1 = t < 64 ? (okHi >> t) : 0ull;
+                                        const int run = ~v0 ? __ffsll((long long)~v0) - 1 : 64 + __ffsll((long long)~v1) - 1;
+                                        last = i + run;
+                                    }
+                                    if (lane == 0) segMp[i] = (uint16_t)cur;
+                                    for (int t = i + 1 + lane; t <= last; t += 32) { segMp[t] = linkArr[t]; atomicOr(&linkedW[t >> 5], 1u << (t & 31)); }
+                                    __syncwarp();
+                                    const unsigned lKS = stopKS[last];
+                                    const int lKind = (int)(lKS >> 16), lState = (int)(lKS & 0xFFFFu), lTgt = stopT[last];
+                                    if (lKind == 1) { endsAt = lState; cur = lState; break; }
+                                    if (lKind == 3) { cur = lTgt; continue; }
+                                    x = lState;                            // long match at the end of the chain: measured below
+                                    j = probe_next(info, okbits, nzw, ntiles, base, x);
+                                }
+                            }
+                            if (!joined) {
+                                if (lane == 0) atomicOr(&Tb[r >> 5], 1u << (r & 31));
+                                if (f0 == 0u) { endsAt = x; break; }
+                                if (f0 != 1u) { cur = (int)f0; continue; }
+                            }
+                            // long match at state x (taken at position j): exact lengths, unless a chain has measured it already
+                            {
+                                const unsigned known = __shfl_sync(0xffffffffu, lz_lookup(exList, ps.exN, x), 0);     // lane 0's view: uniform
+                                if (known) { cur = (int)known; continue; }
+                            }
+                            const int d = lz_cand(cand, &ps, npatch, j);
+                            int fwd, lb;
+                            int nb = lz_exact(win, wb, g.pre, x, j, d, lane, fwd, lb);
+                            int exBase = 0;
+                            if (lane == 0) { exBase = atomicAdd(&ps.exN, 1); if (exBase < kExCap) exList[exBase] = ((unsigned)x << 16) | (unsigned)(nb < 65535 ? nb : 65535); }
+                            // Runs (RLE-like data): a full-length match whose successor states repeat it 258 bytes further on.  The
+                            // equality between the two sides is measured once beyond the first 258 bytes (R, as far as 32 more matches
+                            // can use it and the window reaches) and lane i-1 checks that state x + 258 i is an unmeasured long state
+                            // whose probe position has the same gap and the same distance.  For those states fwd_i = min(258, R - 258 i)
+                            // and the backward part is the gap again (its bytes lie inside [j, j + R)), so match i is
+                            // (start x_i, length 258) exactly as the walk would find it, as long as R - 258 i >= 258 - gap.
+                            const int gap = j - x;
+                            const int p = j - d;
+                            if (fwd == kMaxMatch && lb == gap && nb + 1 < s1) {
+                                const int xi = x + kMaxMatch * (lane + 1);
+                                bool ok = xi < s1;
+                                int ji = -1;
+                                if (ok) ok = lz_succ(sub, xi, ji) == 1u;
+                                if (ok) ok = ji == xi + gap;
+                                if (ok) ok = lz_cand(cand, &ps, npatch, xi + gap) == d;
+                                const unsigned okm = __ballot_sync(0xffffffffu, ok);
+                                int K = okm == 0xffffffffu ? 32 : __ffs(~okm) - 1;            // candidates of the run
+                                if (K > 0) {
+                                    // R: equal bytes between the two sides from j on, measured only as far as K matches need it
+                                    int Rcap = kMaxMatch * (K + 1) - gap;
+                                    { const int limB = g.body - j; if (limB < Rcap) Rcap = limB; }
+                                    { const int limW = hi - 272 - j; if (limW < Rcap) Rcap = limW; }        // what the window holds (a step reads 264 bytes beyond its offset)
+                                    int R = Rcap;
+                                    for (int off = 256; off < Rcap && R == Rcap; off += 1024) {
+                                        unsigned long long xa[4];
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u)
+                                            xa[u] = off + 256 * u < Rcap ? ld8(win, wb + j + off + 256 * u + lane * 8) ^ ld8(win, wb + p + off + 256 * u + lane * 8) : 0ull;
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) {
+                                            const unsigned mm = __ballot_sync(0xffffffffu, xa[u] != 0);
+                                            if (mm && R == Rcap) {
+                                                const int src = __ffs(mm) - 1;
+                                                const unsigned long long xs = __shfl_sync(0xffffffffu, xa[u], src);
+                                                const int rr = off + 256 * u + src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
+                                                if (rr < R) R = rr;
+                                            }
+                                        }
+                                    }
+                                    // match i needs R - 258 i >= 258 - gap
+                                    const int byR = (R - kMaxMatch + gap) / kMaxMatch;
+                                    if (byR < K) K = byR < 0 ? 0 : byR;
+                                    int runBase = 0;
+                                    if (lane == 0 && K > 0) runBase = atomicAdd(&ps.exN, K);
+                                    runBase = __shfl_sync(0xffffffffu, runBase, 0);
+                                    if (lane < K) {
+                                        const int nbi = xi + kMaxMatch;
+                                        if (runBase + lane < kExCap) exList[runBase + lane] = ((unsigned)xi << 16) | (unsigned)(nbi < 65535 ? nbi : 65535);
+                                        atomicOr(&Tb[(xi - base) >> 5], 1u << (xi & 31));
+                                    }
+                                    nb = x + kMaxMatch * (K + 1);
+                                    __syncwarp();
+                                }
+                            }
+                            cur = nb;
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0) { ps.b = cur; ps.npre = npre; ps.endsAt = endsAt; }
+                    PHASE_MARK(13);
+                }
+            }
+            __syncthreads();
+
+            PHASE_MARK(5);
+            // ---- D: the orbit's states, compacted, then expanded to tokens in parallel ----
+            {
+                // states of the orbit in this thread's 32-state word: what the true walk marked, plus every joined chain from the
+                // state where the orbit joined it, plus the link that led there
+                unsigned word = 0;
+                if (tid < ntiles) {
+                    word = Tb[tid];
+                    int t = (tid * 32) / kSegStates; if (t > kChains - 1) t = kChains - 1;
+                    const unsigned mp = segMp[t];
+                    if (mp != 0xFFFFu) {
+                        const int wm = ((int)mp - base) >> 5;
+                        if (tid > wm) word |= Sb[tid];
+                        else if (tid == wm) word |= Sb[tid] & (0xffffffffu << (mp & 31u));
+                        if (tid <= wm && ((linkedW[t >> 5] >> (t & 31)) & 1u)) word |= Lb[tid];
+                    }
+                    const int endsAt = ps.endsAt;
+                    if (endsAt >= 0 && ((endsAt - base) >> 5) == tid) word &= ~(1u << (endsAt & 31));
+                }
+                const unsigned cnt = (unsigned)__popc(word);
+                unsigned inc = cnt;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                if (lane == 31) wsum[warp] = inc;
+                __syncthreads();
+                if (warp == 0) {
+                    unsigned v = lane < kLzWarps ? wsum[lane] : 0u;
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+                    wsum[lane] = v;
+                }
+                __syncthreads();
+                int out = (int)((warp ? wsum[warp - 1] : 0u) + inc - cnt);
+                unsigned wbits = word;
+                while (wbits) {
+                    const int bit = __ffs(wbits) - 1; wbits &= wbits - 1;
+                    stateList[out++] = (uint16_t)(base + tid * 32 + bit);
+                }
+                __syncthreads();
+                const int nbt = (int)wsum[31];
+                const int outBase = ps.ntok + ps.npre;
+                for (int t = tid; t < nbt; t += kLzThreads) {
+                    const int x = stateList[t];
+                    const int j = probe_next(info, okbits, nzw, ntiles, base, x);
+                    const int d = lz_cand(cand, &ps, npatch, j);
+                    int fwd = (int)info[j - base] - 1;
+                    int limit = j - x;                                     // pending literals (encoder.cpp:404)
+                    { const int room = j - d + g.pre; if (room < limit) limit = room; }
+                    if (limit > kMaxMatch) limit = kMaxMatch;
+                    const int lb = back_upto_w(win, wb + j, wb + j - d, limit);
+                    if (fwd >= kCapLen) fwd = fwd_upto_w(win, wb + j, wb + j - d);      // the compare of phase A stopped at 32 bytes
+                    int m = fwd + lb;
+                    if (m > kMaxMatch) m = kMaxMatch;
+                    tokA[outBase + t] = (uint32_t)(j - lb) | ((uint32_t)m << 16);
+                    tokD[outBase + t] = (uint16_t)d;
+                }
+                __syncthreads();
+                if (tid == 0) ps.ntok = outBase + nbt;
+            }
+            __syncthreads();
+            PHASE_MARK(6);
+            s0 = s1;
+        }
+        if (tid == 0) {
+            const int finalB = ps.b;
+            const int newpos = finalB > E ? finalB : E;
+            if (finalB < E && newpos < t0 && ps.nexcl < 4) ps.excl[ps.nexcl++] = newpos;     // next batch start not covered by a match: never inserted
+            ps.pos = newpos;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0 && ps.err) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 8ull);
+    PHASE_MARK(7);
+
+    // ---- histograms (GetFrequencies, encoder.cpp:442-471) ----
+    // Matches are counted token-parallel and mark the positions they cover in a bitmap; literals are then counted
+    // position-parallel (coalesced reads) into per-warp private histograms.  The batch arrays are dead: the space is reused.
+    unsigned* hist = reinterpret_cast<unsigned*>(smem);            // per-warp private copies
+    unsigned* cov = hist + kLzWarps * kHistStride;                 // bit per position: covered by a match
+    unsigned* litBase = cov + kMaxChunk / 32;                      // literals before each 32-position word
+    uint8_t* lits = job.info + (size_t)slot * job.chunk;           // the block's literal bytes in order
+    for (int i = tid; i < kLzWarps * kHistStride + kMaxChunk / 32; i += kLzThreads) hist[i] = 0;
+    __syncthreads();
+    {
+        const int ntok = ps.ntok;
+        unsigned* myh = hist + warp * kHistStride;
+        for (int k = tid; k < ntok; k += kLzThreads) {
+            const uint32_t t = tokA[k];
+            const int ms = (int)(t & 0xFFFF), ln = (int)(t >> 16), me = ms + ln - 1;
+            int eb, ev;
+            atomicAdd(&myh[len_symbol(ln, eb, ev)], 1u);
+            atomicAdd(&myh[286 + dist_symbol(tokD[k], eb, ev)], 1u);
+            for (int w = ms >> 5; w <= (me >> 5); ++w) {
+                unsigned m = 0xffffffffu;
+                if (w == (ms >> 5)) m &= 0xffffffffu << (ms & 31);
+                if (w == (me >> 5)) m &= 0xffffffffu >> (31 - (me & 31));
+                atomicOr(&cov[w], m);
+            }
+        }
+        __syncthreads();
+        // positions at or beyond the block's end are not literals
+        for (int w = tid; w < kMaxChunk / 32; w += kLzThreads) {
+            const int lo = w * 32;
+            if (lo + 32 > g.body) cov[w] |= lo >= g.body ? 0xffffffffu : (0xffffffffu << (g.body - lo));
+        }
+        __syncthreads();
+        {   // exclusive scan of the literal counts per word (four consecutive words per thread)
+            static_assert(kLzThreads * 4 == kMaxChunk / 32, "one pass over the coverage bitmap");
+            const int w0 = tid * 4;
+            unsigned c[4], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { c[k] = (unsigned)__popc(~cov[w0 + k]); sum += c[k]; }
+            unsigned inc = sum;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                unsigned v = lane < kLzWarps ? wsum[lane] : 0u;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+                wsum[lane] = v;
+            }
+            __syncthreads();
+            unsigned before = (warp ? wsum[warp - 1] : 0u) + inc - sum;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { litBase[w0 + k] = before; before += c[k]; }
+            if (tid == kLzThreads - 1) job.state[slot].nlit = before;
+        }
+        __syncthreads();
+        // literals: histogram, and the literal bytes written out in order for K-EMIT (position -> rank through the
+        // coverage bitmap).  A 4-byte aligned chunk reads whole words (a word that holds a valid byte never leaves its page).
+        const bool srcAligned = (reinterpret_cast<uintptr_t>(chunk0) & 3) == 0;
+        for (int pos = tid * 4; pos < g.body; pos += 4 * kLzThreads) {
+            const unsigned cword = cov[pos >> 5];
+            const unsigned cw = (cword >> (pos & 31)) & 0xFu;
+            if (cw == 0xFu) continue;                                   // four covered positions: nothing to count
+            const unsigned v = srcAligned ? __ldg(reinterpret_cast<const unsigned*>(chunk0 + pos)) : gload4(chunk0 + pos, strm.lo, strm.hi);
+            unsigned rank = litBase[pos >> 5] + (unsigned)__popc(~cword & ((1u << (pos & 31)) - 1u));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (!((cw >> k) & 1u)) { const unsigned b = (v >> (8 * k)) & 0xFFu; atomicAdd(&myh[b], 1u); lits[rank++] = (uint8_t)b; }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 316; i += kLzThreads) {
+        unsigned s = 0;
+        for (int w = 0; w < kLzWarps; ++w) s += hist[w * kHistStride + i];
+        if (i == 256) s += 1;                                       // end-of-block (encoder.cpp:470)
+        job.hist[(size_t)slot * kHistStride + i] = s;
+    }
+    if (tid == 0) job.state[slot].ntok = ps.ntok;
+    PHASE_MARK(8);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K-HUFF : one warp per chunk.  Tie-breaks follow the libstdc++ heap layout, so the tree build itself is serial
 // (lane 0, everything in shared memory); the loops around it (frequency loads, leaf compaction, sums, canonical
 // codes, copies to global memory) use all lanes.
@@ -2238,9 +3105,9 @@ void dump_phase_cycles()
 {
     unsigned long long h[16];
     cudaMemcpyFromSymbol(h, g_phaseCycles, sizeof h);
-    static const char* names[9] = { "window", "P1 info", "nzw", "P2 F+E1", "P3 E2", "P4 chase", "P4b mark", "P5 tokens", "hist" };
-    unsigned long long tot = 0; for (int i = 0; i < 9; ++i) tot += h[i];
-    for (int i = 0; i < 9; ++i) fprintf(stderr, "phase %-10s %6.2f%%  %llu\n", names[i], 100.0 * h[i] / (tot ? tot : 1), h[i]);
+    static const char* names[14] = { "window", "firstprobe", "A info", "patch+bits", "B succ", "C sync", "D tokens", "batch end", "hist", "C chains", "C bar1", "C links", "C bar2", "C walk" };
+    unsigned long long tot = 0; for (int i = 0; i < 14; ++i) tot += h[i];
+    for (int i = 0; i < 14; ++i) fprintf(stderr, "phase %-10s %6.2f%%  %llu\n", names[i], 100.0 * h[i] / (tot ? tot : 1), h[i]);
 
     memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_phaseCycles, h, sizeof h);
 }
@@ -2253,6 +3120,7 @@ cudaError_t configure_kernels()
     e = cudaFuncSetAttribute(k_huffman_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffLSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_emit2, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmit2Smem); if (e) return e;
     e = cudaFuncSetAttribute(k_info, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfoSmem); if (e) return e;
+    e = cudaFuncSetAttribute(k_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, kLzSmem); if (e) return e;
     static uint32_t tab[4][256];
     uint32_t powL[257], pow1[256];
     for (uint32_t i = 0; i < 256; ++i) {
@@ -2319,10 +3187,25 @@ int launch_offsets(const Job& job, cudaStream_t s)
 }
 
 // A/B switches of kernel variants (zzgpu_set_option); none changes the produced bytes.
+static int g_optLz = 1;          // 1: fused K-LZ, 0: K-INFO + K-MATCH as separate kernels
+static int g_optTma = 1;         // K-LZ window: 1 = cp.async.bulk (TMA) + mbarrier, 0 = LDG.128 -> STS
+static int g_optSpec = 1;        // K-LZ walk: 1 = speculative per-lane chains merged by the true walk, 0 = the true walk alone
 bool set_kernel_option(const char* name, int value)
 {
-    (void)name; (void)value;
+    if (!strcmp(name, "lz")) { g_optLz = value ? 1 : 0; return true; }
+    if (!strcmp(name, "tma")) { g_optTma = value ? 1 : 0; return true; }
+    if (!strcmp(name, "spec")) { g_optSpec = value ? 1 : 0; return true; }
     return false;
+}
+bool use_fused_lz() { return g_optLz != 0; }
+
+int launch_lz(const Job& job, cudaStream_t s)
+{
+#ifdef ZZ_PHASE_TIMING
+    cudaStreamSynchronize(s); dump_phase_cycles();
+#endif
+    k_lz<<<job.nchunks, kLzThreads, kLzSmem, s>>>(job, g_optTma, g_optSpec);
+    return 1;
 }
 
 int launch_emit(const Job& job, cudaStream_t s)

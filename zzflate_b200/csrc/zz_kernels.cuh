@@ -48,7 +48,7 @@ struct Job {
     int want_checksums;       // bit0 adler, bit1 crc
     // scratch, indexed by slot = chunk - first_chunk
     uint16_t* cand;           // [slots][chunk]     candidate distance per position, 0 = none
-    uint8_t* info;            // [slots][chunk]     K-INFO: 0 = unusable, else 1 + min(forward match length, 32)
+    uint8_t* info;            // [slots][chunk]     K-INFO: 0 = unusable, else 1 + min(forward match length, 32); then the literal stream
     uint32_t* tokA;           // [slots][kMaxTokens] start | length << 16
     uint16_t* tokD;           // [slots][kMaxTokens] distance
     uint32_t* hist;           // [slots][kHistStride]
@@ -64,6 +64,8 @@ struct Job {
 int launch_candidates(const Job& job, cudaStream_t s);
 int launch_info(const Job& job, cudaStream_t s);
 int launch_parse(const Job& job, cudaStream_t s);
+int launch_lz(const Job& job, cudaStream_t s);        // K-INFO + K-MATCH fused
+bool use_fused_lz();
 int launch_huffman(const Job& job, cudaStream_t s);
 int launch_offsets(const Job& job, cudaStream_t s);
 int launch_emit(const Job& job, cudaStream_t s);
