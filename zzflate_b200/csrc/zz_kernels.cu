@@ -1165,18 +1165,15 @@ constexpr int kLzQueue = 32 + 128;
 constexpr int kExCap = 256;                               // exactly measured long matches remembered per sub-batch
 constexpr int kLzScratch = kLzWarps * kLzQueue * 4;       // phase A: long-compare queues; afterwards: bitmaps, nzw, state list
 static_assert(4 * kSubWords * 4 + 544 + (kSub / 4 + 40) * 2 <= kLzScratch, "bitmaps + nzw + state list fit the queue space");
-constexpr int kLzSmem = kLzWin + (kSub + 64) + kLzScratch;
-static_assert(3 * (kLzSmem + 4096) <= 228 * 1024, "K-LZ leaves a third of the SM's shared memory to its neighbours");
+constexpr int kLzSmem = kLzWin + (kSub + 64) + (kSub + 64) * 2 + kLzScratch;
+static_assert(2 * (kLzSmem + 2048) <= 200 * 1024, "two K-LZ CTAs per SM, with room left for a neighbour kernel");
 
 struct LzShared {
     int pos;            // start of the next FirstPass batch
     int ntok;
     int nexcl;          // batch starts that were never inserted into the hash table
     int excl[4];
-    int npatch;         // positions whose candidate changes because of an excluded batch start
-    int patchJ[4];
-    int patchD[4];
-    int npend;          // positions found in phase A whose candidate is an excluded batch start
+    int npend;          // positions found in phase A whose candidate is an excluded batch start (never inserted: encoder.cpp:384)
     int pendJ[8];
     int b;              // current state of the walk
     int npre;           // tokens written directly by warp 0 in this sub-batch (first probe / far entry)
@@ -1209,7 +1206,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void chase_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kChaseWarps * 32) : "memory"); }
+// named barrier of the chase warps; the non-aligned form counts arrivals per thread, so it is safe even where the compiler
+// has not reconverged a warp in front of it
+__device__ __forceinline__ void chase_barrier() { __syncwarp(); asm volatile("barrier.sync 1, %0;" ::"n"(kChaseWarps * 32) : "memory"); }
 
 // info of one position from the window (same definition as phase A); oj = window offset of the position
 __device__ int info_of_w(const uint8_t* win, int oj, int d, int room)
@@ -1307,26 +1306,41 @@ __device__ int lz_effective_cand(const uint16_t* cand, const LzShared* ps, int j
     }
 }
 
-// candidate distance of j as the parse sees it
-__device__ __forceinline__ int lz_cand(const uint16_t* cand, const LzShared* ps, int npatch, int j)
-{
-    int d = __ldg(cand + j);
-    if (npatch) for (int k = 0; k < npatch; ++k) if (ps->patchJ[k] == j) d = ps->patchD[k];
-    return d;
-}
-
 // the arrays of a sub-batch
 struct LzSub {
     const uint8_t* info; const unsigned* okbits; const uint16_t* nzw;
     int ntiles, base, B0, s1;
 };
 
+// First position the walk takes from state b, or -1 (same result as probe_next).  The info bytes of b+1..b+3 and the
+// bitmap words from b+4 on are loaded together, so the common cases cost one shared-memory round trip instead of two:
+// this sits on the serial path of the chains.
+__device__ __forceinline__ int lz_probe(const LzSub& s, int b)
+{
+    const int r = b - s.base;
+    const unsigned* iw = reinterpret_cast<const unsigned*>(s.info) + ((r + 1) >> 2);
+    const unsigned a0 = iw[0], a1 = iw[1];
+    const int x = r + 4, w = x >> 5;
+    const unsigned k0 = s.okbits[w], k1 = s.okbits[w + 1];                  // okbits holds ntiles + 2 words
+    const unsigned near3 = (__funnelshift_r(a0, a1, ((r + 1) & 3) * 8) + 0x007E7D7Cu) & 0x00808080u;   // bytes >= 4 / 3 / 2 (info <= 33: no carry)
+    if (near3) return b + 1 + ((__ffs(near3) - 1) >> 3);
+    const unsigned bits = __funnelshift_r(k0, k1, x & 31);                 // positions b+4 .. b+35
+    if (bits) return b + 4 + __ffs(bits) - 1;
+    if (w + 1 >= s.ntiles) return -1;
+    const unsigned rest = k1 & (~0u << (x & 31));                          // the part of word w+1 the funnel shift did not cover
+    if (rest) return s.base + (w + 1) * 32 + __ffs(rest) - 1;
+    if (w + 2 > s.ntiles) return -1;
+    const unsigned w2 = s.nzw[w + 2];
+    if (w2 == kNone16) return -1;
+    return s.base + (int)w2 * 32 + __ffs(s.okbits[w2]) - 1;
+}
+
 // succ(b): 0 = no position of the sub-batch is taken from b any more, 1 = the match must be measured exactly, else the next state
 __device__ __forceinline__ unsigned lz_succ(const LzSub& s, int b, int& j)
 {
     j = -1;
     if ((unsigned)(b - s.B0) >= (unsigned)(s.s1 - s.B0)) return 0u;
-    j = probe_next(s.info, s.okbits, s.nzw, s.ntiles, s.base, b);
+    j = lz_probe(s, b);
     if (j < 0) return 0u;
     const int fwd = (int)s.info[j - s.base] - 1;
     return needs_exact(fwd, j - b) ? 1u : (unsigned)(j + fwd);
@@ -1360,7 +1374,8 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* win = smem;
     uint8_t* info = win + kLzWin;
-    uint8_t* scratch = info + kSub + 64;
+    uint16_t* dist = reinterpret_cast<uint16_t*>(info + kSub + 64);      // candidate distance per position, as the parse sees it
+    uint8_t* scratch = reinterpret_cast<uint8_t*>(dist + kSub + 64);
     unsigned* okbits = reinterpret_cast<unsigned*>(scratch);
     unsigned* Sb = okbits + kSubWords;               // states visited by the speculative chains
     unsigned* Tb = Sb + kSubWords;                   // states of the orbit
@@ -1390,14 +1405,11 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
     const int phase = (int)(reinterpret_cast<uintptr_t>(chunk0) & 15);
 
     if (tid == 0) {
-        ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npatch = 0; ps.npend = 0; ps.exN = 0; ps.err = 0;
+        ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npend = 0; ps.exN = 0; ps.err = 0;
         mbar_init(&mbar, 1);
     }
     __syncthreads();
     unsigned parity = 0;
-#ifdef ZZ_PHASE_TIMING
-    long long tPhase = clock64();
-#endif
 
     const int t0 = g.t0;
     // ---- batches of the reference's WriteBlock2Pass loop (encoder.cpp:225-234) ----
@@ -1442,7 +1454,6 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
             parity ^= 1u;
         }
         __syncthreads();
-        PHASE_MARK(0);
         const int nexcl = ps.nexcl;
         const int ex0 = nexcl > 0 ? ps.excl[0] : -1, ex1 = nexcl > 1 ? ps.excl[1] : -1, ex2 = nexcl > 2 ? ps.excl[2] : -1;
 
@@ -1463,7 +1474,6 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
             if (lane == 0) ps.b = b;
         }
         __syncthreads();
-        PHASE_MARK(1);
 
         // ---- sub-batches ----
         for (int s0 = B0; s0 < E; ) {
@@ -1512,6 +1522,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                             if (d[k] != 0 && (p == ex0 || p == ex1 || p == ex2)) { const int q = atomicAdd(&ps.npend, 1); if (q < 8) ps.pendJ[q] = j0 + k; }
                         }
                     }
+                    if (inArr) *reinterpret_cast<uint2*>(dist + idx) = make_uint2((unsigned)d[0] | ((unsigned)d[1] << 16), (unsigned)d[2] | ((unsigned)d[3] << 16));
                     const int oj0 = wb + (live ? j0 : s0);
                     const unsigned* wj = w32 + (oj0 >> 2);
                     unsigned packed = 0, longMask = 0;
@@ -1580,20 +1591,18 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                 if (tid < 16) *reinterpret_cast<unsigned*>(info + lim + 4 * tid) = 0u;      // look-ahead of the last states
             }
             __syncthreads();
-            PHASE_MARK(2);
             // the queues are drained: their space now holds the bitmaps, nzw and the state list
             for (int t = tid; t < kSubWords; t += kLzThreads) { Sb[t] = 0; Tb[t] = 0; Lb[t] = 0; }
             if (tid < kChains) segMp[tid] = 0xFFFFu;
             if (tid < kChaseWarps) linkedW[tid] = 0;
             if (tid < ps.npend && tid < 8) {                      // positions whose candidate changes with the parse
                 const int pj = ps.pendJ[tid];
-                const int pd = lz_effective_cand(cand, &ps, pj, (int)__ldg(cand + pj));
-                const int q = atomicAdd(&ps.npatch, 1);
-                if (q < 4) { ps.patchJ[q] = pj; ps.patchD[q] = pd; }
+                const int pd = lz_effective_cand(cand, &ps, pj, (int)dist[pj - base]);
+                dist[pj - base] = (uint16_t)pd;
                 info[pj - base] = (uint8_t)info_of_w(win, wb + pj, pd, pj - pd + g.pre);
             }
             __syncthreads();
-            if (tid == 0) { ps.npend = 0; ps.exN = 0; if (ps.npatch > 4) { ps.npatch = 4; ps.err = 1; } }
+            if (tid == 0) { ps.npend = 0; ps.exN = 0; }
             for (int idx = tid; idx < lim + 64; idx += kLzThreads) {
                 const unsigned m4 = __ballot_sync(0xffffffffu, info[idx] != 0);
                 if (lane == 0) okbits[idx >> 5] = m4;
@@ -1614,9 +1623,6 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                 }
             }
             __syncthreads();
-            const int npatch = ps.npatch;
-            PHASE_MARK(3);
-            PHASE_MARK(4);
 
             // ---- C: the orbit of succ from the entry state ----
             if (warp < kChaseWarps) {
@@ -1648,7 +1654,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                         if (!brk) break;
                         if (__popc(brk) > 8) { givenUp = true; break; }
                         int myJ = 0, myD = 0;
-                        if ((brk >> lane) & 1u) { myJ = probe_next(info, okbits, nzw, ntiles, base, state); myD = lz_cand(cand, &ps, npatch, myJ); }
+                        if ((brk >> lane) & 1u) { myJ = lz_probe(sub, state); myD = (int)dist[myJ - base]; }
                         while (brk) {
                             const int L = __ffs(brk) - 1; brk &= brk - 1;
                             const int xs = __shfl_sync(0xffffffffu, state, L), js = __shfl_sync(0xffffffffu, myJ, L), ds = __shfl_sync(0xffffffffu, myD, L);
@@ -1663,11 +1669,9 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                         }
                     }
                 }
-                PHASE_MARK(9);
                 stopKS[ci] = ((unsigned)kind << 16) | (unsigned)state;
                 stopT[ci] = (uint16_t)(tgt < 65535 ? tgt : 65535);
                 chase_barrier();
-                PHASE_MARK(10);
                 // links: lane i follows succ from the state where lane i-1's chain entered segment i until it steps on its own
                 // chain.  If lane i-1's chain turns out to be the orbit, so is lane i's from that state on.
                 int linkMp = -1;
@@ -1688,14 +1692,12 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                         }
                     }
                 }
-                PHASE_MARK(11);
                 linkArr[ci] = (uint16_t)(linkMp >= 0 ? linkMp : 0xFFFF);
                 {
                     const unsigned m1 = __ballot_sync(0xffffffffu, kind == 3), m2 = __ballot_sync(0xffffffffu, linkMp >= 0);
                     if (lane == 0) { k3Mask[warp] = m1; lkMask[warp] = m2; }
                 }
                 chase_barrier();
-                PHASE_MARK(12);
                 if (warp == 0) {
                     int cur = bIn, npre = 0;
                     const int tokBase = ps.ntok;
@@ -1706,7 +1708,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                         if (w0 == kNone16) alive = false;                 // nothing to take: the state stays
                         else {
                             const int j = base + (int)w0 * 32 + __ffs(okbits[w0]) - 1;
-                            const int d = lz_cand(cand, &ps, npatch, j);
+                            const int d = dist[j - base];
                             int fw, lb;
                             const int nb = lz_exact(win, wb, g.pre, cur, j, d, lane, fw, lb);
                             int m = fw + lb; if (m > kMaxMatch) m = kMaxMatch;
@@ -1754,7 +1756,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                                     if (lKind == 1) { endsAt = lState; cur = lState; break; }
                                     if (lKind == 3) { cur = lTgt; continue; }
                                     x = lState;                            // long match at the end of the chain: measured below
-                                    j = probe_next(info, okbits, nzw, ntiles, base, x);
+                                    j = lz_probe(sub, x);
                                 }
                             }
                             if (!joined) {
@@ -1767,7 +1769,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                                 const unsigned known = __shfl_sync(0xffffffffu, lz_lookup(exList, ps.exN, x), 0);     // lane 0's view: uniform
                                 if (known) { cur = (int)known; continue; }
                             }
-                            const int d = lz_cand(cand, &ps, npatch, j);
+                            const int d = dist[j - base];
                             int fwd, lb;
                             int nb = lz_exact(win, wb, g.pre, x, j, d, lane, fwd, lb);
                             int exBase = 0;
@@ -1786,7 +1788,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                                 int ji = -1;
                                 if (ok) ok = lz_succ(sub, xi, ji) == 1u;
                                 if (ok) ok = ji == xi + gap;
-                                if (ok) ok = lz_cand(cand, &ps, npatch, xi + gap) == d;
+                                if (ok) ok = (int)dist[xi + gap - base] == d;
                                 const unsigned okm = __ballot_sync(0xffffffffu, ok);
                                 int K = okm == 0xffffffffu ? 32 : __ffs(~okm) - 1;            // candidates of the run
                                 if (K > 0) {
@@ -1831,12 +1833,10 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                         __syncwarp();
                     }
                     if (lane == 0) { ps.b = cur; ps.npre = npre; ps.endsAt = endsAt; }
-                    PHASE_MARK(13);
-                }
+                    }
             }
             __syncthreads();
 
-            PHASE_MARK(5);
             // ---- D: the orbit's states, compacted, then expanded to tokens in parallel ----
             {
                 // states of the orbit in this thread's 32-state word: what the true walk marked, plus every joined chain from the
@@ -1878,7 +1878,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                 for (int t = tid; t < nbt; t += kLzThreads) {
                     const int x = stateList[t];
                     const int j = probe_next(info, okbits, nzw, ntiles, base, x);
-                    const int d = lz_cand(cand, &ps, npatch, j);
+                    const int d = dist[j - base];
                     int fwd = (int)info[j - base] - 1;
                     int limit = j - x;                                     // pending literals (encoder.cpp:404)
                     { const int room = j - d + g.pre; if (room < limit) limit = room; }
@@ -1894,7 +1894,6 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                 if (tid == 0) ps.ntok = outBase + nbt;
             }
             __syncthreads();
-            PHASE_MARK(6);
             s0 = s1;
         }
         if (tid == 0) {
@@ -1907,7 +1906,6 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
     }
     __syncthreads();
     if (tid == 0 && ps.err) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 8ull);
-    PHASE_MARK(7);
 
     // ---- histograms (GetFrequencies, encoder.cpp:442-471) ----
     // Matches are counted token-parallel and mark the positions they cover in a bitmap; literals are then counted
@@ -1985,7 +1983,6 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
         job.hist[(size_t)slot * kHistStride + i] = s;
     }
     if (tid == 0) job.state[slot].ntok = ps.ntok;
-    PHASE_MARK(8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -3105,9 +3102,9 @@ void dump_phase_cycles()
 {
     unsigned long long h[16];
     cudaMemcpyFromSymbol(h, g_phaseCycles, sizeof h);
-    static const char* names[14] = { "window", "firstprobe", "A info", "patch+bits", "B succ", "C sync", "D tokens", "batch end", "hist", "C chains", "C bar1", "C links", "C bar2", "C walk" };
-    unsigned long long tot = 0; for (int i = 0; i < 14; ++i) tot += h[i];
-    for (int i = 0; i < 14; ++i) fprintf(stderr, "phase %-10s %6.2f%%  %llu\n", names[i], 100.0 * h[i] / (tot ? tot : 1), h[i]);
+    static const char* names[9] = { "window", "firstprobe", "A info", "patch+bits", "B succ", "C walk", "D tokens", "batch end", "hist" };
+    unsigned long long tot = 0; for (int i = 0; i < 9; ++i) tot += h[i];
+    for (int i = 0; i < 9; ++i) fprintf(stderr, "phase %-10s %6.2f%%  %llu\n", names[i], 100.0 * h[i] / (tot ? tot : 1), h[i]);
 
     memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_phaseCycles, h, sizeof h);
 }
@@ -3201,9 +3198,6 @@ bool use_fused_lz() { return g_optLz != 0; }
 
 int launch_lz(const Job& job, cudaStream_t s)
 {
-#ifdef ZZ_PHASE_TIMING
-    cudaStreamSynchronize(s); dump_phase_cycles();
-#endif
     k_lz<<<job.nchunks, kLzThreads, kLzSmem, s>>>(job, g_optTma, g_optSpec);
     return 1;
 }
