@@ -362,23 +362,36 @@ def test_host_buffers_pipelined_path(zz, oracle):
     out, a0, crc, st = zz.deflate_raw(data, level=2)
     assert out == want[2:-4]
     assert zz.combine(1, a0, n) == zlib.adler32(data) and crc == zlib.crc32(data)
-    assert lib.zzgpu_set_option(b"no-such-option", 1) == _lib.E_ARG
     g1 = zz.ZzFlateEncode(data[: 40 << 20], zz.Config(zz.Format.Gzip, 1, False))
     assert zlib.decompress(g1, 31) == data[: 40 << 20].tobytes()
 
 
 def test_kernel_variants_give_the_same_bytes(zz, oracle, golden):
     """K-HUFF has two variants (warp per chunk for launches of one wave, thread per chunk for full batches, picked by
-    launch size): both must give the oracle's bytes."""
-    from zzflate_b200 import synth
+    launch size) and K-LZ two A/B switches (window by TMA bulk copy or by LDG/STS; speculative chains or the true walk
+    alone): every combination must give the oracle's bytes."""
+    from zzflate_b200 import synth, _lib
+    lib = _lib.load()
     small = golden.input("mixed")                                # a few chunks: warp-per-chunk K-HUFF
     n = 8000 * S + 777                                           # > 148 * 52 chunks: thread-per-chunk K-HUFF
     big = synth.markov_text(n, seg0=3)
     big[5 * S: 6 * S] = synth.random_bytes(S)                    # a stored chunk, a run of zeros and few-symbol data in between
     big[9 * S: 9 * S + 3000] = 0
     big[11 * S: 12 * S] = synth.random_bytes(S) % 7 + 48
-    assert zz.deflate_raw(small, level=2)[0] == oracle.stream_chunked(small, DEFLATE, 2)[0]
-    assert zz.deflate_raw(big, level=2)[0] == oracle.stream_chunked(big, DEFLATE, 2, threads=8)[0]
+    want_small = oracle.stream_chunked(small, DEFLATE, 2)[0]
+    want_big = oracle.stream_chunked(big, DEFLATE, 2, threads=8)[0]
+    try:
+        for tma, spec in ((1, 1), (0, 1), (1, 0), (0, 0)):
+            assert lib.zzgpu_set_option(b"tma", tma) == 0 and lib.zzgpu_set_option(b"spec", spec) == 0
+            assert zz.deflate_raw(small, level=2)[0] == want_small, (tma, spec)
+            for case in ("pattern", "zeros", "kennedy", "ptt5"):
+                data = golden.input(case)
+                assert zz.deflate_raw(data, level=2)[0] == oracle.stream_chunked(data, DEFLATE, 2)[0], (case, tma, spec)
+            if spec:                                             # (the true walk alone is slow on a large input)
+                assert zz.deflate_raw(big, level=2)[0] == want_big, (tma, spec)
+    finally:
+        lib.zzgpu_set_option(b"tma", 1); lib.zzgpu_set_option(b"spec", 1)
+    assert lib.zzgpu_set_option(b"no-such-option", 1) == _lib.E_ARG
 
 
 @pytest.mark.parametrize("workload,size_mib,level", [("text", 1024, 2), ("text", 1088, 2), ("random", 1024, 2), ("zeros", 1024, 2),

@@ -342,12 +342,7 @@ int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final,
         rc = markStage(c, -1, st); if (rc) return rc;
         if (level >= 2) {
             launches += launch_candidates(job, st); rc = markStage(c, ZZGPU_STAGE_CAND, st); if (rc) return rc;
-            if (use_fused_lz()) {
-                launches += launch_lz(job, st); rc = markStage(c, ZZGPU_STAGE_LZ, st); if (rc) return rc;
-            } else {
-                launches += launch_info(job, st); rc = markStage(c, ZZGPU_STAGE_INFO, st); if (rc) return rc;
-                launches += launch_parse(job, st); rc = markStage(c, ZZGPU_STAGE_PARSE, st); if (rc) return rc;
-            }
+            launches += launch_lz(job, st); rc = markStage(c, ZZGPU_STAGE_LZ, st); if (rc) return rc;
         }
         if (level == 1) {
             launches += launch_fixed(job, st); rc = markStage(c, ZZGPU_STAGE_FIXED, st); if (rc) return rc;
@@ -900,7 +895,7 @@ int zzgpu_checksums(const uint8_t* src, size_t n, int src_mem, uint32_t adler_st
             Job job{};
             job.src = d_src; job.n = len; job.chunk = chunk; job.dict = 0; job.first_chunk = first;
             job.nchunks = (uint32_t)std::min<uint64_t>(32768, nchunks - first);
-            job.final_stream = 1; job.ck = c.ck;
+            job.final_stream = 1; job.ck = c.ck; job.want_checksums = (adler ? 1 : 0) | (crc ? 2 : 0);
             launch_checksums(job, c.stream);
         }
         CK(cudaGetLastError());

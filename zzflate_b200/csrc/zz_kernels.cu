@@ -5,11 +5,11 @@
 //   K-CAND   k_candidates  hash heads: nearest earlier position with the same 13-bit hash, per position
 //                          (replaces CalcHash / the table probe+insert of FirstPass / AddHashEntries,
 //                           zzflate/encoder.cpp:11-17,388-390,474-480)
-//   K-INFO   k_info        per-position match info against the candidate: min(forward length, 32), usable or not
-//                          (the compare part of FirstPass: remain / countMatchBackward; encoder.cpp:81-102,391-403)
-//   K-MATCH  k_parse       greedy acceptance as the orbit of a successor function, exact lengths and backward
-//                          extension of the taken matches, histograms, literal stream
-//                          (FirstPass, countMatchBackward, remain, GetFrequencies; encoder.cpp:375-471)
+//   K-LZ     k_lz          per-position match info against the candidate (the compare part of FirstPass: remain /
+//                          countMatchBackward; encoder.cpp:81-102,391-403) and, fused with it, the greedy acceptance as the
+//                          orbit of a successor function, exact lengths and backward extension of the taken matches,
+//                          histograms, literal stream (FirstPass, GetFrequencies; encoder.cpp:375-471); the window of every
+//                          sub-batch arrives in shared memory by TMA bulk copies (cp.async.bulk + mbarrier)
 //   K-HUFF   k_huffman     code lengths (libstdc++-heap Huffman with the reference's limiter), canonical
 //            k_huffman_lanes  codes, code-length RLE, exact block size, stored fallback decision, block header
 //                          (huffman.cpp:67-216, huffman.h:49-81, encoder.cpp:171-187,250-293); warp per chunk for
@@ -294,26 +294,9 @@ __device__ __forceinline__ unsigned long long ld8(const uint8_t* win, int o)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-INFO : per-position match info, parse independent (the compare part of FirstPass, encoder.cpp:391-403).
-//
-//   info[j] = 0                         position j cannot start a match (no candidate, or fewer than 4 bytes agree
-//                                       around j even with the backward extension)
-//           = 1 + min(fwd, 32)          otherwise; fwd = bytes that agree forwards between j and its hash candidate
-//
-// A position whose forward part is shorter than 4 is usable only if the candidate supplies the missing bytes
-// backwards.  One CTA handles a piece of 16 384 positions of one chunk with the 32 KiB before the piece
-// in shared memory (four CTAs per SM, no barrier after the window load); the candidate gathers are the cost.
-// K-MATCH masks the batch edges and recomputes the few positions whose candidate changes with the parse.
+// match info helpers (the compare part of FirstPass, encoder.cpp:391-403)
 // ------------------------------------------------------------------------------------------------
 constexpr int kCapLen = 32;                        // cap of the parallel forward compare
-constexpr int kInfoPiece = 16384;
-constexpr int kInfoThreads = 256;
-constexpr int kInfoBack = kMaxDistance + 16;        // bytes kept before the piece (candidate + 4 bytes backwards)
-constexpr int kInfoWin = 16 + 16 + kInfoBack + kInfoPiece + 64 + 32;      // window bytes (multiple of 16)
-constexpr int kInfoQueue = 32 + 128;                                       // per-warp queue: a remainder + one step
-constexpr int kInfoSmem = kInfoWin + (kInfoThreads / 32) * kInfoQueue * 4;
-static_assert(kInfoWin % 16 == 0, "queue alignment");
-
 // forward match length beyond the first 4 bytes, capped at kCapLen - 4 (oj, op already advanced by 4)
 __device__ __forceinline__ int fwd_more(const uint8_t* win, int oj, int op)
 {
@@ -328,204 +311,16 @@ __device__ __forceinline__ int fwd_more(const uint8_t* win, int oj, int op)
     return x1 ? 24 + ((__ffs(x1) - 1) >> 3) : kCapLen - 4;
 }
 
-__global__ void __launch_bounds__(kInfoThreads, 4) k_info(Job job, int piecesPerChunk)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    const unsigned slot = blockIdx.x / (unsigned)piecesPerChunk;
-    const int piece = (int)(blockIdx.x % (unsigned)piecesPerChunk);
-    const Geom g = chunk_geom(job, slot);
-    const int P0 = piece * kInfoPiece;
-    int P1 = P0 + kInfoPiece; if (P1 > g.t0) P1 = g.t0;       // positions >= t0 are never probed (encoder.cpp:222)
-    if (P0 >= P1) return;
-    const uint8_t* chunk0 = job.src + g.off;
-    const int wb = 16 + kInfoBack + (int)(reinterpret_cast<uintptr_t>(chunk0) & 15) - P0;    // position i at smem[wb + i]
-    int lo = P0 - kInfoBack; if (lo < -g.pre) lo = -g.pre;
-    int hi = P1 + 48; if (hi > g.n) hi = g.n;
-    load_window(smem, wb, chunk0, lo, hi, hi + 16);
-    __syncthreads();
-    const uint16_t* cand = job.cand + (size_t)slot * job.chunk;
-    uint8_t* out = job.info + (size_t)slot * job.chunk;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned ltMask = (1u << lane) - 1u;
-    const unsigned* w32 = reinterpret_cast<const unsigned*>(smem);
-    const int ph8 = (wb & 3) * 8;                       // j0 is a multiple of 4: every thread sees the same byte phase
-    // Positions whose first four bytes agree need the longer compare (up to 32 bytes).  They are a minority of the lanes
-    // of every step, so they are queued per warp (position and candidate as shared-memory offsets) and measured 32 at a
-    // time with all lanes busy, instead of letting every step pay for the longest lane.
-    unsigned* queue = reinterpret_cast<unsigned*>(smem + kInfoWin) + (tid >> 5) * kInfoQueue;
-    int queued = 0;
-    auto drain = [&](int n) {                            // measures queue[0, n), n <= 32
-        if (lane < n) {
-            const unsigned e = queue[lane];
-            const int oj = (int)(e & 0xFFFFu), op = (int)(e >> 16);
-            out[oj - wb] = (uint8_t)(4 + fwd_more(smem, oj + 4, op + 4) + 1);
-        }
-    };
-    // Four consecutive positions per thread: their own bytes [j0-4, j0+8) come from four aligned words (lanes read
-    // consecutive words: conflict free), the candidate side is two gathered words per position (all eight gathers are
-    // issued before the first compare), a third one only where bytes are missing forwards.
-    const int iters = (P1 - P0 + 4 * kInfoThreads - 1) / (4 * kInfoThreads);
-    uint2 ddNext = make_uint2(0u, 0u);
-    if (P0 + 4 * tid < P1) ddNext = __ldg(reinterpret_cast<const uint2*>(cand + P0 + 4 * tid));
-    for (int it = 0; it < iters; ++it) {
-        const int j0 = P0 + 4 * tid + it * 4 * kInfoThreads;
-        const bool live = j0 < P1;
-        const uint2 dd = ddNext;
-        ddNext = make_uint2(0u, 0u);                                     // the next step's candidates travel during this one
-        if (j0 + 4 * kInfoThreads < P1) ddNext = __ldg(reinterpret_cast<const uint2*>(cand + j0 + 4 * kInfoThreads));
-        int d[4] = { (int)(dd.x & 0xFFFFu), (int)(dd.x >> 16), (int)(dd.y & 0xFFFFu), (int)(dd.y >> 16) };
-        if (j0 == 0) d[0] = 0;                          // position 0 is never probed (encoder.cpp:384)
-        if (j0 + 3 >= P1) {
-#pragma unroll
-            for (int k = 1; k < 4; ++k) if (j0 + k >= P1) d[k] = 0;
-        }
-        const int oj0 = wb + (live ? j0 : P0);
-        const unsigned* wj = w32 + (oj0 >> 2);
-        const unsigned W0 = wj[-1], W1 = wj[0], W2 = wj[1], W3 = wj[2];
-        const unsigned V0 = __funnelshift_r(W0, W1, ph8), V1 = __funnelshift_r(W1, W2, ph8), V2 = __funnelshift_r(W2, W3, ph8);
-        unsigned pw0[4], pw1[4]; int op[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            op[k] = oj0 + k - d[k];
-            const unsigned* wp = w32 + (op[k] >> 2);
-            pw0[k] = wp[0]; pw1[k] = wp[1];
-        }
-        unsigned packed = 0, longMask = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned x = __funnelshift_r(V1, V2, 8 * k) ^ __funnelshift_r(pw0[k], pw1[k], op[k] * 8);
-            if (d[k] != 0) {
-                if (x == 0) longMask |= 1u << k;         // >= 4 bytes forwards: usable whatever lies behind; length from the queue
-                else {
-                    const int fwd = (__ffs(x) - 1) >> 3;
-                    const unsigned y = __funnelshift_r(V0, V1, 8 * k) ^ __funnelshift_r(w32[(op[k] >> 2) - 1], pw0[k], op[k] * 8);
-                    int back = y ? (__clz(y) >> 3) : 4;
-                    const int room = j0 + k - d[k] + g.pre;   // bytes of real history before the candidate (R4 clamp)
-                    if (back > room) back = room;
-                    if (fwd + back >= 4) packed |= (unsigned)(fwd + 1) << (8 * k);
-                }
-            }
-        }
-        // queued bytes are stored as 0 here and overwritten when the queue is drained: the drain comes after a
-        // __syncwarp(), which orders the two stores of the warp
-        if (live) *reinterpret_cast<unsigned*>(out + j0) = packed;
-        {   // append: a lane queues 0..4 positions; its slot = positions queued by lower lanes (three votes on the count's bits)
-            const unsigned cnt = (unsigned)__popc(longMask);
-            const unsigned b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u), b2 = __ballot_sync(0xffffffffu, cnt & 4u);
-            int slotq = queued + __popc(b0 & ltMask) + 2 * __popc(b1 & ltMask) + 4 * __popc(b2 & ltMask);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((longMask >> k) & 1u) queue[slotq++] = (unsigned)(oj0 + k) | ((unsigned)op[k] << 16);
-            queued += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-        }
-        __syncwarp();
-        int head = 0;
-        while (queued - head >= 32) {
-            if (true) { const unsigned e = queue[head + lane]; const int oj = (int)(e & 0xFFFFu), opq = (int)(e >> 16);
-                        out[oj - wb] = (uint8_t)(4 + fwd_more(smem, oj + 4, opq + 4) + 1); }
-            head += 32;
-        }
-        if (head) {                                      // keep the remainder (< 32 entries) at the front
-            const int rem = queued - head;
-            unsigned e = 0;
-            if (lane < rem) e = queue[head + lane];
-            __syncwarp();
-            if (lane < rem) queue[lane] = e;
-            queued = rem;
-        }
-        __syncwarp();
-    }
-    drain(queued);
-}
-
 // ------------------------------------------------------------------------------------------------
-// K-MATCH : one CTA per chunk.
-//
-// The reference's greedy parse (FirstPass, encoder.cpp:375-440) is a sequential walk, but it factors into
-// parse-independent pieces:
-//   * info[j]   = (forward match length, backward match length) of position j against its hash candidate,
-//                 both capped at 32 -- computed for every position in parallel;
-//   * a *state* is b = end of the last emitted match.  From state b the walk probes b+1, b+2, ... and takes the
-//                 first j that is usable (fwd+back >= 4) with j-b >= 4-min(fwd,4).  The next state is
-//                 F(b) = j + fwd (the backward extension only moves the match start) -- again computable for
-//                 every b in parallel;
-//   * the parse is the orbit of F from the batch start.  Orbits are followed tile by tile (32 states): E1[b] is
-//                 the first iterate of F that leaves b's tile (3 rounds of pointer jumping with warp shuffles),
-//                 so one lane hops over 2048 tiles instead of ~10^4 matches; tiles then expand their part of
-//                 the orbit into tokens in parallel.
-// Matches of 32 bytes or more are resolved exactly (up to 258) only where the orbit actually meets them.
+// helpers of the parse
 // ------------------------------------------------------------------------------------------------
-#ifdef ZZ_PHASE_TIMING
-__device__ unsigned long long g_phaseCycles[16];
-#define PHASE_MARK(i) do { if (tid == 0) { const long long now_ = clock64(); atomicAdd(&g_phaseCycles[i], (unsigned long long)(now_ - tPhase)); tPhase = now_; } } while (0)
-#else
-#define PHASE_MARK(i) do { } while (0)
-#endif
-constexpr int kParseThreads = 512;               // two CTAs per SM: the serial phases of one overlap the other's parallel phases
-constexpr int kBatchCap = kBatch + 128;            // entries of the per-batch arrays (tile-aligned base + slack)
-constexpr int kTilesCap = kBatchCap / 32;
-constexpr int kSegCap = kTilesCap + 32;
-constexpr int kSuperShift = 9;                     // super tile = 16 tiles = 512 states: one per warp and batch
-constexpr int kSuperStates = 1 << kSuperShift;
-constexpr int kSuperTiles = kSuperStates / 32;
 constexpr int kLongGap = kMaxMatch - kCapLen + 1;   // literal gap from which fwd + backward extension can exceed 258
 
-// F(b) = j + fwd holds while the match length fwd + lb stays below the 258 cap.  A match is resolved exactly (by the
-// orbit chase) when its forward part reached the 32-byte compare cap, or when the pending literal run is so long that the
-// backward extension alone could push fwd + lb over 258 (then the next state is j - lb + 258 < j + fwd).
+// succ(b) = j + fwd holds while the match length fwd + lb stays below the 258 cap.  A match is measured exactly when its
+// forward part reached the 32-byte compare cap, or when the pending literal run is so long that the backward extension
+// alone could push fwd + lb over 258 (then the next state is j - lb + 258 < j + fwd).
 __device__ __forceinline__ bool needs_exact(int fwd, int gap) { return fwd >= kCapLen || gap >= kLongGap; }
 constexpr unsigned kNone16 = 0xFFFFu;
-constexpr int kParseSmem = kBatchCap /*info*/ + 2 * kBatchCap * 2 /*F,E2*/ + kBatchCap /*E1*/ +
-                           (kTilesCap + 4) * (4 + 4 + 2 + 2) + kSegCap * 2 + 16;
-static_assert(2 * (kParseSmem + 1024 + 512) <= 228 * 1024, "two K-MATCH CTAs must fit one SM");
-
-// tile exit packed to a byte: 0 = the orbit ends in the tile, 1..32 = it meets a long match at state tileStart + v - 1,
-// 33..254 = first state beyond the tile at tileEnd + v - 33, 255 = further away (the reader follows F instead)
-__device__ __forceinline__ unsigned e1_pack(unsigned e, int tileStart)
-{
-    // both non-zero cases are rel + 1 (1..32 inside the tile, 33..254 beyond it), saturated at 255
-    const unsigned v = e - (unsigned)tileStart + 1u;
-    return e == 0u ? 0u : (v < 255u ? v : 255u);
-}
-
-struct ParseShared {
-    int pos;            // start of the next FirstPass batch
-    int ntok;
-    int nexcl;          // batch starts that were never inserted into the hash table
-    int excl[4];
-    int npatch;         // positions whose candidate changes because of an excluded batch start
-    int patchJ[4];
-    int patchD[4];
-    int fixS;           // excluded position whose successor still has to be found, or -1
-    int fixJ;
-    int npre;           // 1 if the batch's first probe (j == backRefEnd) produced a token
-    int nseg;           // orbit segments of the batch (one per super tile entered / long match resolved)
-    int finalB;         // last state of the batch, or -1 while it is still inside a tile
-};
-
-// candidate of j with the never-inserted batch starts removed from the hash chain
-__device__ int effective_cand(const uint16_t* cand, const ParseShared* ps, int j)
-{
-    int d = cand[j];
-    for (;;) {
-        if (d == 0) return 0;
-        const int p = j - d;
-        bool hit = false;
-        for (int k = 0; k < ps->nexcl; ++k) hit |= (ps->excl[k] == p);
-        if (!hit) return d;
-        const int dd = p > 0 ? cand[p] : 0;
-        if (dd == 0) return 0;
-        d += dd;
-        if (d >= kMaxDistance) return 0;
-    }
-}
-
-__device__ __forceinline__ int patched_cand(const uint16_t* cand, const ParseShared* ps, int npatch, int j)
-{
-    int d = __ldg(cand + j);
-    if (npatch) for (int k = 0; k < npatch; ++k) if (ps->patchJ[k] == j) d = ps->patchD[k];
-    return d;
-}
 
 // unaligned 8-byte little-endian load from global memory; bytes outside [lo, hi) read as zero
 __device__ __forceinline__ unsigned long long gload8(const uint8_t* p, const uint8_t* lo, const uint8_t* hi)
@@ -559,78 +354,8 @@ __device__ __forceinline__ unsigned gload4(const uint8_t* p, const uint8_t* lo, 
     return v;
 }
 
-// The stream bytes K-MATCH still needs (exact lengths of long matches, backward extension of the tokens, literal
-// histogram, the rare patched positions) are read from global memory: pj / pp point at the position and its candidate,
-// [lo, hi) is the readable stream.
+// [lo, hi) is the readable stream
 struct Stream { const uint8_t* lo; const uint8_t* hi; };
-
-// info of one position (same definition as K-INFO)
-__device__ int info_of_g(const uint8_t* pj, int d, int room, Stream st)
-{
-    if (d == 0) return 0;
-    const uint8_t* pp = pj - d;
-    int fwd = 0;
-    while (fwd < kCapLen) {
-        const unsigned x = gload4(pj + fwd, st.lo, st.hi) ^ gload4(pp + fwd, st.lo, st.hi);
-        if (x) { fwd += (__ffs(x) - 1) >> 3; break; }
-        fwd += 4;
-    }
-    bool ok = fwd >= 4;
-    if (!ok) {
-        const unsigned y = gload4(pj - 4, st.lo, st.hi) ^ gload4(pp - 4, st.lo, st.hi);
-        int back = y ? (__clz(y) >> 3) : 4;
-        if (back > room) back = room;                    // bytes of real history before the candidate (R4 clamp)
-        ok = fwd + back >= 4;
-    }
-    return ok ? fwd + 1 : 0;
-}
-
-// exact forward and backward match lengths (<= 258 each) of a long match, all 32 lanes cooperate (remain(),
-// countMatchBackward; encoder.cpp:81-102).  Both sides are loaded before the first vote so that the global-memory
-// latency is paid once.
-__device__ __forceinline__ void coop_lengths(const uint8_t* pj, const uint8_t* pp, Stream st, int lane, bool wantBack, int& fwd, int& lb)
-{
-    const unsigned long long xa = gload8(pj + lane * 8, st.lo, st.hi) ^ gload8(pp + lane * 8, st.lo, st.hi);
-    unsigned long long xb = 0;
-    unsigned ta = 1, tb = 1;
-    if (wantBack) xb = gload8(pj - 8 - lane * 8, st.lo, st.hi) ^ gload8(pp - 8 - lane * 8, st.lo, st.hi);
-    if (lane < 2) ta = (unsigned)(gload4(pj + 256 + lane, st.lo, st.hi) ^ gload4(pp + 256 + lane, st.lo, st.hi)) & 0xFFu;
-    if (wantBack && lane < 2) tb = (unsigned)(gload4(pj - 257 - lane, st.lo, st.hi) ^ gload4(pp - 257 - lane, st.lo, st.hi)) & 0xFFu;
-    const unsigned ma = __ballot_sync(0xffffffffu, xa != 0);
-    const unsigned mta = __ballot_sync(0xffffffffu, ta == 0);       // bit 0: byte 256 equal, bit 1: byte 257 equal
-    if (ma) {
-        const int src = __ffs(ma) - 1;
-        const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src);
-        fwd = src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
-    } else {
-        fwd = 256 + ((mta & 1u) ? ((mta & 2u) ? 2 : 1) : 0);
-    }
-    lb = 0;
-    if (wantBack) {
-        const unsigned mb = __ballot_sync(0xffffffffu, xb != 0);
-        const unsigned mtb = __ballot_sync(0xffffffffu, tb == 0);
-        if (mb) {
-            const int src = __ffs(mb) - 1;
-            const unsigned long long xs = __shfl_sync(0xffffffffu, xb, src);
-            lb = src * 8 + (__clzll((long long)xs) >> 3);
-        } else {
-            lb = 256 + ((mtb & 1u) ? ((mtb & 2u) ? 2 : 1) : 0);
-        }
-    }
-}
-
-// single-thread backward match length, at most `limit` bytes (token expansion: limit is the literal gap, mostly <= 3)
-__device__ __forceinline__ int back_upto(const uint8_t* pj, const uint8_t* pp, int limit, Stream st)
-{
-    int lb = 0;
-    while (lb < limit) {
-        const unsigned y = gload4(pj - 4 - lb, st.lo, st.hi) ^ gload4(pp - 4 - lb, st.lo, st.hi);
-        const int c = y ? (__clz(y) >> 3) : 4;
-        lb += c;
-        if (c < 4) break;
-    }
-    return lb < limit ? lb : limit;
-}
 
 // First position the walk would take from state b (b = end of the previous match), or -1.
 // info == 0 marks an unusable position, otherwise info - 1 = min(forward length, 32); a usable position j is
@@ -650,475 +375,6 @@ __device__ __forceinline__ int probe_next(const uint8_t* info, const unsigned* o
     const unsigned w2 = nzw[w + 1];
     if (w2 == kNone16) return -1;
     return base + (int)w2 * 32 + __ffs(okbits[w2]) - 1;
-}
-
-__global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t* info = smem;
-    uint16_t* F = reinterpret_cast<uint16_t*>(info + kBatchCap);
-    uint16_t* E2 = F + kBatchCap;
-    uint8_t* E1 = reinterpret_cast<uint8_t*>(E2 + kBatchCap);        // tile exits, packed to a byte (e1_pack)
-    unsigned* okbits = reinterpret_cast<unsigned*>(E1 + kBatchCap);  // bit per position: usable (info != 0)
-    unsigned* entry = okbits + (kTilesCap + 4);      // first orbit state inside each tile (atomicMin: a tile can be entered twice)
-    uint16_t* nzw = reinterpret_cast<uint16_t*>(entry + (kTilesCap + 4));
-    uint16_t* seg = nzw + 2 * (kTilesCap + 4);
-    __shared__ ParseShared ps;
-    __shared__ unsigned wsum[32];
-
-    const unsigned slot = blockIdx.x;
-    const Geom g = chunk_geom(job, slot);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kParseThreads >> 5;
-    const uint8_t* chunk0 = job.src + g.off;
-    const Stream strm = { job.src - job.history, job.src + job.n };
-    const uint16_t* cand = job.cand + (size_t)slot * job.chunk;
-    uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
-    uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
-
-#ifdef ZZ_PHASE_TIMING
-    long long tPhase = clock64();
-#endif
-    if (tid == 0) { ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npatch = 0; ps.fixS = -1; ps.fixJ = 0x7fffffff; }
-    __syncthreads();
-    PHASE_MARK(0);
-
-    const int t0 = g.t0;
-    // ---- batches of the reference's WriteBlock2Pass loop (encoder.cpp:225-234) ----
-    for (;;) {
-        const int pos = ps.pos;
-        if (pos >= t0) break;
-        const int fixS = ps.fixS;
-        if (fixS >= 0) {
-            // the batch start fixS was never inserted: its successor in the hash chain must see fixS's
-            // own predecessor instead.  Find the successor (first j > fixS whose raw candidate is fixS).
-            int hiJ = fixS + kMaxDistance; if (hiJ > t0) hiJ = t0;
-            for (int j = fixS + 1 + tid; j < hiJ; j += kParseThreads)
-                if ((int)cand[j] == j - fixS) atomicMin(&ps.fixJ, j);
-            __syncthreads();
-            if (tid == 0) {
-                const int fj = ps.fixJ;
-                if (fj < 0x7fffffff) { const int k = ps.npatch++; ps.patchJ[k] = fj; ps.patchD[k] = effective_cand(cand, &ps, fj); }
-            }
-            __syncthreads();
-        }
-        const int npatch = ps.npatch;
-        int E = pos + kBatch; if (E > t0) E = t0;
-        const int B0 = pos + 1;                          // FirstPass: backRefEnd = j = startPos + 1
-        const int base = B0 & ~31;
-        const int ntiles = (E - base + 31) >> 5;
-        const int nsuper = (ntiles + kSuperTiles - 1) / kSuperTiles;
-
-        // ---- P1: per-position match info of the batch (computed by K-INFO), masked to the batch's probe range
-        //      [B0, E); the positions whose candidate changed with the parse are recomputed here ----
-        {
-            const int lim = ntiles * 32 + 64;
-            const uint8_t* ginfo = job.info + (size_t)slot * job.chunk + base;          // 32-byte aligned
-            for (int idx = tid * 4; idx < lim; idx += 4 * kParseThreads) {
-                unsigned v = __ldg(reinterpret_cast<const unsigned*>(ginfo + idx));
-                const int j = base + idx;
-                if (j < B0 || j + 3 >= E) {
-                    unsigned m = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (j + k >= B0 && j + k < E) m |= 0xFFu << (8 * k);
-                    v &= m;
-                }
-                *reinterpret_cast<unsigned*>(info + idx) = v;
-            }
-            __syncthreads();
-            if (tid < npatch) {
-                const int pj = ps.patchJ[tid];
-                if (pj >= B0 && pj < E) { const int pd = ps.patchD[tid]; info[pj - base] = (uint8_t)info_of_g(chunk0 + pj, pd, pj - pd + g.pre, strm); }
-            }
-            __syncthreads();
-            for (int idx = tid; idx < lim; idx += kParseThreads) {
-                const unsigned inf = info[idx];
-                const unsigned m4 = __ballot_sync(0xffffffffu, inf != 0);
-                if (lane == 0) okbits[idx >> 5] = m4;
-            }
-        }
-        for (int t = tid; t < kTilesCap; t += kParseThreads) entry[t] = kNone16;
-        __syncthreads();
-        PHASE_MARK(1);
-        // next non-empty bitmap word at or after w
-        for (int w = tid; w <= ntiles; w += kParseThreads) {
-            int k = w;
-            while (k < ntiles && okbits[k] == 0) ++k;
-            nzw[w] = (uint16_t)(k < ntiles ? k : kNone16);
-        }
-        __syncthreads();
-        PHASE_MARK(2);
-
-        // ---- P2: successor function F over states, and E1 = where the orbit of b leaves b's tile.
-        //      Values: 0 = no further match in the batch; a state inside the tile = the orbit meets a long match
-        //      there (F == 1 marks such states); otherwise the first iterate beyond the tile.  A match advances
-        //      the state by >= 4, so 3 rounds of pointer jumping (8 hops) cover a 32-state tile.
-        for (int sp = warp; sp < nsuper; sp += nwarps) {
-          const int superEnd = base + (sp + 1) * kSuperStates;
-          const int tFirst = sp * kSuperTiles;
-          int tLast = tFirst + kSuperTiles - 1; if (tLast >= ntiles) tLast = ntiles - 1;
-          // pass A: F and the tile exits; the tiles of the super tile are independent, so their shared-memory
-          // round trips overlap
-#pragma unroll 8
-          for (int t = tFirst; t <= tLast; ++t) {
-            const int tileStart = base + t * 32, tileEnd = tileStart + 32;
-            const int r = t * 32 + lane, b = tileStart + lane;
-            unsigned f = 0;
-            {
-                // probe_next for the 32 states of the tile: positions b+1..b+3 need 1..3 bytes backwards less than a
-                // full match (info >= 4 / 3 / 2), from b+4 on any usable position is taken (bitmap)
-                int j = -1;
-                // info[r+1..r+3] from two aligned words; adding 0x7C / 0x7D / 0x7E sets bit 7 of a byte iff it is >= 4 / 3 / 2
-                const unsigned* iw = reinterpret_cast<const unsigned*>(info) + ((r + 1) >> 2);
-                const unsigned near3 = (__funnelshift_r(iw[0], iw[1], ((r + 1) & 3) * 8) + 0x007E7D7Cu) & 0x00808080u;   // info <= 33: no carry between bytes
-                if (near3) j = b + 1 + ((__ffs(near3) - 1) >> 3);
-                else {
-                    const unsigned low = okbits[t], hiw = okbits[t + 1];
-                    const int sh = lane + 4;                                           // first position that needs nothing backwards
-                    const unsigned near = sh < 32 ? __funnelshift_r(low, hiw, sh) : hiw >> (sh - 32);   // from position b+4
-                    const unsigned far = sh < 32 ? hiw >> sh : 0u;                    // from position b+36
-                    if (near) j = b + 4 + __ffs(near) - 1;
-                    else if (far) j = b + 36 + __ffs(far) - 1;
-                    else if (t + 2 <= ntiles) {
-                        const unsigned w2 = nzw[t + 2];
-                        if (w2 != kNone16) j = base + (int)w2 * 32 + __ffs(okbits[w2]) - 1;
-                    }
-                }
-                if ((unsigned)(b - B0) < (unsigned)(E - B0) && j >= 0) {
-                    const unsigned fwd = (unsigned)info[j - base] - 1u;
-                    f = needs_exact((int)fwd, j - b) ? 1u : (unsigned)j + fwd;
-                }
-            }
-            F[r] = (uint16_t)f;
-            // a state that meets a long match carries kLongFlag: a lane that lands on it inherits "long match at that
-            // state" and stops (flagged values fail the inside-the-tile test).  Tiles start at multiples of 32, so the
-            // lane that holds state e is e & 31, which is what the shuffle takes.
-            constexpr unsigned kLongFlag = 0x80000000u;
-            unsigned e = f == 1u ? ((unsigned)b | kLongFlag) : f;
-#pragma unroll
-            for (int rr = 0; rr < 3; ++rr) {
-                const unsigned e2 = __shfl_sync(0xffffffffu, e, (int)e);
-                if (e >= 2u && e < (unsigned)tileEnd) e = e2;
-            }
-            e &= ~kLongFlag;
-            E1[r] = (uint8_t)e1_pack(e, tileStart);
-            E2[r] = (uint16_t)e;                       // tile exit for now; pass B turns it into the super-tile exit
-          }
-          __syncwarp();
-          // pass B: E2 = where the orbit leaves the super tile (kSuperTiles tiles).  The warp walks the super tile's tiles
-          // from the last to the first: a state whose tile exit lands on a later tile of the same super tile inherits that
-          // state's (already final) super-tile exit, so every state is touched once.
-          const unsigned stayEnd = (unsigned)(superEnd < E ? superEnd : E);   // exits below it stay inside the super tile and the batch
-          for (int t = tLast; t >= tFirst; --t) {
-            const unsigned tileEnd = (unsigned)(base + (t + 1) * 32);
-            const unsigned e = E2[t * 32 + lane];
-            unsigned fin = e;
-            if (e >= tileEnd && e < stayEnd && F[(int)e - base] != 1) fin = E2[(int)e - base];
-            E2[t * 32 + lane] = (uint16_t)fin;
-            __syncwarp();
-          }
-        }
-        __syncthreads();
-        PHASE_MARK(3);
-        PHASE_MARK(4);
-
-        // ---- P4: follow the orbit super tile by super tile (warp 0; lanes cooperate on long matches) ----
-        if (warp == 0) {
-            int b = B0, finalB = B0, npre = 0, nseg = 0;
-            const int tokBase = ps.ntok;
-            if (B0 < E) {
-                const unsigned inf = info[B0 - base];
-                if (inf >= 5) {                           // first probe of the batch: j == backRefEnd, no backward room
-                    const int d = patched_cand(cand, &ps, npatch, B0);
-                    int fwd = (int)inf - 1;
-                    if (fwd >= kCapLen) { int lbNone; coop_lengths(chunk0 + B0, chunk0 + B0 - d, strm, lane, false, fwd, lbNone); }
-                    if (lane == 0) { tokA[tokBase] = (uint32_t)B0 | ((uint32_t)fwd << 16); tokD[tokBase] = (uint16_t)d; }
-                    b = B0 + fwd; npre = 1;
-                }
-            }
-            // The hop is a dependent shared-memory load per super tile and sits on the kernel's critical path (every other
-            // warp waits), so it is written with explicit shared addresses: ld.shared, compare, branch.
-            const unsigned aE2 = (unsigned)__cvta_generic_to_shared(E2) - 2u * (unsigned)base;   // &E2[b - base] = aE2 + 2 b
-            const unsigned aSeg = (unsigned)__cvta_generic_to_shared(seg);
-            for (;;) {
-                // every iteration starts a new segment (a super tile is entered / a long match was resolved)
-                unsigned e = 0;
-                bool done = false;
-                for (;;) {
-                    finalB = b;
-                    if (b >= E) { done = true; break; }
-                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(aSeg + 2u * (unsigned)nseg), "h"((unsigned short)b) : "memory");
-                    ++nseg;
-                    unsigned short ev;
-                    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ev) : "r"(aE2 + 2u * (unsigned)b) : "memory");
-                    e = ev;
-                    // E2 is complete for every state, so: beyond the super tile (or the batch) = plain hop,
-                    // 0 = the orbit ends inside a tile, anything else = the state where it meets a long match
-                    int lim = base + (((b - base) | (kSuperStates - 1)) + 1); if (lim > E) lim = E;
-                    if ((int)e < lim) break;
-                    b = (int)e;
-                }
-                if (done) break;
-                if (e == 0) { finalB = -1; break; }       // ends inside a tile: the tile reports the last state
-
-                // long match at state x = e: exact lengths
-                const int x = (int)e;
-                const int j = probe_next(info, okbits, nzw, ntiles, base, x);
-                const int d = patched_cand(cand, &ps, npatch, j);
-                const int p = j - d;
-                int maxBack = j - x;
-                { const int room = p + g.pre; if (room < maxBack) maxBack = room; }     // R4: clamp at stream start
-                if (maxBack > kMaxMatch) maxBack = kMaxMatch;                            // R6: cap (reference breaks at 259)
-                int fwd, lb;
-                coop_lengths(chunk0 + j, chunk0 + p, strm, lane, maxBack > 0, fwd, lb);
-                if (lb > maxBack) lb = maxBack;
-                int m = fwd + lb; if (m > kMaxMatch) m = kMaxMatch;
-                const int ms = j - lb;
-                b = ms + m;
-                // F becomes exact for this state.  With a long backward part the match can end inside x's own tile
-                // (b = j - lb + 258 may be as small as j): the tile's expansion then simply walks on from b.
-                if (lane == 0) F[x - base] = (uint16_t)(b < 65535 ? b : 65535);
-                // Runs (RLE-like data): a full-length match whose successor states repeat it 258 bytes further on.  Each
-                // of them would cost two dependent trips to memory on this serial path; instead the equality between
-                // the two sides is measured once beyond the first 258 bytes (R, as far as 32 more matches can use it) and
-                // lane i-1 checks that state x + 258 i is an unresolved long state whose probe position has the same gap
-                // and the same distance.  For those states fwd_i = min(258, R - 258 i) and the backward part is the gap
-                // again (its bytes lie inside [j, j + R)), so match i is (start x_i, length 258) exactly as the walk
-                // would find it, as long as R - 258 i >= 258 - gap.
-                const int gap = j - x;
-                if (fwd == kMaxMatch && lb == gap && b + 1 < E) {
-                    const int xi = x + kMaxMatch * (lane + 1);
-                    bool ok = xi < E;
-                    if (ok) ok = F[xi - base] == 1;
-                    if (ok) ok = probe_next(info, okbits, nzw, ntiles, base, xi) == xi + gap;
-                    if (ok) ok = patched_cand(cand, &ps, npatch, xi + gap) == d;
-                    const unsigned okm = __ballot_sync(0xffffffffu, ok);
-                    int K = okm == 0xffffffffu ? 32 : __ffs(~okm) - 1;            // candidates of the run
-                    if (K > 0) {
-                        // R: equal bytes between the two sides from j on, measured only as far as K matches need it
-                        int Rcap = kMaxMatch * (K + 1) - gap; { const int lim = g.body - j; if (lim < Rcap) Rcap = lim; }
-                        int R = Rcap;
-                        for (int off = 256; off < Rcap && R == Rcap; off += 1024) {
-                            unsigned long long xa[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                xa[u] = off + 256 * u < Rcap ? gload8(chunk0 + j + off + 256 * u + lane * 8, strm.lo, strm.hi) ^ gload8(chunk0 + p + off + 256 * u + lane * 8, strm.lo, strm.hi) : 0ull;
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const unsigned mm = __ballot_sync(0xffffffffu, xa[u] != 0);
-                                if (mm && R == Rcap) {
-                                    const int src = __ffs(mm) - 1;
-                                    const unsigned long long xs = __shfl_sync(0xffffffffu, xa[u], src);
-                                    const int r = off + 256 * u + src * 8 + ((__ffsll((long long)xs) - 1) >> 3);
-                                    if (r < R) R = r;
-                                }
-                            }
-                        }
-                        // match i needs R - 258 i >= 258 - gap
-                        const int byR = (R - kMaxMatch + gap) / kMaxMatch;
-                        if (byR < K) K = byR < 0 ? 0 : byR;
-                        if (lane < K) {
-                            const int nb = xi + kMaxMatch;
-                            F[xi - base] = (uint16_t)(nb < 65535 ? nb : 65535);
-                            seg[nseg + lane] = (uint16_t)xi;         // every resolved long state starts a segment
-                        }
-                        nseg += K;
-                        b = x + kMaxMatch * (K + 1);
-                        __syncwarp();
-                    }
-                }
-            }
-            if (lane == 0) { ps.npre = npre; ps.nseg = nseg; ps.finalB = finalB; }
-        }
-        __syncthreads();
-        PHASE_MARK(5);
-        // ---- P4b: every segment marks the tiles it enters ----
-        for (int sg = tid; sg < ps.nseg; sg += kParseThreads) {
-            int b = seg[sg];
-            const int superEnd = base + (((b - base) >> kSuperShift) + 1) * kSuperStates;
-            for (;;) {
-                const int t = (b - base) >> 5;
-                const int tileEnd = base + (t + 1) * 32;
-                atomicMin(&entry[t], (unsigned)b);
-                const unsigned v = E1[b - base];
-                if (v <= 32u) break;                       // orbit ends in the tile (0) or meets a long match there (1..32)
-                unsigned e;
-                if (v < 255u) e = (unsigned)tileEnd + (v - 33u);
-                else {                                     // exit too far for the byte: follow F through the tile (no long match on the way)
-                    int x = b;
-                    for (;;) { e = F[x - base]; if (e < 2u || (int)e >= tileEnd) break; x = (int)e; }
-                    if (e < 2u) break;
-                }
-                if ((int)e >= superEnd || (int)e >= E) break;
-                b = (int)e;
-            }
-        }
-        __syncthreads();
-        PHASE_MARK(6);
-
-        // ---- P5: tiles list the orbit states they hold (each state yields one token), then the tokens of the batch are
-        //      expanded token-parallel: the candidate loads overlap and the token stores are coalesced ----
-        unsigned cnt = 0;
-        const int tBeg = tid < ntiles ? tid : ntiles;
-        const int tEnd = tid == kParseThreads - 1 ? ntiles : (tid + 1 < ntiles ? tid + 1 : ntiles);   // the last thread takes the tail
-        for (int tt = tBeg; tt < tEnd; ++tt) {
-            const unsigned e = entry[tt];
-            if (e != kNone16) {
-                const int tileEnd = base + (tt + 1) * 32;
-                int x = (int)e;
-                for (;;) {
-                    const unsigned f = F[x - base];
-                    if (f == 0) { ps.finalB = x; break; }
-                    ++cnt;
-                    if (f != 1 && (int)f >= E) ps.finalB = (int)f;      // the match that leaves the batch
-                    if (f == 1 || (int)f >= tileEnd) break;
-                    x = (int)f;
-                }
-            }
-        }
-        unsigned inc = cnt;
-        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-        if (lane == 31) wsum[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned v = lane < nwarps ? wsum[lane] : 0u;
-            for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-            wsum[lane] = v;
-        }
-        __syncthreads();
-        uint16_t* stateList = E2;                                    // E2 is dead after the chase
-        if (cnt) {
-            int out = (int)((warp ? wsum[warp - 1] : 0) + inc - cnt);
-            for (int tt = tBeg; tt < tEnd; ++tt) {
-                const unsigned e0 = entry[tt];
-                if (e0 == kNone16) continue;
-                const int tileEnd = base + (tt + 1) * 32;
-                int x = (int)e0;
-                for (;;) {
-                    const unsigned f = F[x - base];
-                    if (f == 0) break;
-                    stateList[out++] = (uint16_t)x;
-                    if (f == 1 || (int)f >= tileEnd) break;
-                    x = (int)f;
-                }
-            }
-        }
-        __syncthreads();
-        {
-            const int nbt = (int)wsum[31];
-            const int outBase = ps.ntok + ps.npre;
-            for (int t = tid; t < nbt; t += kParseThreads) {
-                const int x = stateList[t];
-                const unsigned f = F[x - base];
-                const int j = probe_next(info, okbits, nzw, ntiles, base, x);
-                const int d = patched_cand(cand, &ps, npatch, j);
-                const int fwd = (int)info[j - base] - 1;
-                int limit = j - x;                                     // pending literals (encoder.cpp:404)
-                { const int room = j - d + g.pre; if (room < limit) limit = room; }
-                if (limit > kMaxMatch) limit = kMaxMatch;
-                const int lb = back_upto(chunk0 + j, chunk0 + j - d, limit, strm);
-                const int ms = j - lb;
-                // matches of 32 bytes or more were measured exactly by the orbit chase, which left the exact next
-                // state in F: their length is the distance from the match start to that state
-                int m = needs_exact(fwd, j - x) ? (int)f - ms : fwd + lb;
-                if (m > kMaxMatch) m = kMaxMatch;
-                tokA[outBase + t] = (uint32_t)ms | ((uint32_t)m << 16);
-                tokD[outBase + t] = (uint16_t)d;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            ps.ntok += ps.npre + (int)wsum[31];
-            const int finalB = ps.finalB;
-            const int newpos = finalB > E ? finalB : E;
-            ps.fixS = -1; ps.fixJ = 0x7fffffff;
-            if (finalB < E && newpos < t0 && ps.nexcl < 4) {       // next batch start not covered by a match: never inserted
-                ps.excl[ps.nexcl++] = newpos;
-                ps.fixS = newpos;
-            }
-            ps.pos = newpos;
-        }
-        __syncthreads();
-        PHASE_MARK(7);
-    }
-    __syncthreads();
-
-    // ---- histograms (GetFrequencies, encoder.cpp:442-471) ----
-    // Matches are counted token-parallel and mark the positions they cover in a bitmap; literals are then counted
-    // position-parallel (coalesced window reads) into per-warp private histograms.
-    unsigned* hist = reinterpret_cast<unsigned*>(info);            // per-warp private copies (batch arrays are dead)
-    unsigned* cov = hist + nwarps * kHistStride;                   // bit per position: covered by a match
-    unsigned* litBase = cov + kMaxChunk / 32;                      // literals before each 32-position word
-    uint8_t* lits = job.info + (size_t)slot * job.chunk;           // the block's literal bytes in order (the info row is dead)
-    for (int i = tid; i < nwarps * kHistStride + kMaxChunk / 32; i += kParseThreads) hist[i] = 0;
-    __syncthreads();
-    {
-        const int ntok = ps.ntok;
-        unsigned* myh = hist + warp * kHistStride;
-        for (int k = tid; k < ntok; k += kParseThreads) {
-            const uint32_t t = tokA[k];
-            const int ms = (int)(t & 0xFFFF), ln = (int)(t >> 16), me = ms + ln - 1;
-            int eb, ev;
-            atomicAdd(&myh[len_symbol(ln, eb, ev)], 1u);
-            atomicAdd(&myh[286 + dist_symbol(tokD[k], eb, ev)], 1u);
-            for (int w = ms >> 5; w <= (me >> 5); ++w) {
-                unsigned m = 0xffffffffu;
-                if (w == (ms >> 5)) m &= 0xffffffffu << (ms & 31);
-                if (w == (me >> 5)) m &= 0xffffffffu >> (31 - (me & 31));
-                atomicOr(&cov[w], m);
-            }
-        }
-        __syncthreads();
-        // positions at or beyond the block's end are not literals
-        for (int w = tid; w < kMaxChunk / 32; w += kParseThreads) {
-            const int lo = w * 32;
-            if (lo + 32 > g.body) cov[w] |= lo >= g.body ? 0xffffffffu : (0xffffffffu << (g.body - lo));
-        }
-        __syncthreads();
-        {   // exclusive scan of the literal counts per word (four consecutive words per thread)
-            static_assert(kParseThreads * 4 == kMaxChunk / 32, "one pass over the coverage bitmap");
-            const int w0 = tid * 4;
-            unsigned c[4], sum = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { c[k] = (unsigned)__popc(~cov[w0 + k]); sum += c[k]; }
-            unsigned inc = sum;
-            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-            if (lane == 31) wsum[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                unsigned v = lane < nwarps ? wsum[lane] : 0u;
-                for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-                wsum[lane] = v;
-            }
-            __syncthreads();
-            unsigned before = (warp ? wsum[warp - 1] : 0u) + inc - sum;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { litBase[w0 + k] = before; before += c[k]; }
-            if (tid == kParseThreads - 1) job.state[slot].nlit = before;
-        }
-        __syncthreads();
-        // literals: histogram, and the literal bytes written out in order for K-EMIT (position -> rank through the
-        // coverage bitmap).  A 4-byte aligned chunk reads whole words (a word that holds a valid byte never leaves its page).
-        const bool srcAligned = (reinterpret_cast<uintptr_t>(chunk0) & 3) == 0;
-        for (int pos = tid * 4; pos < g.body; pos += 4 * kParseThreads) {
-            const unsigned cword = cov[pos >> 5];
-            const unsigned cw = (cword >> (pos & 31)) & 0xFu;
-            if (cw == 0xFu) continue;                                   // four covered positions: nothing to count
-            const unsigned v = srcAligned ? __ldg(reinterpret_cast<const unsigned*>(chunk0 + pos)) : gload4(chunk0 + pos, strm.lo, strm.hi);
-            unsigned rank = litBase[pos >> 5] + (unsigned)__popc(~cword & ((1u << (pos & 31)) - 1u));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (!((cw >> k) & 1u)) { const unsigned b = (v >> (8 * k)) & 0xFFu; atomicAdd(&myh[b], 1u); lits[rank++] = (uint8_t)b; }
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < 316; i += kParseThreads) {
-        unsigned s = 0;
-        for (int w = 0; w < nwarps; ++w) s += hist[w * kHistStride + i];
-        if (i == 256) s += 1;                                       // end-of-block (encoder.cpp:470)
-        job.hist[(size_t)slot * kHistStride + i] = s;
-    }
-    if (tid == 0) job.state[slot].ntok = ps.ntok;
-    PHASE_MARK(8);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1148,25 +404,25 @@ __global__ void __launch_bounds__(kParseThreads, 2) k_parse(Job job)
 //      literals, encoder.cpp:404-416).
 // After the last batch: histograms and the literal stream for K-EMIT, as before.
 // ------------------------------------------------------------------------------------------------
-constexpr int kLzThreads = 512;
+constexpr int kLzThreads = 384;                           // three CTAs per SM: the serial parts of one overlap the parallel parts of the others
 constexpr int kLzWarps = kLzThreads / 32;
-constexpr int kLzBack = kPreCap;                          // bytes kept before the batch's first probed position
+constexpr int kSub = 4 * 4 * kLzThreads;                  // states per sub-batch (tile-aligned base up to 95 below its first position): 6144
+constexpr int kLzBack = kPreCap;                          // bytes kept before the sub-batch's first probed position
 constexpr int kLzAhead = 304;                             // bytes kept behind its last one (258 + 8-byte loads + slack)
-constexpr int kLzWin = 32 + kLzBack + kBatch + kLzAhead + 16;
+constexpr int kLzWin = 32 + kLzBack + kSub + kLzAhead + 16;
 static_assert(kLzWin % 16 == 0 && kLzWin < 65536, "window offsets are kept in 16 bits");
-constexpr int kSub = 8192;                                // states per sub-batch (tile-aligned base up to 95 below its first position)
 constexpr int kSubTiles = kSub / 32;
 constexpr int kSubWords = kSubTiles + 5;
 constexpr int kSegStates = 64;                            // states per lane in the speculative pass
 constexpr int kChains = kSub / kSegStates;
 constexpr int kChaseWarps = kChains / 32;
-static_assert(kChains % 32 == 0 && kChaseWarps <= kLzWarps && kSubTiles <= kLzThreads && kSub % (4 * kLzThreads) == 0, "geometry");
+static_assert(kChains % 32 == 0 && kChaseWarps <= 4 && kChaseWarps <= kLzWarps && kSubTiles <= kLzThreads && kSub % (4 * kLzThreads) == 0, "geometry");
 constexpr int kLzQueue = 32 + 128;
 constexpr int kExCap = 256;                               // exactly measured long matches remembered per sub-batch
 constexpr int kLzScratch = kLzWarps * kLzQueue * 4;       // phase A: long-compare queues; afterwards: bitmaps, nzw, state list
 static_assert(4 * kSubWords * 4 + 544 + (kSub / 4 + 40) * 2 <= kLzScratch, "bitmaps + nzw + state list fit the queue space");
 constexpr int kLzSmem = kLzWin + (kSub + 64) + (kSub + 64) * 2 + kLzScratch;
-static_assert(2 * (kLzSmem + 2048) <= 200 * 1024, "two K-LZ CTAs per SM, with room left for a neighbour kernel");
+static_assert(3 * (kLzSmem + 2048) <= 227 * 1024, "three K-LZ CTAs per SM");
 
 struct LzShared {
     int pos;            // start of the next FirstPass batch
@@ -1369,7 +625,7 @@ __device__ __forceinline__ unsigned lz_lookup(const unsigned* exList, int exN, i
     return nb;
 }
 
-__global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int useSpec)
+__global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int useSpec)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* win = smem;
@@ -1390,7 +646,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
     __shared__ uint16_t stopT[kChains];              // where the chain left its segment (kind 3)
     __shared__ uint16_t linkArr[kChains];            // state where the link joined the chain, 0xFFFF = it did not
     __shared__ uint16_t segMp[kChains];              // first state of the chain that belongs to the orbit, 0xFFFF = none
-    __shared__ unsigned k3Mask[kChaseWarps], lkMask[kChaseWarps], linkedW[kChaseWarps];
+    __shared__ unsigned k3Mask[4], lkMask[4], linkedW[4];
     __shared__ unsigned grpMin[kSubWords / 32 + 2];
 
     const unsigned slot = blockIdx.x;
@@ -1406,6 +662,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
 
     if (tid == 0) {
         ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npend = 0; ps.exN = 0; ps.err = 0;
+        for (int w = 0; w < 4; ++w) { k3Mask[w] = 0; lkMask[w] = 0; }
         mbar_init(&mbar, 1);
     }
     __syncthreads();
@@ -1418,73 +675,75 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
         if (pos >= t0) break;
         int E = pos + kBatch; if (E > t0) E = t0;
         const int B0 = pos + 1;                          // FirstPass: backRefEnd = j = startPos + 1
-        // ---- window of the batch: position i lives at win[wb + i]; shared and global 16-byte phases agree ----
-        const int off0 = B0 - kLzBack;
-        const int wb = 16 + ((phase + off0) & 15) - off0;
-        int lo = off0; if (lo < -g.pre) lo = -g.pre;
-        int hi = E + kLzAhead - 16; if (hi > g.n) hi = g.n;
-        bool tmaIssued = false;
-        {
-            const int s_lo = wb + lo, s_hi = wb + hi;
-            const int a_lo = (s_lo + 15) & ~15, a_hi = s_hi & ~15;
-            tmaIssued = useTma && a_lo < a_hi;
-            if (tmaIssued) {
-                if (tid == 0) {
-                    // the window was read through the generic proxy by the previous batch: order those accesses before
-                    // the asynchronous writes
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    const unsigned bytes = (unsigned)(a_hi - a_lo);
-                    mbar_expect_tx(&mbar, bytes);
-                    const uint8_t* gsrc = chunk0 + (a_lo - wb);
-                    for (unsigned o = 0; o < bytes; o += 16384u) {
-                        const unsigned len = bytes - o < 16384u ? bytes - o : 16384u;
-                        bulk_g2s(win + a_lo + o, gsrc + o, len, &mbar);
-                    }
-                }
-                for (int s = s_lo + tid; s < a_lo; s += kLzThreads) win[s] = chunk0[s - wb];
-                for (int s = a_hi + tid; s < s_hi; s += kLzThreads) win[s] = chunk0[s - wb];
-                for (int s = s_hi + tid; s < s_hi + 16; s += kLzThreads) win[s] = 0;
-            } else {
-                load_window(win, wb, chunk0, lo, hi, hi + 16);
-            }
-        }
-        if (tmaIssued) {
-            unsigned spins = 0;
-            while (!mbar_try_wait(&mbar, parity)) { if (++spins > (1u << 18)) { ps.err = 1; break; } }
-            parity ^= 1u;
-        }
-        __syncthreads();
         const int nexcl = ps.nexcl;
         const int ex0 = nexcl > 0 ? ps.excl[0] : -1, ex1 = nexcl > 1 ? ps.excl[1] : -1, ex2 = nexcl > 2 ? ps.excl[2] : -1;
-
-        // ---- first probe of the batch: j == backRefEnd, no backward room (encoder.cpp:384-386) ----
-        if (warp == 0) {
-            int b = B0;
-            if (B0 < E) {
-                const int d = lz_effective_cand(cand, &ps, B0, (int)__ldg(cand + B0));     // the excluded start may be B0's own candidate
-                const int inf = info_of_w(win, wb + B0, d, B0 - d + g.pre);
-                if (inf >= 5) {
-                    int fwd = inf - 1, lbNone;
-                    if (fwd >= kCapLen) coop_lengths_w(win, wb + B0, wb + B0 - d, lane, false, fwd, lbNone);
-                    const int tk = ps.ntok;
-                    if (lane == 0) { tokA[tk] = (uint32_t)B0 | ((uint32_t)fwd << 16); tokD[tk] = (uint16_t)d; ps.ntok = tk + 1; }
-                    b = B0 + fwd;
-                }
-            }
-            if (lane == 0) ps.b = b;
-        }
+        if (tid == 0) ps.b = B0;
         __syncthreads();
 
         // ---- sub-batches ----
+        bool firstSub = true;
         for (int s0 = B0; s0 < E; ) {
-            const int bIn = ps.b;
+            int s1n = s0 + kSub; if (s1n > E) s1n = E;
+            if (!firstSub && ps.b >= s1n) { s0 = s1n; continue; }     // a long match jumped over the whole sub-batch
+            // ---- window of the sub-batch: position i lives at win[wb + i]; shared and global 16-byte phases agree ----
+            const int off0 = s0 - kLzBack;
+            const int wb = 16 + ((phase + off0) & 15) - off0;
+            int lo = off0; if (lo < -g.pre) lo = -g.pre;
+            int hi = s1n + kLzAhead - 16; if (hi > g.n) hi = g.n;
+            bool tmaIssued = false;
             {
-                int s1n = s0 + kSub; if (s1n > E) s1n = E;
-                if (bIn >= s1n) { s0 = s1n; continue; }            // a long match jumped over the whole sub-batch
+                const int s_lo = wb + lo, s_hi = wb + hi;
+                const int a_lo = (s_lo + 15) & ~15, a_hi = s_hi & ~15;
+                tmaIssued = useTma && a_lo < a_hi;
+                if (tmaIssued) {
+                    if (tid == 0) {
+                        // the window was read through the generic proxy by the previous sub-batch: order those accesses before
+                        // the asynchronous writes
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        const unsigned bytes = (unsigned)(a_hi - a_lo);
+                        mbar_expect_tx(&mbar, bytes);
+                        const uint8_t* gsrc = chunk0 + (a_lo - wb);
+                        for (unsigned o = 0; o < bytes; o += 16384u) {
+                            const unsigned len = bytes - o < 16384u ? bytes - o : 16384u;
+                            bulk_g2s(win + a_lo + o, gsrc + o, len, &mbar);
+                        }
+                    }
+                    for (int q = s_lo + tid; q < a_lo; q += kLzThreads) win[q] = chunk0[q - wb];
+                    for (int q = a_hi + tid; q < s_hi; q += kLzThreads) win[q] = chunk0[q - wb];
+                    for (int q = s_hi + tid; q < s_hi + 16; q += kLzThreads) win[q] = 0;
+                } else {
+                    load_window(win, wb, chunk0, lo, hi, hi + 16);
+                }
             }
+            if (tmaIssued) {
+                unsigned spins = 0;
+                while (!mbar_try_wait(&mbar, parity)) { if (++spins > (1u << 18)) { ps.err = 1; break; } }
+                parity ^= 1u;
+            }
+            __syncthreads();
+            if (firstSub) {
+                // ---- first probe of the batch: j == backRefEnd, no backward room (encoder.cpp:384-386) ----
+                firstSub = false;
+                if (warp == 0) {
+                    int b = B0;
+                    const int d = lz_effective_cand(cand, &ps, B0, (int)__ldg(cand + B0));     // the excluded start may be B0's own candidate
+                    const int inf = info_of_w(win, wb + B0, d, B0 - d + g.pre);
+                    if (inf >= 5) {
+                        int fwd = inf - 1, lbNone;
+                        if (fwd >= kCapLen) coop_lengths_w(win, wb + B0, wb + B0 - d, lane, false, fwd, lbNone);
+                        const int tk = ps.ntok;
+                        if (lane == 0) { tokA[tk] = (uint32_t)B0 | ((uint32_t)fwd << 16); tokD[tk] = (uint16_t)d; ps.ntok = tk + 1; }
+                        b = B0 + fwd;
+                    }
+                    if (lane == 0) ps.b = b;
+                }
+                __syncthreads();
+                if (ps.b >= s1n) { __syncthreads(); s0 = s1n; continue; }
+            }
+            const int bIn = ps.b;
             int lowb = bIn > s0 - 64 ? bIn : s0 - 64; if (lowb > s0) lowb = s0;
             const int base = lowb & ~31;
-            int s1 = base + kSub; if (s1 > E) s1 = E;               // the arrays hold kSub states from the tile-aligned base
+            int s1 = base + kSub; if (s1 > s1n) s1 = s1n;           // the arrays hold kSub states from the tile-aligned base
             const int ntiles = (s1 - base + 31) >> 5;
             const int lim = ntiles * 32;
 
@@ -1594,7 +853,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
             // the queues are drained: their space now holds the bitmaps, nzw and the state list
             for (int t = tid; t < kSubWords; t += kLzThreads) { Sb[t] = 0; Tb[t] = 0; Lb[t] = 0; }
             if (tid < kChains) segMp[tid] = 0xFFFFu;
-            if (tid < kChaseWarps) linkedW[tid] = 0;
+            if (tid < 4) linkedW[tid] = 0;
             if (tid < ps.npend && tid < 8) {                      // positions whose candidate changes with the parse
                 const int pj = ps.pendJ[tid];
                 const int pd = lz_effective_cand(cand, &ps, pj, (int)dist[pj - base]);
@@ -1720,7 +979,6 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
                     int endsAt = -1;                                       // orbit state with succ == 0 that ended the walk (it yields no token)
                     if (alive && cur < s1) {
                         // bit t of okRun: segment t is entered through its link provided segment t-1's chain is the orbit and leaves into it
-                        static_assert(kChaseWarps == 4, "okRun is kept as two 64-bit words");
                         const unsigned long long k3lo = k3Mask[0] | ((unsigned long long)k3Mask[1] << 32), k3hi = k3Mask[2] | ((unsigned long long)k3Mask[3] << 32);
                         const unsigned long long lklo = lkMask[0] | ((unsigned long long)lkMask[1] << 32), lkhi = lkMask[2] | ((unsigned long long)lkMask[3] << 32);
                         const unsigned long long okLo = (k3lo << 1) & lklo, okHi = ((k3hi << 1) | (k3lo >> 63)) & lkhi;
@@ -1939,12 +1197,12 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
             if (lo + 32 > g.body) cov[w] |= lo >= g.body ? 0xffffffffu : (0xffffffffu << (g.body - lo));
         }
         __syncthreads();
-        {   // exclusive scan of the literal counts per word (four consecutive words per thread)
-            static_assert(kLzThreads * 4 == kMaxChunk / 32, "one pass over the coverage bitmap");
-            const int w0 = tid * 4;
-            unsigned c[4], sum = 0;
+        {   // exclusive scan of the literal counts per word (kWordsPerThread consecutive words per thread)
+            constexpr int kWordsPerThread = (kMaxChunk / 32 + kLzThreads - 1) / kLzThreads;
+            const int w0 = tid * kWordsPerThread;
+            unsigned c[kWordsPerThread], sum = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { c[k] = (unsigned)__popc(~cov[w0 + k]); sum += c[k]; }
+            for (int k = 0; k < kWordsPerThread; ++k) { c[k] = w0 + k < kMaxChunk / 32 ? (unsigned)__popc(~cov[w0 + k]) : 0u; sum += c[k]; }
             unsigned inc = sum;
             for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
             if (lane == 31) wsum[warp] = inc;
@@ -1957,7 +1215,7 @@ __global__ void __launch_bounds__(kLzThreads, 2) k_lz(Job job, int useTma, int u
             __syncthreads();
             unsigned before = (warp ? wsum[warp - 1] : 0u) + inc - sum;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { litBase[w0 + k] = before; before += c[k]; }
+            for (int k = 0; k < kWordsPerThread; ++k) if (w0 + k < kMaxChunk / 32) { litBase[w0 + k] = before; before += c[k]; }
             if (tid == kLzThreads - 1) job.state[slot].nlit = before;
         }
         __syncthreads();
@@ -3031,6 +2289,9 @@ constexpr int kCkSlice = 256;
 // Each thread owns a 256-byte slice: Adler partial sums with dp4a (s1 = sum d, s2 = sum (len-i) d_i), raw CRC
 // with slicing-by-4, then the slice CRC is multiplied by x^(8 * bytes after the slice) and everything is
 // XOR-/sum-reduced.  The chunk's standard CRC adds the propagated 0xFFFFFFFF preset and the final inversion.
+// kWant: bit 0 Adler-32, bit 1 CRC-32 (the Zlib trailer needs only the first, the Gzip trailer only the second; the CRC's
+// table look-ups are the expensive half)
+template <int kWant>
 __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
 {
     __shared__ uint32_t tab[4][256];
@@ -3039,8 +2300,10 @@ __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int k = 0; k < 4; ++k) tab[k][tid] = c_crcTable[k][tid];
-    __syncthreads();
+    if (kWant & 2) {
+        for (int k = 0; k < 4; ++k) tab[k][tid] = c_crcTable[k][tid];
+        __syncthreads();
+    }
     const uint8_t* p = job.src + g.off;
     const int lo = tid * kCkSlice;
     int hi = lo + kCkSlice; if (hi > g.n) hi = g.n;
@@ -3051,11 +2314,15 @@ __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
         int i = 0;
         auto word = [&](unsigned w, int remaining) {                  // 4 bytes at offset i, `remaining` = len - i
             // sum_{k<4} (remaining - k) d_k = remaining * sum d_k - (0 d0 + 1 d1 + 2 d2 + 3 d3)
-            const unsigned sum = __dp4a(w, 0x01010101u, 0u);
-            b += (unsigned)remaining * sum - __dp4a(w, 0x03020100u, 0u);
-            a += sum;
-            crc ^= w;
-            crc = tab[3][crc & 0xFF] ^ tab[2][(crc >> 8) & 0xFF] ^ tab[1][(crc >> 16) & 0xFF] ^ tab[0][crc >> 24];
+            if (kWant & 1) {
+                const unsigned sum = __dp4a(w, 0x01010101u, 0u);
+                b += (unsigned)remaining * sum - __dp4a(w, 0x03020100u, 0u);
+                a += sum;
+            }
+            if (kWant & 2) {
+                crc ^= w;
+                crc = tab[3][crc & 0xFF] ^ tab[2][(crc >> 8) & 0xFF] ^ tab[1][(crc >> 16) & 0xFF] ^ tab[0][crc >> 24];
+            }
         };
         const uint8_t* q = p + lo;
         if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
@@ -3068,12 +2335,12 @@ __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
         }
         for (; i < len; ++i) {
             const unsigned v = q[i];
-            a += v; b += (unsigned)(len - i) * v;
-            crc = (crc >> 8) ^ tab[0][(crc ^ v) & 0xFF];
+            if (kWant & 1) { a += v; b += (unsigned)(len - i) * v; }
+            if (kWant & 2) crc = (crc >> 8) ^ tab[0][(crc ^ v) & 0xFF];
         }
         const int after = g.n - hi;
         s1 = a; s2 = (unsigned long long)b + (unsigned long long)after * a;      // b_chunk = sum (n - i) d[i]
-        crc = gf2_mulmod(gf2_mulmod(crc, c_powL[after >> 8]), c_pow1[after & 255]);
+        if (kWant & 2) crc = gf2_mulmod(gf2_mulmod(crc, c_powL[after >> 8]), c_pow1[after & 255]);
     }
     for (int o = 16; o; o >>= 1) {
         s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
@@ -3087,8 +2354,10 @@ __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
         uint32_t* ck = job.ck + 2 * (job.first_chunk + slot);
         ck[0] = (uint32_t)(((b % 65521ull) << 16) | (a % 65521ull));
         // standard CRC = raw(M) ^ (0xFFFFFFFF * x^(8n)) ^ 0xFFFFFFFF
-        const uint32_t init = gf2_mulmod(gf2_mulmod(0xFFFFFFFFu, c_powL[g.n >> 8]), c_pow1[g.n & 255]);
-        ck[1] = c ^ init ^ 0xFFFFFFFFu;
+        if (kWant & 2) {
+            const uint32_t init = gf2_mulmod(gf2_mulmod(0xFFFFFFFFu, c_powL[g.n >> 8]), c_pow1[g.n & 255]);
+            ck[1] = c ^ init ^ 0xFFFFFFFFu;
+        } else ck[1] = 0;
     }
 }
 
@@ -3097,26 +2366,11 @@ __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
 // ------------------------------------------------------------------------------------------------
 // host side: launch wrappers and checksum folds
 // ------------------------------------------------------------------------------------------------
-#ifdef ZZ_PHASE_TIMING
-void dump_phase_cycles()
-{
-    unsigned long long h[16];
-    cudaMemcpyFromSymbol(h, g_phaseCycles, sizeof h);
-    static const char* names[9] = { "window", "firstprobe", "A info", "patch+bits", "B succ", "C walk", "D tokens", "batch end", "hist" };
-    unsigned long long tot = 0; for (int i = 0; i < 9; ++i) tot += h[i];
-    for (int i = 0; i < 9; ++i) fprintf(stderr, "phase %-10s %6.2f%%  %llu\n", names[i], 100.0 * h[i] / (tot ? tot : 1), h[i]);
-
-    memset(h, 0, sizeof h); cudaMemcpyToSymbol(g_phaseCycles, h, sizeof h);
-}
-#endif
-
 cudaError_t configure_kernels()
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, kParseSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_huffman_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, kHuffLSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_emit2, cudaFuncAttributeMaxDynamicSharedMemorySize, kEmit2Smem); if (e) return e;
-    e = cudaFuncSetAttribute(k_info, cudaFuncAttributeMaxDynamicSharedMemorySize, kInfoSmem); if (e) return e;
     e = cudaFuncSetAttribute(k_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, kLzSmem); if (e) return e;
     static uint32_t tab[4][256];
     uint32_t powL[257], pow1[256];
@@ -3153,22 +2407,6 @@ int launch_candidates(const Job& job, cudaStream_t s)
     return 1;
 }
 
-int launch_info(const Job& job, cudaStream_t s)
-{
-    const int ppc = (int)((job.chunk + kInfoPiece - 1) / kInfoPiece);
-    k_info<<<job.nchunks * (unsigned)ppc, kInfoThreads, kInfoSmem, s>>>(job, ppc);
-    return 1;
-}
-
-int launch_parse(const Job& job, cudaStream_t s)
-{
-#ifdef ZZ_PHASE_TIMING
-    cudaStreamSynchronize(s); dump_phase_cycles();
-#endif
-    k_parse<<<job.nchunks, kParseThreads, kParseSmem, s>>>(job);
-    return 1;
-}
-
 int launch_huffman(const Job& job, cudaStream_t s)
 {
     // resident warps of the warp-per-chunk kernel: 13 CTAs of 4 warps per SM (17 KiB of shared memory each)
@@ -3184,18 +2422,14 @@ int launch_offsets(const Job& job, cudaStream_t s)
 }
 
 // A/B switches of kernel variants (zzgpu_set_option); none changes the produced bytes.
-static int g_optLz = 1;          // 1: fused K-LZ, 0: K-INFO + K-MATCH as separate kernels
 static int g_optTma = 1;         // K-LZ window: 1 = cp.async.bulk (TMA) + mbarrier, 0 = LDG.128 -> STS
 static int g_optSpec = 1;        // K-LZ walk: 1 = speculative per-lane chains merged by the true walk, 0 = the true walk alone
 bool set_kernel_option(const char* name, int value)
 {
-    if (!strcmp(name, "lz")) { g_optLz = value ? 1 : 0; return true; }
     if (!strcmp(name, "tma")) { g_optTma = value ? 1 : 0; return true; }
     if (!strcmp(name, "spec")) { g_optSpec = value ? 1 : 0; return true; }
     return false;
 }
-bool use_fused_lz() { return g_optLz != 0; }
-
 int launch_lz(const Job& job, cudaStream_t s)
 {
     k_lz<<<job.nchunks, kLzThreads, kLzSmem, s>>>(job, g_optTma, g_optSpec);
@@ -3210,7 +2444,10 @@ int launch_emit(const Job& job, cudaStream_t s)
 
 int launch_checksums(const Job& job, cudaStream_t s)
 {
-    k_checksums<<<job.nchunks, kCkThreads, 0, s>>>(job);
+    const int want = job.want_checksums & 3;
+    if (want == 1) k_checksums<1><<<job.nchunks, kCkThreads, 0, s>>>(job);
+    else if (want == 2) k_checksums<2><<<job.nchunks, kCkThreads, 0, s>>>(job);
+    else k_checksums<3><<<job.nchunks, kCkThreads, 0, s>>>(job);
     return 1;
 }
 

@@ -62,10 +62,7 @@ struct Job {
 
 // launch wrappers (zz_kernels.cu); each returns the number of kernels launched
 int launch_candidates(const Job& job, cudaStream_t s);
-int launch_info(const Job& job, cudaStream_t s);
-int launch_parse(const Job& job, cudaStream_t s);
-int launch_lz(const Job& job, cudaStream_t s);        // K-INFO + K-MATCH fused
-bool use_fused_lz();
+int launch_lz(const Job& job, cudaStream_t s);        // match info + greedy parse, fused
 int launch_huffman(const Job& job, cudaStream_t s);
 int launch_offsets(const Job& job, cudaStream_t s);
 int launch_emit(const Job& job, cudaStream_t s);
