@@ -89,7 +89,7 @@ def test_callback_api(zz, golden):
 def test_callback_api_streams(zz, oracle):
     """N2 (zzflate.cpp:197-222 on the GPU): the callback receives the first data while later pieces of the input have
     not even been copied to the device, and nothing of the size of the stream is buffered: 600 MiB of pageable input
-    are cut into 4 pieces (H2D -> kernels -> D2H), the first slice must arrive before the last piece's H2D is done."""
+    are cut into pieces (H2D -> kernels -> D2H), the first slice must arrive before the last piece's H2D is done."""
     from zzflate_b200 import synth, _lib
     n = 600 << 20
     data = synth.markov_text(n, seg0=5)
@@ -112,7 +112,7 @@ def test_callback_api_streams(zz, oracle):
     zz.ZzFlateEncodeToCallback(data, zz.Config(zz.Format.Zlib, 2, False), sink)
     assert ok[0] and pos[0] == n and d.eof
     done, pieces = lib.zzgpu_get_counter(b"sink_first_h2d_done"), lib.zzgpu_get_counter(b"sink_pieces")
-    assert pieces == 4 and 1 <= done < pieces, (done, pieces)
+    assert pieces >= 4 and 1 <= done < pieces, (done, pieces)
 
 
 def test_hold_and_fetch(zz, oracle, golden):

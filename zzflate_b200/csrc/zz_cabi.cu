@@ -340,6 +340,10 @@ int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final,
                                 (uint32_t)std::min<uint64_t>(c.slots, lastChunk - first));
         cudaStream_t st = c.stream;
         rc = markStage(c, -1, st); if (rc) return rc;
+        if (level == 0) {                                   // every size is known beforehand: one kernel does it all
+            launches += launch_stored(job, st); rc = markStage(c, ZZGPU_STAGE_EMIT, st); if (rc) return rc;
+            continue;
+        }
         if (level >= 2) {
             launches += launch_candidates(job, st); rc = markStage(c, ZZGPU_STAGE_CAND, st); if (rc) return rc;
             launches += launch_lz(job, st); rc = markStage(c, ZZGPU_STAGE_LZ, st); if (rc) return rc;
@@ -373,8 +377,8 @@ std::vector<uint64_t> pieceSchedule(uint64_t nchunks, uint32_t chunk)
 {
     // Every piece costs one launch of each kernel (the Huffman kernel alone is ~0.4 ms however few chunks it gets), so
     // pieces are few.  Their sizes are multiples of 888 chunks = 148 SMs x 6 resident K-CAND warps, which is also a
-    // whole number of waves of K-MATCH / K-EMIT (296 CTAs) and K-INFO (148 chunks): 888, 1776, 3552, then 4440 chunks,
-    // and the last <= 7104 chunks in two pieces (about 60/40) so that the final D2H is short.
+    // whole number of waves of K-LZ (444 CTAs) and K-EMIT (296 CTAs): 888, 1776, 3552, then 4440 chunks, and the last
+    // <= 7104 chunks in up to three shrinking pieces so that the final D2H is short.
     std::vector<uint64_t> ends;
     if (nchunks * chunk < kPipelineMin) { ends.push_back(nchunks); return ends; }
     const uint64_t unit = 888, big = 5 * unit;
@@ -383,7 +387,9 @@ std::vector<uint64_t> pieceSchedule(uint64_t nchunks, uint32_t chunk)
         pos += size; ends.push_back(pos);
         size = size < 4 * unit ? size * 2 : big;
     }
-    const uint64_t rem = nchunks - pos;
+    // the tail in pieces of about 50 / 30 / 20 %: what follows the last H2D (that piece's kernels and its D2H) is short
+    uint64_t rem = nchunks - pos;
+    if (rem > 3 * unit) { uint64_t take = ((rem / 2 + unit / 2) / unit) * unit; if (take == 0 || take >= rem) take = rem / 2; pos += take; ends.push_back(pos); rem = nchunks - pos; }
     if (rem > 2 * unit) { uint64_t take = ((rem * 3 / 5 + unit / 2) / unit) * unit; if (take == 0 || take >= rem) take = rem / 2; pos += take; ends.push_back(pos); }
     if (pos < nchunks) ends.push_back(nchunks);
     return ends;

@@ -20,6 +20,7 @@
 //                           UncompressedFallback / WriteUncompressedBlock; encoder.cpp:305-317,482-502), symbol-parallel
 //   K-FIXED  k_fixed, k_gather   level 1: WriteBlockFixedHuff (encoder.cpp:329-373)
 //   K-CKSUM  k_checksums   per-chunk Adler-32 / CRC-32 partials (adler.cpp:17, crc.cpp:24)
+//   K-STORED k_stored      level 0: stored blocks and the checksum partials in one kernel (encoder.cpp:482-502)
 //
 // Everything is integer work; nothing here is a dense contraction, so tensor cores are not used.
 #include "zz_kernels.cuh"
@@ -1228,6 +1229,12 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
             if (cw == 0xFu) continue;                                   // four covered positions: nothing to count
             const unsigned v = srcAligned ? __ldg(reinterpret_cast<const unsigned*>(chunk0 + pos)) : gload4(chunk0 + pos, strm.lo, strm.hi);
             unsigned rank = litBase[pos >> 5] + (unsigned)__popc(~cword & ((1u << (pos & 31)) - 1u));
+            if (cw == 0u && (rank & 3u) == 0u && pos + 4 <= g.body) {   // four literals in a row at an aligned place (incompressible data): one store
+                *reinterpret_cast<unsigned*>(lits + rank) = v;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) atomicAdd(&myh[(v >> (8 * k)) & 0xFFu], 1u);
+                continue;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 if (!((cw >> k) & 1u)) { const unsigned b = (v >> (8 * k)) & 0xFFu; atomicAdd(&myh[b], 1u); lits[rank++] = (uint8_t)b; }
@@ -1812,11 +1819,11 @@ __device__ __forceinline__ void copy_g2g(uint8_t* D, const uint8_t* S, unsigned 
     const unsigned smis = (unsigned)(reinterpret_cast<uintptr_t>(S2) & 3);
     const unsigned* Sw = reinterpret_cast<const unsigned*>(S2 - smis);
     if (smis == 0) {
-#pragma unroll 4
+#pragma unroll 8
         for (unsigned i = tid; i < nfull; i += nt) Dw[i] = __ldg(Sw + i);
     } else {
         const int sh = (int)smis * 8;
-#pragma unroll 4
+#pragma unroll 8
         for (unsigned i = tid; i < nfull; i += nt) Dw[i] = __funnelshift_r(__ldg(Sw + i), __ldg(Sw + i + 1), sh);
     }
     const unsigned done = head + nfull * 4;
@@ -2292,13 +2299,11 @@ constexpr int kCkSlice = 256;
 // kWant: bit 0 Adler-32, bit 1 CRC-32 (the Zlib trailer needs only the first, the Gzip trailer only the second; the CRC's
 // table look-ups are the expensive half)
 template <int kWant>
-__global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
+__device__ __forceinline__ void checksum_chunk(const Job& job, unsigned slot, const Geom& g)
 {
     __shared__ uint32_t tab[4][256];
     __shared__ unsigned long long redA[8], redB[8];
     __shared__ uint32_t redC[8];
-    const unsigned slot = blockIdx.x;
-    const Geom g = chunk_geom(job, slot);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (kWant & 2) {
         for (int k = 0; k < 4; ++k) tab[k][tid] = c_crcTable[k][tid];
@@ -2359,6 +2364,56 @@ __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
             ck[1] = c ^ init ^ 0xFFFFFFFFu;
         } else ck[1] = 0;
     }
+}
+
+template <int kWant>
+__global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
+{
+    const unsigned slot = blockIdx.x;
+    checksum_chunk<kWant>(job, slot, chunk_geom(job, slot));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-STORED (level 0) : WriteUncompressedBlock (encoder.cpp:482-502) for every chunk plus, in the same kernel, the
+// chunk's checksum partials.  At level 0 every size is known beforehand (5 bytes per block of <= 65535 bytes, the
+// aligning 1-byte block behind every non-final chunk), so chunk c starts at c * size(full chunk): no
+// Huffman stage, no offset scan, and the input is read from HBM once (the checksum pass finds it in cache).
+// ------------------------------------------------------------------------------------------------
+template <int kWant>
+__global__ void __launch_bounds__(kCkThreads) k_stored(Job job)
+{
+    const unsigned slot = blockIdx.x;
+    const Geom g = chunk_geom(job, slot);
+    const int tid = threadIdx.x;
+    const unsigned long long perFull = (unsigned long long)stored_size((int)job.chunk - 1) + 6ull;
+    const unsigned long long off = (job.first_chunk + slot) * perFull;
+    const uint32_t bytes = stored_size(g.body) + (g.final ? 0u : 6u);
+    if (off + bytes > job.cap) {                                      // never write past the caller's buffer
+        if (tid == 0) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 1ull);
+        return;
+    }
+    const uint8_t* chunk0 = job.src + g.off;
+    uint8_t* Dst = job.dst + off;
+    int written = 0; unsigned o = 0;
+    while (written < g.body) {
+        const int len = min(g.body - written, 0xFFFF);
+        if (tid == 0) {
+            Dst[o] = (uint8_t)((g.final && written + len == g.body) ? 1 : 0);
+            Dst[o + 1] = (uint8_t)len; Dst[o + 2] = (uint8_t)(len >> 8);
+            Dst[o + 3] = (uint8_t)~len; Dst[o + 4] = (uint8_t)((~len) >> 8);
+        }
+        copy_g2g(Dst + o + 5, chunk0 + written, (unsigned)len);
+        o += 5 + len; written += len;
+    }
+    if (!g.final && tid == 0) {
+        Dst[o] = 0; Dst[o + 1] = 1; Dst[o + 2] = 0; Dst[o + 3] = 0xFE; Dst[o + 4] = 0xFF; Dst[o + 5] = chunk0[g.n - 1];
+    }
+    if (tid == 0) {
+        ChunkState& st = job.state[slot];
+        st.ntok = 0; st.block_type = 0; st.hdr_bits = 0; st.total_bits = 0; st.out_bytes = bytes; st.out_off = off;
+        if (slot == job.nchunks - 1) { job.total[0] = off + bytes; job.total[3] += job.nchunks; }
+    }
+    if (kWant) checksum_chunk<(kWant ? kWant : 3)>(job, slot, g);
 }
 
 }  // namespace
@@ -2448,6 +2503,17 @@ int launch_checksums(const Job& job, cudaStream_t s)
     if (want == 1) k_checksums<1><<<job.nchunks, kCkThreads, 0, s>>>(job);
     else if (want == 2) k_checksums<2><<<job.nchunks, kCkThreads, 0, s>>>(job);
     else k_checksums<3><<<job.nchunks, kCkThreads, 0, s>>>(job);
+    return 1;
+}
+
+int launch_stored(const Job& job, cudaStream_t s)
+{
+    switch (job.want_checksums & 3) {
+    case 0: k_stored<0><<<job.nchunks, kCkThreads, 0, s>>>(job); break;
+    case 1: k_stored<1><<<job.nchunks, kCkThreads, 0, s>>>(job); break;
+    case 2: k_stored<2><<<job.nchunks, kCkThreads, 0, s>>>(job); break;
+    default: k_stored<3><<<job.nchunks, kCkThreads, 0, s>>>(job); break;
+    }
     return 1;
 }
 

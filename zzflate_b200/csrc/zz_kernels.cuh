@@ -67,6 +67,7 @@ int launch_huffman(const Job& job, cudaStream_t s);
 int launch_offsets(const Job& job, cudaStream_t s);
 int launch_emit(const Job& job, cudaStream_t s);
 int launch_checksums(const Job& job, cudaStream_t s);
+int launch_stored(const Job& job, cudaStream_t s);    // level 0: stored blocks + checksum partials, one kernel
 int launch_fixed(const Job& job, cudaStream_t s);     // level 1: bits into the scratch slot
 int launch_gather(const Job& job, cudaStream_t s);    // level 1: scratch slot -> stream
 cudaError_t configure_kernels();
