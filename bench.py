@@ -278,6 +278,10 @@ def main():
             good = good and piece == shard[pos: pos + len(piece)].tobytes()
             pos += len(piece)
         ok["inflate_equals_input"] = bool(good and pos == nbytes and (d.eof or not final))
+        if final:
+            # second, zlib-independent judge: the library's own inflater (include/decoder.h, host code)
+            back = zz.ZzFlateDecode(got, zz.Format.Deflate, max_len=nbytes + 16, dictionary=host[:hist] if hist else None)
+            ok["decoder_h_equals_input"] = bool(back is not None and len(back) == nbytes and np.array_equal(np.frombuffer(back, dtype=np.uint8), shard))
         ok["adler32"] = bool(a0 == zlib.adler32(shard, 0))
         ok["crc32"] = bool(crc_v == zlib.crc32(shard))
         if rank == 0:

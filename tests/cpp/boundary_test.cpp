@@ -12,6 +12,7 @@
 #include "../../include/crc.h"
 #include "../../include/huffman.h"
 #include "../../include/outputbitstream.h"
+#include "../../include/decoder.h"
 
 #include <zlib.h>
 #include <algorithm>
@@ -62,6 +63,11 @@ static long testroundtrip(const std::vector<uint8_t>& in, Config config)
     size_t outLen = out.size();
     if (ZlibUncompress(out.data(), &outLen, compressed.data(), compressed.size(), config.format == Gzip) != Z_OK) return -1;
     if (outLen != in.size() || !std::equal(in.begin(), in.end(), out.begin())) return -1;
+    // and through the library's own inflater (include/decoder.h: the role zzflate/decoder.h was meant to have)
+    std::vector<uint8_t> out2(in.size() + 1);
+    size_t outLen2 = out2.size();
+    ZzFlateDecode(out2.data(), &outLen2, compressed.data(), compressed.size(), config.format);
+    if (outLen2 != in.size() || !std::equal(in.begin(), in.end(), out2.begin())) return -1;
     return (long)compressed.size();
 }
 

@@ -31,6 +31,7 @@ def test_golden_cases_identical_to_oracle_and_reference(zz, oracle, golden, leve
         want, _ = oracle.stream_chunked(data, DEFLATE, level)
         assert out == want, (case, level)
         assert zlib.decompress(out, -15) == data
+        assert zz.ZzFlateDecode(out, zz.Format.Deflate, max_len=len(data) + 16) == data          # include/decoder.h, the second judge
         assert zz.combine(1, a0, len(data)) == zlib.adler32(data) and crc == zlib.crc32(data)
         # directly against the reference's own per-chunk bytes, no oracle in between
         chunks, well = golden.chunks(case, ref_level)

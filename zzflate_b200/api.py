@@ -151,6 +151,24 @@ def debug_chunk(source, chunk_index: int, level: int = 2, chunk: int = DEFAULT_C
             "block_type": int(info[0]), "hdr_bits": int(info[1]), "out_bytes": int(info[2]), "total_bits": int(info[3])}
 
 
+def ZzFlateDecode(stream, fmt: Format = Format.Zlib, max_len: Optional[int] = None, dictionary=None) -> Optional[bytes]:
+    """include/decoder.h -- the host inflater that fills the role of the reference's stub decoder.h.  Returns the
+    inflated bytes, or None on any error (bad header / block / code / distance / checksum, truncated input)."""
+    lib = _lib.load()
+    src = _as_u8(stream)
+    cap = max_len if max_len is not None else max(1024, src.size * 64)
+    dest = np.empty(max(cap, 1), dtype=np.uint8)
+    d = _as_u8(dictionary) if dictionary is not None and len(dictionary) else None
+    lib.zz_c_decode.restype = C.c_size_t
+    lib.zz_c_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+    status = C.c_int(0)
+    w = lib.zz_c_decode(dest.ctypes.data, cap, src.ctypes.data, src.size, int(fmt), d.ctypes.data if d is not None else None,
+                        d.size if d is not None else 0, C.byref(status))
+    if w == _ERR:
+        return None
+    return dest[:w].tobytes()
+
+
 def device_count() -> int:
     return _lib.load().zzgpu_device_count()
 

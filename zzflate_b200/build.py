@@ -13,9 +13,9 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB = PKG_DIR / "libzzflate_b200.so"
-SOURCES = ["zz_kernels.cu", "zz_cabi.cu", "zz_host.cpp"]
+SOURCES = ["zz_kernels.cu", "zz_cabi.cu", "zz_host.cpp", "zz_decoder.cpp"]
 DEPS = SOURCES + ["zz_kernels.cuh", "../../include/zzgpu.h", "../../include/zzflate.h",
-                  "../../include/encoder.h", "../../include/crc.h", "../../include/outputbitstream.h"]
+                  "../../include/encoder.h", "../../include/crc.h", "../../include/outputbitstream.h", "../../include/decoder.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 
