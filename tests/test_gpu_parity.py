@@ -116,6 +116,33 @@ def test_callback_api_streams(zz, oracle):
     assert pieces >= 4 and 1 <= done < pieces, (done, pieces)
 
 
+def test_gzip_members_for_large_inputs(zz, oracle, golden):
+    """N4: a gzip member stores its input length modulo 2^32, so inputs of 4 GiB and more are written as a series of members
+    (RFC 1952 2.2), each a complete stream with its own CRC-32 and ISIZE.  With the member size lowered to 128 KiB a
+    300 KiB input becomes three members; gzip / zlib / the library's own inflater read them back as one stream."""
+    import ctypes as C, gzip
+    from zzflate_b200 import _lib
+    lib = _lib.load()
+    lib.zz_c_set_gzip_member_bytes.argtypes = [C.c_size_t]; lib.zz_c_set_gzip_member_bytes.restype = None
+    data = golden.input("alice29")[:150000] + golden.input("kennedy")[:157200]
+    lib.zz_c_set_gzip_member_bytes(2 * S)
+    try:
+        for threaded in (False, True):
+            out = zz.ZzFlateEncode(data, zz.Config(zz.Format.Gzip, 2, threaded))
+            assert out is not None and out.count(b"\x1f\x8b\x08\x00") >= 3
+            assert gzip.decompress(out) == data
+            assert zz.ZzFlateDecode(out, zz.Format.Gzip, max_len=len(data) + 16) == data
+            members = [oracle.stream_chunked(data[o: o + 2 * S], GZIP, 2)[0] for o in range(0, len(data), 2 * S)]
+            assert out == b"".join(members)
+        pieces = []
+        zz.ZzFlateEncodeToCallback(data, zz.Config(zz.Format.Gzip, 2, False), lambda b: pieces.append(b) or False)
+        assert b"".join(pieces) == out
+        z = zz.ZzFlateEncode(data, zz.Config(zz.Format.Zlib, 2, False))          # zlib has no length field: one stream
+        assert zlib.decompress(z) == data and z == oracle.stream_chunked(data, ZLIB, 2)[0]
+    finally:
+        lib.zz_c_set_gzip_member_bytes(0)
+
+
 def test_hold_and_fetch(zz, oracle, golden):
     """zzgpu_deflate_hold / zzgpu_fetch (the stitch of zzflate.cpp:136-154 without a temporary): same bytes as the
     one-call path, to memory and to a sink; a second call of the holding thread is refused until the fetch."""

@@ -195,6 +195,18 @@ int distanceSymbol(int offset)
     return 2 * nb + ((t >> (nb - 1)) & 1);
 }
 
+
+// A gzip member records its input length modulo 2^32 (ISIZE, RFC 1952 2.3.1), so inputs of 4 GiB and more are written
+// as several members (RFC 1952 2.2: "a gzip file consists of a series of members"): every member is a complete
+// deflate stream with its own header, CRC-32 and ISIZE, and inflaters concatenate them.  (The reference truncates ISIZE,
+// zzflate.cpp:183-186.)  Zlib and raw deflate have no such field and stay one stream.
+size_t g_gzipMemberBytes = ((size_t)0xFFFFFFFFu / ZZGPU_DEFAULT_CHUNK) * ZZGPU_DEFAULT_CHUNK;      // 4 GiB - 64 KiB
+
+size_t memberLimit(Format f, size_t n)
+{
+    return (f == Gzip && n > g_gzipMemberBytes) ? g_gzipMemberBytes : n;
+}
+
 }  // namespace
 
 void ZzFlateEncode(uint8_t* dest, size_t* destLen, const uint8_t* source, size_t sourceLen, const Config* config)
@@ -203,14 +215,23 @@ void ZzFlateEncode(uint8_t* dest, size_t* destLen, const uint8_t* source, size_t
     const size_t hl = headerBytes(config->format, h);
     const size_t tl = config->format == Zlib ? 4 : config->format == Gzip ? 8 : 0;
     if (config->level > 3 || *destLen < hl + tl) { *destLen = ~(size_t)0; return; }     // zzflate.cpp:230-234
-    memcpy(dest, h, hl);
-    size_t body = 0; uint32_t adler = 1, crc = 0;
-    const int rc = deflateStream(dest + hl, *destLen - hl - tl, nullptr, source, sourceLen, config->level, config->threaded,
-                                 config->format, &body, &adler, &crc);
-    if (rc != ZZGPU_OK) { *destLen = ~(size_t)0; return; }
-    trailerBytes(config->format, adler, crc, sourceLen, t);
-    memcpy(dest + hl + body, t, tl);
-    *destLen = hl + body + tl;
+    const size_t cap = *destLen;
+    const size_t member = memberLimit(config->format, sourceLen);
+    size_t pos = 0, off = 0;
+    do {
+        const size_t len = std::min(member, sourceLen - off);
+        if (cap - pos < hl + tl) { *destLen = ~(size_t)0; return; }
+        memcpy(dest + pos, h, hl);
+        size_t body = 0; uint32_t adler = 1, crc = 0;
+        const int rc = deflateStream(dest + pos + hl, cap - pos - hl - tl, nullptr, source + off, len, config->level, config->threaded,
+                                     config->format, &body, &adler, &crc);
+        if (rc != ZZGPU_OK) { *destLen = ~(size_t)0; return; }
+        trailerBytes(config->format, adler, crc, len, t);
+        memcpy(dest + pos + hl + body, t, tl);
+        pos += hl + body + tl;
+        off += len;
+    } while (off < sourceLen);
+    *destLen = pos;
 }
 
 // Header, the stream in pieces of <= 1 000 000 bytes as they leave the GPU (the first piece arrives while later
@@ -222,13 +243,19 @@ void ZzFlateEncodeToCallback(const uint8_t* source, size_t sourceLen, const Conf
     if (zzgpu_device_count() <= 0) return;                                             // no CPU fallback: nothing is delivered
     uint8_t h[10], t[8];
     const size_t hl = headerBytes(config->format, h);
-    callback(h, hl);
-    size_t body = 0; uint32_t adler = 1, crc = 0;
-    const int rc = deflateStream(nullptr, 0, &callback, source, sourceLen, config->level, config->threaded,
-                                 config->format, &body, &adler, &crc);
-    if (rc != ZZGPU_OK) return;                       // a failed stream gets no trailer, so no inflater accepts it
-    const size_t tl = trailerBytes(config->format, adler, crc, sourceLen, t);
-    callback(t, tl);
+    const size_t member = memberLimit(config->format, sourceLen);
+    size_t off = 0;
+    do {
+        const size_t len = std::min(member, sourceLen - off);
+        callback(h, hl);
+        size_t body = 0; uint32_t adler = 1, crc = 0;
+        const int rc = deflateStream(nullptr, 0, &callback, source + off, len, config->level, config->threaded,
+                                     config->format, &body, &adler, &crc);
+        if (rc != ZZGPU_OK) return;                   // a failed stream gets no trailer, so no inflater accepts it
+        const size_t tl = trailerBytes(config->format, adler, crc, len, t);
+        callback(t, tl);
+        off += len;
+    } while (off < sourceLen);
 }
 
 uint32_t adler32x(uint32_t startValue, const uint8_t* data, size_t len)
@@ -350,6 +377,13 @@ ZZGPU_API int zz_c_partition(size_t n, int ndev, uint32_t chunk, uint64_t* tripl
     const std::vector<Shard> sh = partition(n, ndev, chunk ? chunk : ZZGPU_DEFAULT_CHUNK);
     for (size_t g = 0; g < sh.size() && (int)g < maxShards; ++g) { triples[3 * g] = sh[g].off; triples[3 * g + 1] = sh[g].len; triples[3 * g + 2] = sh[g].final ? 1 : 0; }
     return (int)sh.size();
+}
+
+// tests: gzip member size (default 4 GiB - 64 KiB; 0 restores the default)
+ZZGPU_API void zz_c_set_gzip_member_bytes(size_t bytes)
+{
+    g_gzipMemberBytes = bytes ? (bytes / ZZGPU_DEFAULT_CHUNK) * ZZGPU_DEFAULT_CHUNK : ((size_t)0xFFFFFFFFu / ZZGPU_DEFAULT_CHUNK) * ZZGPU_DEFAULT_CHUNK;
+    if (g_gzipMemberBytes == 0) g_gzipMemberBytes = ZZGPU_DEFAULT_CHUNK;
 }
 
 ZZGPU_API void* zz_c_encoder_new(int level, uint8_t* out, int64_t cap) { return new Encoder(level, out, cap); }
