@@ -113,6 +113,17 @@ ZZGPU_API int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int
                                int level, uint32_t chunk, uint32_t dict, int want_checksums,
                                size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats);
 
+/* zzgpu_deflate_ex with a mode.  0 = reference-equivalent ("E-mode": every chunk byte-identical to the reference encoder,
+ * what every other entry point produces).  1 = free mode: the same tokens and code lengths, but the dynamic
+ * block header carries HLIT / HDIST / HCLEN trimmed to the codes in use (the reference always writes 286 / 30 / 19,
+ * encoder.cpp:283-290), which also shortens the run-length coded length sequence.  (A per-chunk choice of the fixed code
+ * was measured and dropped: with this parse -- the last 258 bytes of a block are always literals, encoder.cpp:222 -- it
+ * never beat both the dynamic and the stored form.)  Levels 2 and 3; other levels ignore the mode. */
+ZZGPU_API int zzgpu_deflate_mode(const uint8_t* src, size_t n, size_t history, int final, int src_mem,
+                                 uint8_t* dst, size_t cap, int dst_mem,
+                                 int level, uint32_t chunk, uint32_t dict, int want_checksums, int mode,
+                                 size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats);
+
 /* Same as zzgpu_deflate_ex on host buffers, with the `hist_len` bytes of preceding stream given by their own pointer
  * (they need not lie in front of src).  Used by Encoder::AddData, which keeps a private copy of the last
  * 32 KiB + 288 bytes it was fed (the reference keeps its hash table across calls, encoder.cpp:248,320-327). */

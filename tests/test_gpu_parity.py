@@ -124,12 +124,12 @@ def test_gzip_members_for_large_inputs(zz, oracle, golden):
     from zzflate_b200 import _lib
     lib = _lib.load()
     lib.zz_c_set_gzip_member_bytes.argtypes = [C.c_size_t]; lib.zz_c_set_gzip_member_bytes.restype = None
-    data = golden.input("alice29")[:150000] + golden.input("kennedy")[:157200]
+    data = (golden.input("alice29") + golden.input("kennedy") + golden.input("markov"))[:307200]
     lib.zz_c_set_gzip_member_bytes(2 * S)
     try:
         for threaded in (False, True):
             out = zz.ZzFlateEncode(data, zz.Config(zz.Format.Gzip, 2, threaded))
-            assert out is not None and out.count(b"\x1f\x8b\x08\x00") >= 3
+            assert out is not None and len(data) > 4 * S and out.count(b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\xff") >= 3
             assert gzip.decompress(out) == data
             assert zz.ZzFlateDecode(out, zz.Format.Gzip, max_len=len(data) + 16) == data
             members = [oracle.stream_chunked(data[o: o + 2 * S], GZIP, 2)[0] for o in range(0, len(data), 2 * S)]
@@ -141,6 +141,37 @@ def test_gzip_members_for_large_inputs(zz, oracle, golden):
         assert zlib.decompress(z) == data and z == oracle.stream_chunked(data, ZLIB, 2)[0]
     finally:
         lib.zz_c_set_gzip_member_bytes(0)
+
+
+def test_free_mode(zz, oracle, golden):
+    """N1 (first step): mode 1 of zzgpu_deflate_mode keeps the tokens and code lengths of the reference-equivalent parse but
+    trims HLIT / HDIST / HCLEN in the dynamic block header to the codes in use.  Every stream must inflate (zlib and
+    include/decoder.h) and never be larger than E-mode's."""
+    from zzflate_b200 import synth
+    total_e = total_f = 0
+    for case in golden.cases:
+        data = golden.input(case)
+        for level in (2, 3):
+            e, *_ = zz.deflate_raw(data, level=level)
+            f, a0, crc, st = zz.deflate_raw(data, level=level, mode=1)
+            assert zlib.decompress(f, -15) == data, case
+            assert zz.ZzFlateDecode(f, zz.Format.Deflate, max_len=len(data) + 16) == data, case
+            assert len(f) <= len(e), (case, len(f), len(e))
+            assert zz.combine(1, a0, len(data)) == zlib.adler32(data) and crc == zlib.crc32(data)
+        total_e += len(e); total_f += len(f)
+    assert total_f < total_e
+    for n in (40, 80, 150, 260, 300, 400, 600, 1000, 1500):                             # small inputs: stored or dynamic by size
+        small = golden.input("alice29")[:n]
+        f, *_ = zz.deflate_raw(small, level=2, mode=1)
+        assert zlib.decompress(f, -15) == small and len(f) <= len(zz.deflate_raw(small, level=2)[0])
+    for lvl in (0, 1):                                                                  # other levels ignore the mode
+        assert zz.deflate_raw(golden.input("alice29"), level=lvl, mode=1)[0] == zz.deflate_raw(golden.input("alice29"), level=lvl)[0]
+    text = synth.markov_text(64 << 20, seg0=2)
+    e, *_ = zz.deflate_raw(text, level=2)
+    f, *_ = zz.deflate_raw(text, level=2, mode=1)
+    assert zlib.decompress(f, -15) == text.tobytes() and len(f) < len(e)
+    print("free mode vs E-mode on 64 MiB of Markov text: %d vs %d bytes (%.4f %%); golden inputs: %d vs %d (%.4f %%)"
+          % (len(f), len(e), 100.0 * (len(f) - len(e)) / len(e), total_f, total_e, 100.0 * (total_f - total_e) / total_e))
 
 
 def test_hold_and_fetch(zz, oracle, golden):

@@ -41,7 +41,7 @@ SYMBOLS = [
     "zzgpu_init", "zzgpu_shutdown", "zzgpu_device_count", "zzgpu_strerror", "zzgpu_last_error", "zzgpu_bound",
     "zzgpu_deflate", "zzgpu_deflate_ex", "zzgpu_checksums", "zzgpu_adler32_combine", "zzgpu_crc32_combine",
     "zzgpu_debug_chunk", "zzgpu_set_option", "zzgpu_get_counter", "zzgpu_deflate_hist", "zzgpu_deflate_sink",
-    "zzgpu_deflate_hold", "zzgpu_fetch", "zzgpu_release",
+    "zzgpu_deflate_hold", "zzgpu_fetch", "zzgpu_release", "zzgpu_deflate_mode",
 ]
 
 SINK_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_uint8), C.c_size_t, C.c_void_p)
@@ -73,6 +73,11 @@ def load() -> C.CDLL:
                                      C.c_void_p, C.c_size_t, C.c_int,
                                      C.c_int, C.c_uint32, C.c_uint32, C.c_int,
                                      C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(Stats)]
+    lib.zzgpu_deflate_mode.restype = C.c_int
+    lib.zzgpu_deflate_mode.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_size_t, C.c_int,
+                                       C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                       C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(Stats)]
     lib.zzgpu_checksums.restype = C.c_int
     lib.zzgpu_checksums.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32,
                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]

@@ -102,7 +102,7 @@ def crc32_combine(crc1: int, crc2: int, len2: int) -> int:
 
 
 def deflate_raw(source, level: int = 2, chunk: int = DEFAULT_CHUNK, dict_size: int = DEFAULT_DICT,
-                history: int = 0, final: bool = True, checksums: bool = True):
+                history: int = 0, final: bool = True, checksums: bool = True, mode: int = 0):
     """zzgpu_deflate_ex on host buffers.  `source` holds `history` bytes of preceding stream first.
     Returns (bytes, adler_start0, crc, Stats)."""
     lib = _lib.load()
@@ -111,9 +111,9 @@ def deflate_raw(source, level: int = 2, chunk: int = DEFAULT_CHUNK, dict_size: i
     cap = bound(n, level, chunk) + 16
     dst = np.empty(cap, dtype=np.uint8)
     out_len = C.c_size_t(0); a0 = C.c_uint32(0); crc = C.c_uint32(0); st = Stats()
-    check(lib.zzgpu_deflate_ex(src.ctypes.data + history, n, history, int(final), MEM_HOST, dst.ctypes.data, cap, MEM_HOST,
-                               level, chunk, dict_size, 3 if checksums else 0,
-                               C.byref(out_len), C.byref(a0), C.byref(crc), C.byref(st)))
+    check(lib.zzgpu_deflate_mode(src.ctypes.data + history, n, history, int(final), MEM_HOST, dst.ctypes.data, cap, MEM_HOST,
+                                 level, chunk, dict_size, 3 if checksums else 0, mode,
+                                 C.byref(out_len), C.byref(a0), C.byref(crc), C.byref(st)))
     return dst[: out_len.value].tobytes(), a0.value, crc.value, st
 
 

@@ -316,10 +316,13 @@ int preparePipeline(Ctx& c, size_t n, uint32_t chunk, int wantCk)
     return ZZGPU_OK;
 }
 
+thread_local int t_mode = 0;                // zzgpu_deflate_mode: mode of the call in progress on this thread
+
 Job makeJob(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap, int level,
             uint32_t chunk, uint32_t dict, int wantCk, uint64_t first, uint32_t count)
 {
     Job job{};
+    job.mode = t_mode;
     job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
     job.first_chunk = first; job.nchunks = count;
     job.final_stream = final; job.level = level; job.want_checksums = wantCk;
@@ -799,6 +802,19 @@ int zzgpu_deflate_ex(const uint8_t* src, size_t n, size_t history, int final, in
     const CallArgs a = { src, n, nullptr, history, final, src_mem, dst, cap, dst_mem, level, chunk, dict, want_checksums,
                          HostOut::Direct, nullptr, nullptr, 0 };
     return deflateCall(a, out_len, adler0, crc, stats);
+}
+
+int zzgpu_deflate_mode(const uint8_t* src, size_t n, size_t history, int final, int src_mem,
+                       uint8_t* dst, size_t cap, int dst_mem,
+                       int level, uint32_t chunk, uint32_t dict, int want_checksums, int mode,
+                       size_t* out_len, uint32_t* adler0, uint32_t* crc, zzgpu_stats* stats)
+{
+    if (mode != 0 && mode != 1) return fail(ZZGPU_E_ARG, "invalid mode");
+    t_mode = mode;
+    const int rc = zzgpu_deflate_ex(src, n, history, final, src_mem, dst, cap, dst_mem, level, chunk, dict, want_checksums,
+                                    out_len, adler0, crc, stats);
+    t_mode = 0;
+    return rc;
 }
 
 int zzgpu_deflate_hist(const uint8_t* src, size_t n, const uint8_t* hist, size_t hist_len, int final,

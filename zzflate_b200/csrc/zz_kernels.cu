@@ -1688,13 +1688,18 @@ __global__ void __launch_bounds__(kHuffLThreads) k_huffman_lanes(Job job)
     for (int i = 0; i < 286; ++i) freq[i] = (int)hist[i];
     calc_lengthsL(freq, 286, 15, lens, heap);
     generate_codesL(lens, 286, cc.lit);
-    const int nSym = rle_lengths(lens, 286, symRec, metaF);
+    // free mode: only the used part of each alphabet goes into the header (HLIT / HDIST; the reference always writes 286 / 30,
+    // encoder.cpp:283-285)
+    int nl = 286, nd = 30;
+    if (job.mode) while (nl > 257 && lens[nl - 1] == 0) --nl;
+    const int nSym = rle_lengths(lens, nl, symRec, metaF);
     for (int i = 0; i < 286; ++i) bits += (long long)freq[i] * (lens[i] + len_extra_bits(i));
 
     for (int i = 0; i < 30; ++i) freq[i] = (int)hist[286 + i];
     calc_lengthsL(freq, 30, 15, lens + 286, heap);
     generate_codesL(lens + 286, 30, cc.dist);
-    const int nDist = rle_lengths(lens + 286, 30, distRec, metaF);
+    if (job.mode) while (nd > 1 && lens[286 + nd - 1] == 0) --nd;
+    const int nDist = rle_lengths(lens + 286, nd, distRec, metaF);
     for (int i = 0; i < 30; ++i) bits += (long long)freq[i] * (lens[286 + i] + dist_extra_bits(i));
 
     calc_lengthsL(metaF, 19, 7, metaL, heap);
@@ -1704,7 +1709,9 @@ __global__ void __launch_bounds__(kHuffLThreads) k_huffman_lanes(Job job)
     for (int i = 0; i < 336 / 4; ++i)
         reinterpret_cast<uint32_t*>(cc.lens)[i] = lens[4 * i] | (lens[4 * i + 1] << 8) | (lens[4 * i + 2] << 16) | ((uint32_t)lens[4 * i + 3] << 24);
 
-    long long total = 3 + 5 + 5 + 4 + 3 * 19 + bits;
+    int hclen = 19;
+    if (job.mode) while (hclen > 4 && metaL[kOrder[hclen - 1]] == 0) --hclen;
+    long long total = 3 + 5 + 5 + 4 + 3 * hclen + bits;
     for (int pass = 0; pass < 2; ++pass) {
         const unsigned short* rec = pass ? distRec : symRec;
         const int cnt = pass ? nDist : nSym;
@@ -1723,9 +1730,9 @@ __global__ void __launch_bounds__(kHuffLThreads) k_huffman_lanes(Job job)
     st.block_type = 2;
     HdrWriter w; w.out = cc.hdr; w.acc = 0; w.used = 0; w.pos = 0;
     w.put(g.final ? 1u : 0u, 1); w.put(2u, 2);                       // StartBlock (encoder.cpp:143-147)
-    w.put(29u, 5); w.put(29u, 5); w.put(15u, 4);                     // encoder.cpp:283-285
-    for (int i = 0; i < 19; ++i) w.put(metaL[kOrder[i]], 3);
-    int hdrBits = 17 + 57;
+    w.put((unsigned)(nl - 257), 5); w.put((unsigned)(nd - 1), 5); w.put((unsigned)(hclen - 4), 4);     // 29, 29, 15 in reference-equivalent mode (encoder.cpp:283-285)
+    for (int i = 0; i < hclen; ++i) w.put(metaL[kOrder[i]], 3);
+    int hdrBits = 17 + 3 * hclen;
     for (int pass = 0; pass < 2; ++pass) {                           // WriteLengths (encoder.cpp:20-35)
         const unsigned short* rec = pass ? distRec : symRec;
         const int cnt = pass ? nDist : nSym;
@@ -2465,7 +2472,7 @@ int launch_candidates(const Job& job, cudaStream_t s)
 int launch_huffman(const Job& job, cudaStream_t s)
 {
     // resident warps of the warp-per-chunk kernel: 13 CTAs of 4 warps per SM (17 KiB of shared memory each)
-    if (job.nchunks <= 148u * 52u) k_huffman<<<(job.nchunks + kHuffWarps - 1) / kHuffWarps, kHuffThreads, 0, s>>>(job);
+    if (job.nchunks <= 148u * 52u && !job.mode) k_huffman<<<(job.nchunks + kHuffWarps - 1) / kHuffWarps, kHuffThreads, 0, s>>>(job);
     else k_huffman_lanes<<<(job.nchunks + kHuffLThreads - 1) / kHuffLThreads, kHuffLThreads, kHuffLSmem, s>>>(job);
     return 1;
 }

@@ -46,6 +46,7 @@ struct Job {
     int final_stream;         // the call's last chunk carries BFINAL
     int level;
     int want_checksums;       // bit0 adler, bit1 crc
+    int mode;                 // 0: reference-equivalent (E-mode), 1: free mode (header counts trimmed to the codes in use)
     // scratch, indexed by slot = chunk - first_chunk
     uint16_t* cand;           // [slots][chunk]     candidate distance per position, 0 = none
     uint8_t* info;            // [slots][chunk]     K-INFO: 0 = unusable, else 1 + min(forward match length, 32); then the literal stream
