@@ -32,6 +32,7 @@ def localise(data, chunk=S, dict_size=D, maxshow=2):
             if shown >= maxshow: return
 
 def one(name, data, level=2, chunk=S, dict_size=D):
+    print('  case', name, len(data), chunk, dict_size, flush=True) if VERBOSE else None
     try:
         got, *_ = zz.deflate_raw(data, level=level, chunk=chunk, dict_size=dict_size)
     except Exception as e:
@@ -44,6 +45,8 @@ def one(name, data, level=2, chunk=S, dict_size=D):
 
 from fuzz_model import gen, rng     # the same structured generator the CPU model was fuzzed with
 
+import os
+VERBOSE = bool(os.environ.get('LZ_CHECK_VERBOSE'))
 budget = float(sys.argv[1])
 total_bad = 0
 for combo in sys.argv[2:]:

@@ -420,10 +420,23 @@ constexpr int kChaseWarps = kChains / 32;
 static_assert(kChains % 32 == 0 && kChaseWarps <= 4 && kChaseWarps <= kLzWarps && kSubTiles <= kLzThreads && kSub % (4 * kLzThreads) == 0, "geometry");
 constexpr int kLzQueue = 32 + 128;
 constexpr int kExCap = 256;                               // exactly measured long matches remembered per sub-batch
+constexpr int kRegionMax = kSub + 512;                    // positions whose literals / match symbols are counted in one go beside the walk
+constexpr int kRegionWords = kRegionMax / 32 + 8;
+constexpr int kHistCopies = 4;                            // private histogram copies (warps share them round robin)
+constexpr int kWorkerThreads = (kLzWarps - kChaseWarps) * 32;
 constexpr int kLzScratch = kLzWarps * kLzQueue * 4;       // phase A: long-compare queues; afterwards: bitmaps, nzw, state list
 static_assert(4 * kSubWords * 4 + 544 + (kSub / 4 + 40) * 2 <= kLzScratch, "bitmaps + nzw + state list fit the queue space");
 constexpr int kLzSmem = kLzWin + (kSub + 64) + (kSub + 64) * 2 + kLzScratch;
 static_assert(3 * (kLzSmem + 2048) <= 227 * 1024, "three K-LZ CTAs per SM");
+
+#ifdef ZZ_LZ_CHECKS
+__device__ unsigned g_lzDebug[8];
+#define LZ_CHECK(cond, code, a, b) do { if (!(cond)) { if (atomicCAS(&g_lzDebug[0], 0u, (unsigned)(code)) == 0u) { g_lzDebug[1] = (unsigned)(a); g_lzDebug[2] = (unsigned)(b); g_lzDebug[3] = blockIdx.x; g_lzDebug[4] = threadIdx.x; } } } while (0)
+#define LZ_GUARD(var, limit, code, a, b) if (++(var) > (limit)) { LZ_CHECK(false, code, a, b); break; }
+#else
+#define LZ_CHECK(cond, code, a, b) do { } while (0)
+#define LZ_GUARD(var, limit, code, a, b)
+#endif
 
 struct LzShared {
     int pos;            // start of the next FirstPass batch
@@ -436,6 +449,10 @@ struct LzShared {
     int npre;           // tokens written directly by warp 0 in this sub-batch (first probe / far entry)
     int exN;            // entries of the exact list
     int endsAt;         // orbit state without successor in the sub-batch (it yields no token), or -1
+    // GetFrequencies beside the walk: positions below histPos / tokens below histTok are counted and their literals written;
+    // [histPos, regEnd) / [histTok, regTok) are final (everything below the walk's state is) and wait for the next walk
+    int histPos, histTok, regEnd, regTok, histStop;
+    unsigned nlits, regLits;
     int err;
 };
 
@@ -466,6 +483,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // named barrier of the chase warps; the non-aligned form counts arrivals per thread, so it is safe even where the compiler
 // has not reconverged a warp in front of it
 __device__ __forceinline__ void chase_barrier() { __syncwarp(); asm volatile("barrier.sync 1, %0;" ::"n"(kChaseWarps * 32) : "memory"); }
+__device__ __forceinline__ void worker_barrier() { __syncwarp(); asm volatile("barrier.sync 2, %0;" ::"n"(kWorkerThreads) : "memory"); }
 
 // info of one position from the window (same definition as phase A); oj = window offset of the position
 __device__ int info_of_w(const uint8_t* win, int oj, int d, int room)
@@ -626,7 +644,7 @@ __device__ __forceinline__ unsigned lz_lookup(const unsigned* exList, int exN, i
     return nb;
 }
 
-__global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int useSpec)
+__global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int useSpec, int useRegion)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t* win = smem;
@@ -649,6 +667,9 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
     __shared__ uint16_t segMp[kChains];              // first state of the chain that belongs to the orbit, 0xFFFF = none
     __shared__ unsigned k3Mask[4], lkMask[4], linkedW[4];
     __shared__ unsigned grpMin[kSubWords / 32 + 2];
+    __shared__ unsigned hist4[kHistCopies * kHistStride];     // literal/length + distance histograms (private copies)
+    __shared__ unsigned rcov[kRegionWords];                   // region: bit per position, covered by a match
+    __shared__ uint16_t rbase[kRegionWords];                  // region: literals before each 32-position word
 
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
@@ -657,12 +678,16 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
     const uint8_t* chunk0 = job.src + g.off;
     const Stream strm = { job.src - job.history, job.src + job.n };
     const uint16_t* cand = job.cand + (size_t)slot * job.chunk;
+    uint8_t* lits = job.info + (size_t)slot * job.chunk;           // the block's literal bytes in order
+    unsigned* myh = hist4 + (warp % kHistCopies) * kHistStride;
+    for (int i = tid; i < kHistCopies * kHistStride; i += kLzThreads) hist4[i] = 0;
     uint32_t* tokA = job.tokA + (size_t)slot * kMaxTokens;
     uint16_t* tokD = job.tokD + (size_t)slot * kMaxTokens;
     const int phase = (int)(reinterpret_cast<uintptr_t>(chunk0) & 15);
 
     if (tid == 0) {
         ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npend = 0; ps.exN = 0; ps.err = 0;
+        ps.histPos = 0; ps.histTok = 0; ps.regEnd = 0; ps.regTok = 0; ps.histStop = 0; ps.nlits = 0; ps.regLits = 0;
         for (int w = 0; w < 4; ++w) { k3Mask[w] = 0; lkMask[w] = 0; }
         mbar_init(&mbar, 1);
     }
@@ -884,8 +909,15 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
             }
             __syncthreads();
 
+            // the region that is final by now (everything below the walk's state) and not yet counted: done beside this walk
+            const int rA = ps.histPos, rB = ps.regEnd, tA = ps.histTok, tB = ps.regTok;
+            const unsigned nlit0 = ps.nlits;
+            const int regSpan = rB - (rA & ~31);
+            const bool regionNow = useRegion && !ps.histStop && rB > rA && regSpan <= kRegionMax;
+
             // ---- C: the orbit of succ from the entry state ----
             if (warp < kChaseWarps) {
+                __syncwarp();
                 const LzSub sub = { info, okbits, nzw, ntiles, base, B0, s1 };
                 // speculative chains: lane i follows succ from the first state of its segment and marks what it visits
                 const int ci = tid;
@@ -896,9 +928,13 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                     int x = segLo;
                     bool go = useSpec && segLo < s1;
                     bool givenUp = false;
+                    int guardR = 0; (void)guardR;
                     for (;;) {
                         if (go) {
+                            int guard1 = 0;
                             for (;;) {
+                                LZ_GUARD(guard1, kSub, 1, x, base)
+                                LZ_CHECK(x >= base && x < base + lim, 2, x, base);
                                 atomicOr(&Sb[(x - base) >> 5], 1u << (x & 31));
                                 int j;
                                 const unsigned f = lz_succ(sub, x, j);
@@ -912,6 +948,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                         // long matches that stopped chains: measured here while they are few (text), left to the true walk otherwise
                         unsigned brk = __ballot_sync(0xffffffffu, kind == 2 && !givenUp);
                         if (!brk) break;
+                        LZ_GUARD(guardR, 4 * kSegStates, 3, x, state)
                         if (__popc(brk) > 8) { givenUp = true; break; }
                         int myJ = 0, myD = 0;
                         if ((brk >> lane) & 1u) { myJ = lz_probe(sub, state); myD = (int)dist[myJ - base]; }
@@ -941,7 +978,9 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                     if ((pks >> 16) == 3u && pt >= segLo && pt < segHi && pt < s1) {
                         const int exN = ps.exN;
                         int x = pt;
+                        int guard2 = 0; (void)guard2;
                         for (;;) {
+                            LZ_GUARD(guard2, kSegStates + 2, 4, x, segLo)
                             if ((Sb[(x - base) >> 5] >> (x & 31)) & 1u) { linkMp = x; break; }
                             atomicOr(&Lb[(x - base) >> 5], 1u << (x & 31));
                             int j;
@@ -983,8 +1022,11 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                         const unsigned long long k3lo = k3Mask[0] | ((unsigned long long)k3Mask[1] << 32), k3hi = k3Mask[2] | ((unsigned long long)k3Mask[3] << 32);
                         const unsigned long long lklo = lkMask[0] | ((unsigned long long)lkMask[1] << 32), lkhi = lkMask[2] | ((unsigned long long)lkMask[3] << 32);
                         const unsigned long long okLo = (k3lo << 1) & lklo, okHi = ((k3hi << 1) | (k3lo >> 63)) & lkhi;
+                        int guard3 = 0; (void)guard3;
                         for (;;) {
                             if (cur >= s1) break;
+                            LZ_GUARD(guard3, 2 * kSub, 5, cur, base)
+                            LZ_CHECK(cur >= base, 6, cur, base);
                             const int r = cur - base;
                             int j;
                             const unsigned f0 = lz_succ(sub, cur, j);
@@ -1092,9 +1134,65 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                         __syncwarp();
                     }
                     if (lane == 0) { ps.b = cur; ps.npre = npre; ps.endsAt = endsAt; }
+                }
+            } else if (regionNow) {
+                // ---- beside the walk: GetFrequencies (encoder.cpp:442-471) for the region the previous sub-batches finished.  Its
+                //      matches are counted token-parallel and mark the positions they cover; the literals in between are counted
+                //      position-parallel from the window and written in order to the literal stream for K-EMIT ----
+                const int wt = tid - kChaseWarps * 32;
+                const int r0 = rA & ~31;
+                const int words = (rB - r0 + 31) >> 5;
+                LZ_CHECK(words <= kRegionWords && tB >= tA && wb + r0 >= 0 && wb + rB + 8 < kLzWin, 10, rA, rB);
+                for (int w = wt; w < words; w += kWorkerThreads) rcov[w] = 0;
+                worker_barrier();
+                for (int k = tA + wt; k < tB; k += kWorkerThreads) {
+                    const uint32_t t = tokA[k];
+                    const int ms = (int)(t & 0xFFFF) - r0, ln = (int)(t >> 16), me = ms + ln - 1;
+                    int eb, ev;
+                    atomicAdd(&myh[len_symbol(ln, eb, ev)], 1u);
+                    atomicAdd(&myh[286 + dist_symbol(tokD[k], eb, ev)], 1u);
+                    for (int w = ms >> 5; w <= (me >> 5); ++w) {
+                        unsigned m = 0xffffffffu;
+                        if (w == (ms >> 5)) m &= 0xffffffffu << (ms & 31);
+                        if (w == (me >> 5)) m &= 0xffffffffu >> (31 - (me & 31));
+                        atomicOr(&rcov[w], m);
                     }
+                }
+                if (wt == 0) {                                       // positions outside [rA, rB) are not this region's literals
+                    if (rA & 31) atomicOr(&rcov[0], (1u << (rA & 31)) - 1u);
+                    if ((rB - r0) & 31) atomicOr(&rcov[words - 1], 0xffffffffu << ((rB - r0) & 31));
+                }
+                worker_barrier();
+                if (warp == kChaseWarps) {                           // exclusive scan of the literal counts per word
+                    constexpr int kPer = (kRegionWords + 31) / 32;
+                    unsigned c[kPer], sum = 0;
+#pragma unroll
+                    for (int k = 0; k < kPer; ++k) { const int w = lane * kPer + k; c[k] = w < words ? (unsigned)__popc(~rcov[w]) : 0u; sum += c[k]; }
+                    unsigned inc = sum;
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                    unsigned before = inc - sum;
+#pragma unroll
+                    for (int k = 0; k < kPer; ++k) { const int w = lane * kPer + k; if (w < words) rbase[w] = (uint16_t)before; before += c[k]; }
+                    if (lane == 31) ps.regLits = inc;
+                }
+                worker_barrier();
+                for (int q = wt * 4; q < words * 32; q += kWorkerThreads * 4) {
+                    const unsigned cword = rcov[q >> 5];
+                    const unsigned cw = (cword >> (q & 31)) & 0xFu;
+                    if (cw == 0xFu) continue;                        // four covered positions: nothing to count
+                    const unsigned v = ld4(win, wb + r0 + q);
+                    unsigned rank = nlit0 + rbase[q >> 5] + (unsigned)__popc(~cword & ((1u << (q & 31)) - 1u));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (!((cw >> k) & 1u)) { const unsigned b = (v >> (8 * k)) & 0xFFu; atomicAdd(&myh[b], 1u); LZ_CHECK(rank < job.chunk, 9, rank, q); lits[rank++] = (uint8_t)b; }
+                }
             }
             __syncthreads();
+            // (no divergent statement may sit between a CTA barrier and the chase warps' named barriers: the bookkeeping is here)
+            if (tid == 0) {
+                if (regionNow) { ps.histPos = rB; ps.histTok = tB; ps.nlits = nlit0 + ps.regLits; }
+                else if (regSpan > kRegionMax) ps.histStop = 1;        // too much at once: left to the end
+            }
 
             // ---- D: the orbit's states, compacted, then expanded to tokens in parallel ----
             {
@@ -1129,6 +1227,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                 unsigned wbits = word;
                 while (wbits) {
                     const int bit = __ffs(wbits) - 1; wbits &= wbits - 1;
+                    LZ_CHECK(out < kSub / 4 + 40, 7, out, base);
                     stateList[out++] = (uint16_t)(base + tid * 32 + bit);
                 }
                 __syncthreads();
@@ -1146,11 +1245,12 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                     if (fwd >= kCapLen) fwd = fwd_upto_w(win, wb + j, wb + j - d);      // the compare of phase A stopped at 32 bytes
                     int m = fwd + lb;
                     if (m > kMaxMatch) m = kMaxMatch;
+                    LZ_CHECK(outBase + t < kMaxTokens && j >= 0, 8, outBase + t, j);
                     tokA[outBase + t] = (uint32_t)(j - lb) | ((uint32_t)m << 16);
                     tokD[outBase + t] = (uint16_t)d;
                 }
                 __syncthreads();
-                if (tid == 0) ps.ntok = outBase + nbt;
+                if (tid == 0) { ps.ntok = outBase + nbt; ps.regEnd = ps.b; ps.regTok = outBase + nbt; }
             }
             __syncthreads();
             s0 = s1;
@@ -1166,19 +1266,18 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
     __syncthreads();
     if (tid == 0 && ps.err) atomicOr(reinterpret_cast<unsigned long long*>(&job.total[1]), 8ull);
 
-    // ---- histograms (GetFrequencies, encoder.cpp:442-471) ----
-    // Matches are counted token-parallel and mark the positions they cover in a bitmap; literals are then counted
-    // position-parallel (coalesced reads) into per-warp private histograms.  The batch arrays are dead: the space is reused.
-    unsigned* hist = reinterpret_cast<unsigned*>(smem);            // per-warp private copies
-    unsigned* cov = hist + kLzWarps * kHistStride;                 // bit per position: covered by a match
+    // ---- the rest of GetFrequencies (encoder.cpp:442-471): what the walks left uncounted (the last sub-batch's matches, the
+    //      literals behind histPos including the block's tail, or everything if a region grew too large to be counted beside
+    //      a walk).  Same scheme over the whole chunk: matches mark a coverage bitmap, literals are counted position-parallel
+    //      (coalesced reads from global memory).  The batch arrays are dead: the space is reused. ----
+    unsigned* cov = reinterpret_cast<unsigned*>(smem);             // bit per position: covered by a match (or counted already)
     unsigned* litBase = cov + kMaxChunk / 32;                      // literals before each 32-position word
-    uint8_t* lits = job.info + (size_t)slot * job.chunk;           // the block's literal bytes in order
-    for (int i = tid; i < kLzWarps * kHistStride + kMaxChunk / 32; i += kLzThreads) hist[i] = 0;
+    for (int i = tid; i < kMaxChunk / 32; i += kLzThreads) cov[i] = 0;
     __syncthreads();
     {
-        const int ntok = ps.ntok;
-        unsigned* myh = hist + warp * kHistStride;
-        for (int k = tid; k < ntok; k += kLzThreads) {
+        const int ntok = ps.ntok, hp = ps.histPos, ht = ps.histTok;
+        const unsigned nl0 = ps.nlits;
+        for (int k = ht + tid; k < ntok; k += kLzThreads) {
             const uint32_t t = tokA[k];
             const int ms = (int)(t & 0xFFFF), ln = (int)(t >> 16), me = ms + ln - 1;
             int eb, ev;
@@ -1192,10 +1291,13 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
             }
         }
         __syncthreads();
-        // positions at or beyond the block's end are not literals
+        // positions counted already, and positions at or beyond the block's end, are not literals here
         for (int w = tid; w < kMaxChunk / 32; w += kLzThreads) {
             const int lo = w * 32;
-            if (lo + 32 > g.body) cov[w] |= lo >= g.body ? 0xffffffffu : (0xffffffffu << (g.body - lo));
+            unsigned m = 0;
+            if (lo < hp) m |= lo + 32 <= hp ? 0xffffffffu : ((1u << (hp - lo)) - 1u);
+            if (lo + 32 > g.body) m |= lo >= g.body ? 0xffffffffu : (0xffffffffu << (g.body - lo));
+            if (m) cov[w] |= m;
         }
         __syncthreads();
         {   // exclusive scan of the literal counts per word (kWordsPerThread consecutive words per thread)
@@ -1214,7 +1316,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                 wsum[lane] = v;
             }
             __syncthreads();
-            unsigned before = (warp ? wsum[warp - 1] : 0u) + inc - sum;
+            unsigned before = nl0 + (warp ? wsum[warp - 1] : 0u) + inc - sum;
 #pragma unroll
             for (int k = 0; k < kWordsPerThread; ++k) if (w0 + k < kMaxChunk / 32) { litBase[w0 + k] = before; before += c[k]; }
             if (tid == kLzThreads - 1) job.state[slot].nlit = before;
@@ -1223,7 +1325,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
         // literals: histogram, and the literal bytes written out in order for K-EMIT (position -> rank through the
         // coverage bitmap).  A 4-byte aligned chunk reads whole words (a word that holds a valid byte never leaves its page).
         const bool srcAligned = (reinterpret_cast<uintptr_t>(chunk0) & 3) == 0;
-        for (int pos = tid * 4; pos < g.body; pos += 4 * kLzThreads) {
+        for (int pos = (hp & ~3) + tid * 4; pos < g.body; pos += 4 * kLzThreads) {
             const unsigned cword = cov[pos >> 5];
             const unsigned cw = (cword >> (pos & 31)) & 0xFu;
             if (cw == 0xFu) continue;                                   // four covered positions: nothing to count
@@ -1243,7 +1345,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
     __syncthreads();
     for (int i = tid; i < 316; i += kLzThreads) {
         unsigned s = 0;
-        for (int w = 0; w < kLzWarps; ++w) s += hist[w * kHistStride + i];
+        for (int w = 0; w < kHistCopies; ++w) s += hist4[w * kHistStride + i];
         if (i == 256) s += 1;                                       // end-of-block (encoder.cpp:470)
         job.hist[(size_t)slot * kHistStride + i] = s;
     }
@@ -2486,15 +2588,26 @@ int launch_offsets(const Job& job, cudaStream_t s)
 // A/B switches of kernel variants (zzgpu_set_option); none changes the produced bytes.
 static int g_optTma = 1;         // K-LZ window: 1 = cp.async.bulk (TMA) + mbarrier, 0 = LDG.128 -> STS
 static int g_optSpec = 1;        // K-LZ walk: 1 = speculative per-lane chains merged by the true walk, 0 = the true walk alone
+static int g_optRegion = 1;      // K-LZ histograms: 1 = counted beside the walks region by region, 0 = all at the end of the chunk
 bool set_kernel_option(const char* name, int value)
 {
     if (!strcmp(name, "tma")) { g_optTma = value ? 1 : 0; return true; }
     if (!strcmp(name, "spec")) { g_optSpec = value ? 1 : 0; return true; }
+    if (!strcmp(name, "region")) { g_optRegion = value ? 1 : 0; return true; }
     return false;
 }
 int launch_lz(const Job& job, cudaStream_t s)
 {
-    k_lz<<<job.nchunks, kLzThreads, kLzSmem, s>>>(job, g_optTma, g_optSpec);
+    k_lz<<<job.nchunks, kLzThreads, kLzSmem, s>>>(job, g_optTma, g_optSpec, g_optRegion);
+#ifdef ZZ_LZ_CHECKS
+    {   // diagnostic build: bounds and loop guards inside K-LZ report the first violation
+        const cudaError_t e = cudaStreamSynchronize(s);
+        unsigned h[8] = { 0 };
+        cudaMemcpyFromSymbol(h, g_lzDebug, sizeof h);
+        if (e != cudaSuccess || h[0]) fprintf(stderr, "K-LZ check: cuda=%d code=%u a=%d b=%d block=%u thread=%u\n", (int)e, h[0], (int)h[1], (int)h[2], h[3], h[4]);
+        unsigned z[8] = { 0 }; cudaMemcpyToSymbol(g_lzDebug, z, sizeof z);
+    }
+#endif
     return 1;
 }
 
