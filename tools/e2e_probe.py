@@ -20,3 +20,12 @@ for it in range(4):
 d = torch.empty(n, dtype=torch.uint8, device='cuda')
 torch.cuda.synchronize(); t = time.perf_counter(); d.copy_(src, non_blocking=True); torch.cuda.synchronize(); print('H2D GB/s', n / (time.perf_counter() - t) / 1e9)
 t = time.perf_counter(); dst[:n//2].copy_(d[:n//2], non_blocking=True); torch.cuda.synchronize(); print('D2H GB/s', n / 2 / (time.perf_counter() - t) / 1e9)
+# both directions at once (two streams), as the pipelined call uses the link
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+m = int(n * 0.55)
+for rep in range(2):
+    torch.cuda.synchronize(); t = time.perf_counter()
+    with torch.cuda.stream(s1): d.copy_(src, non_blocking=True)
+    with torch.cuda.stream(s2): dst[:m].copy_(d[:m], non_blocking=True)
+    torch.cuda.synchronize(); el = time.perf_counter() - t
+    print('H2D 1 GiB + D2H 0.55 GiB concurrently: ms', round(el * 1e3, 2), 'H2D-equivalent GB/s', round(n / el / 1e9, 2))

@@ -22,6 +22,9 @@ using namespace zz;
 
 constexpr uint32_t kMaxSlots = 16384;       // chunks per batch (scratch is sized for one batch)
 constexpr int kMaxDevices = 16;
+constexpr int kMaxLanes = 4;
+uint64_t g_pieceFirst = 888, g_pieceMid = 1332, g_pieceLast = 888;   // piece schedule of host-buffer calls, in chunks
+int g_optLanes = 3;                               // host-buffer calls: kernel streams that consecutive pieces alternate on ("lanes" option)
 size_t g_segBytes = (size_t)2 << 30;             // host-buffer calls: input bytes staged on the device at a time ("segment_mib" option)
 constexpr size_t kPipelineMin = (size_t)32 << 20;   // host inputs from this size on are cut into overlapping pieces
 constexpr size_t kDefaultSlice = 1000000;   // outputbitstream.h:183
@@ -41,6 +44,7 @@ struct Ctx {
     std::thread::id holder;
     size_t heldLen = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t extra[kMaxLanes - 1] = {};  // host-buffer path: piece p runs on lane p % lanes (lane 0 is `stream`)
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     uint32_t slots = 0;
     uint32_t slotChunk = 0;
@@ -58,6 +62,7 @@ struct Ctx {
     cudaEvent_t stageInEv[2] = { nullptr, nullptr }, stageOutEv[2] = { nullptr, nullptr };
     std::vector<cudaEvent_t> pieceEv;
     uint64_t* hPiece = nullptr; size_t hPieceCap = 0;     // pinned: running totals after each piece
+    uint64_t* dPiece = nullptr; size_t dPieceCap = 0;     // device: the totals as K-OFFS of each piece left them
     std::vector<cudaEvent_t> stageEv;       // pool of events bracketing each stage launch
     std::vector<int> stageOf;               // stage id of the interval that ENDS at event i (-1: start marker)
     size_t stageUsed = 0;
@@ -114,11 +119,12 @@ void destroyCtx(Ctx& c)
 {
     if (c.device >= 0) cudaSetDevice(c.device);
     if (c.stream) cudaStreamSynchronize(c.stream);
+    for (auto& x : c.extra) if (x) cudaStreamSynchronize(x);
     if (c.copyIn) cudaStreamSynchronize(c.copyIn);
     if (c.copyOut) cudaStreamSynchronize(c.copyOut);
     freeScratch(c);
     cudaFree(c.total); cudaFreeHost(c.hTotal); cudaFree(c.ck); cudaFreeHost(c.hCk); cudaFree(c.dIn); cudaFree(c.dOut);
-    cudaFreeHost(c.hPiece);
+    cudaFreeHost(c.hPiece); cudaFree(c.dPiece);
     for (auto& e : c.pieceEv) cudaEventDestroy(e);
     for (auto& e : c.stageEv) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -129,15 +135,16 @@ void destroyCtx(Ctx& c)
     }
     if (c.copyIn) cudaStreamDestroy(c.copyIn);
     if (c.copyOut) cudaStreamDestroy(c.copyOut);
+    for (auto& x : c.extra) if (x) cudaStreamDestroy(x);
     for (auto& e : c.ev) if (e) cudaEventDestroy(e);
     if (c.stream) cudaStreamDestroy(c.stream);
     (void)cudaGetLastError();
     c.device = -1; c.ready = false; c.heldLen = 0;
-    c.stream = nullptr; for (auto& e : c.ev) e = nullptr;
+    c.stream = nullptr; for (auto& x : c.extra) x = nullptr; for (auto& e : c.ev) e = nullptr;
     c.total = nullptr; c.hTotal = nullptr; c.ck = nullptr; c.ckCap = 0; c.hCk = nullptr; c.hCkCap = 0;
     c.dIn = nullptr; c.dInCap = 0; c.dOut = nullptr; c.dOutCap = 0; c.copyIn = nullptr; c.copyOut = nullptr;
     for (int i = 0; i < 2; ++i) { c.stageIn[i] = c.stageOut[i] = nullptr; c.stageInEv[i] = c.stageOutEv[i] = nullptr; }
-    c.pieceEv.clear(); c.hPiece = nullptr; c.hPieceCap = 0;
+    c.pieceEv.clear(); c.hPiece = nullptr; c.hPieceCap = 0; c.dPiece = nullptr; c.dPieceCap = 0;
     c.stageEv.clear(); c.stageOf.clear(); c.stageUsed = 0;
 }
 
@@ -319,29 +326,42 @@ int preparePipeline(Ctx& c, size_t n, uint32_t chunk, int wantCk)
 thread_local int t_mode = 0;                // zzgpu_deflate_mode: mode of the call in progress on this thread
 
 Job makeJob(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap, int level,
-            uint32_t chunk, uint32_t dict, int wantCk, uint64_t first, uint32_t count)
+            uint32_t chunk, uint32_t dict, int wantCk, uint64_t first, uint32_t count, uint32_t slotBase = 0)
 {
     Job job{};
     job.mode = t_mode;
     job.src = d_src; job.n = n; job.history = history; job.chunk = chunk; job.dict = dict;
     job.first_chunk = first; job.nchunks = count;
     job.final_stream = final; job.level = level; job.want_checksums = wantCk;
-    job.cand = c.cand; job.info = c.info; job.tokA = c.tokA; job.tokD = c.tokD;
-    job.hist = c.hist; job.codes = c.codes; job.state = c.state;
+    const size_t sb = slotBase;                  // the job's rows of the per-chunk scratch arrays start here
+    job.cand = c.cand + sb * chunk; job.info = c.info + sb * chunk; job.tokA = c.tokA + sb * kMaxTokens; job.tokD = c.tokD + sb * kMaxTokens;
+    job.hist = c.hist + sb * kHistStride; job.codes = c.codes + sb; job.state = c.state + sb;
     job.dst = d_dst; job.cap = cap; job.total = c.total; job.ck = c.ck;
     return job;
 }
 
+// A piece of the host-buffer path that runs beside its neighbours: its own stream and half of the scratch rows.  K-OFFS
+// carries the running output offset from piece to piece, so it waits for the previous piece's K-OFFS and leaves its own
+// totals in `snapshot` for the host (the live totals move on with the next piece).
+struct Lane {
+    cudaStream_t st; uint32_t slotBase, slotCap;
+    cudaEvent_t waitOffs, doneOffs;             // previous piece's K-OFFS done (or null) / this piece's
+    uint64_t* snapshot;                         // device [4]
+};
+
 // Kernel pipeline over chunks [firstChunk, lastChunk) of the call (geometry is always that of the whole call):
 // batches of up to 16 384 chunks, kernels back to back on one stream.
 int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final, uint8_t* d_dst, size_t cap,
-              int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t firstChunk, uint64_t lastChunk, uint64_t& launches)
+              int level, uint32_t chunk, uint32_t dict, int wantCk, uint64_t firstChunk, uint64_t lastChunk, uint64_t& launches,
+              const Lane* lane = nullptr)
 {
     int rc;
-    for (uint64_t first = firstChunk; first < lastChunk; first += c.slots) {
+    const uint32_t slotCap = lane ? lane->slotCap : c.slots, slotBase = lane ? lane->slotBase : 0;
+    cudaStream_t st = lane ? lane->st : c.stream;
+    for (uint64_t first = firstChunk; first < lastChunk; first += slotCap) {
         const Job job = makeJob(c, d_src, n, history, final, d_dst, cap, level, chunk, dict, wantCk, first,
-                                (uint32_t)std::min<uint64_t>(c.slots, lastChunk - first));
-        cudaStream_t st = c.stream;
+                                (uint32_t)std::min<uint64_t>(slotCap, lastChunk - first), slotBase);
+        const bool firstBatch = first == firstChunk, lastBatch = first + slotCap >= lastChunk;
         rc = markStage(c, -1, st); if (rc) return rc;
         if (level == 0) {                                   // every size is known beforehand: one kernel does it all
             launches += launch_stored(job, st); rc = markStage(c, ZZGPU_STAGE_EMIT, st); if (rc) return rc;
@@ -356,7 +376,13 @@ int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final,
         } else {
             launches += launch_huffman(job, st); rc = markStage(c, ZZGPU_STAGE_HUFF, st); if (rc) return rc;
         }
+        if (lane && firstBatch && lane->waitOffs) { CK(cudaStreamWaitEvent(st, lane->waitOffs, 0)); rc = markStage(c, -1, st); if (rc) return rc; }
         launches += launch_offsets(job, st); rc = markStage(c, ZZGPU_STAGE_OFFS, st); if (rc) return rc;
+        if (lane && lastBatch) {
+            CK(cudaMemcpyAsync(lane->snapshot, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+            CK(cudaEventRecord(lane->doneOffs, st));
+            rc = markStage(c, -1, st); if (rc) return rc;
+        }
         if (level == 1) { launches += launch_gather(job, st); rc = markStage(c, ZZGPU_STAGE_GATHER, st); if (rc) return rc; }
         else { launches += launch_emit(job, st); rc = markStage(c, ZZGPU_STAGE_EMIT, st); if (rc) return rc; }
         if (wantCk) { launches += launch_checksums(job, st); rc = markStage(c, ZZGPU_STAGE_CKSUM, st); if (rc) return rc; }
@@ -378,22 +404,25 @@ int runPipeline(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int fina
 // the middle (full occupancy, one dictionary-priming pass per long run of chunks), small at the end (short drain).
 std::vector<uint64_t> pieceSchedule(uint64_t nchunks, uint32_t chunk)
 {
-    // Every piece costs one launch of each kernel (the Huffman kernel alone is ~0.4 ms however few chunks it gets), so
-    // pieces are few.  Their sizes are multiples of 888 chunks = 148 SMs x 6 resident K-CAND warps, which is also a
-    // whole number of waves of K-LZ (444 CTAs) and K-EMIT (296 CTAs): 888, 1776, 3552, then 4440 chunks, and the last
-    // <= 7104 chunks in up to three shrinking pieces so that the final D2H is short.
+    // Every piece costs one launch of each kernel (the Huffman kernel alone is ~0.4 ms however few chunks it gets), and the
+    // kernels of a piece start when its H2D is complete.  The link moves a chunk in about the time the kernels need for it,
+    // so what counts is the sum of the pieces' fixed costs plus the first H2D and the last piece's kernels and D2H: a
+    // short first piece, equal middle pieces, a short last one.  Sizes are multiples of 444 chunks = one wave of K-LZ
+    // (148 SMs x 3 CTAs); 888 is a whole number of waves of K-CAND and K-EMIT too.
     std::vector<uint64_t> ends;
-    if (nchunks * chunk < kPipelineMin) { ends.push_back(nchunks); return ends; }
-    const uint64_t unit = 888, big = 5 * unit;
-    uint64_t pos = 0, size = unit;
-    while (nchunks - pos > big + 3 * unit) {
-        pos += size; ends.push_back(pos);
-        size = size < 4 * unit ? size * 2 : big;
+    const uint64_t first = g_pieceFirst, mid = g_pieceMid, last = g_pieceLast, unit = 444;
+    if (nchunks * chunk < kPipelineMin || nchunks < first + last + unit) { ends.push_back(nchunks); return ends; }
+    ends.push_back(first);
+    const uint64_t middle = nchunks - first - last;
+    const uint64_t k = std::max<uint64_t>(1, (middle + mid / 2) / mid);            // number of middle pieces
+    uint64_t pos = first;
+    for (uint64_t i = 0; i < k; ++i) {
+        uint64_t take = i + 1 == k ? nchunks - last - pos : ((middle / k + unit / 2) / unit) * unit;
+        if (take == 0) take = unit;
+        if (pos + take > nchunks - last) take = nchunks - last - pos;
+        if (take == 0) break;
+        pos += take; ends.push_back(pos);
     }
-    // the tail in pieces of about 50 / 30 / 20 %: what follows the last H2D (that piece's kernels and its D2H) is short
-    uint64_t rem = nchunks - pos;
-    if (rem > 3 * unit) { uint64_t take = ((rem / 2 + unit / 2) / unit) * unit; if (take == 0 || take >= rem) take = rem / 2; pos += take; ends.push_back(pos); rem = nchunks - pos; }
-    if (rem > 2 * unit) { uint64_t take = ((rem * 3 / 5 + unit / 2) / unit) * unit; if (take == 0 || take >= rem) take = rem / 2; pos += take; ends.push_back(pos); }
     if (pos < nchunks) ends.push_back(nchunks);
     return ends;
 }
@@ -411,6 +440,7 @@ struct HostOut {
 int ensureStaging(Ctx& c)
 {
     if (!c.copyIn) { CK(cudaStreamCreateWithFlags(&c.copyIn, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c.copyOut, cudaStreamNonBlocking)); }
+    for (auto& x : c.extra) if (!x) CK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         if (!c.stageIn[i]) CK(cudaMallocHost(&c.stageIn[i], kStageBlock));
         if (!c.stageOut[i]) CK(cudaMallocHost(&c.stageOut[i], kStageBlock));
@@ -451,7 +481,7 @@ int deliver(Ctx& c, HostOut& out, const uint8_t* d_from, size_t len, const Piece
                 if (out.firstSlice) {
                     out.firstSlice = false;
                     long long doneH2d = 0;
-                    if (probe) for (size_t q = 0; q < probe->issued; ++q) if (cudaEventQuery((*probe->ev)[2 * q]) == cudaSuccess) ++doneH2d;
+                    if (probe) for (size_t q = 0; q < probe->issued; ++q) if (cudaEventQuery((*probe->ev)[3 * q]) == cudaSuccess) ++doneH2d;
                     (void)cudaGetLastError();
                     t_sinkFirstH2dDone = doneH2d; t_sinkPieces = probe ? (long long)probe->total : 0;
                 }
@@ -478,13 +508,23 @@ int runHostSegment(Ctx& c, const uint8_t* src, size_t n, const uint8_t* histSrc,
     const bool srcPinned = isPinnedHost(src);
     const std::vector<uint64_t> ends = pieceSchedule(nchunks, chunk);
     const size_t np = ends.size();
-    while (c.pieceEv.size() < 2 * np) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.pieceEv.push_back(e); }
+    while (c.pieceEv.size() < 3 * np) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c.pieceEv.push_back(e); }
     rc = ensureBuf(c.hPiece, c.hPieceCap, 4 * np, true); if (rc) return rc;
+    rc = ensureBuf(c.dPiece, c.dPieceCap, 4 * np); if (rc) return rc;
     rc = preparePipeline(c, n, chunk, wantCk); if (rc) return rc;
+    // Two lanes: consecutive pieces alternate between two streams and the two halves of the scratch rows, so that the
+    // latency-bound kernels of one piece (K-HUFF, K-OFFS, the tails of the others) run beside the next piece's K-CAND / K-LZ.
+    uint64_t maxPiece = 0;
+    for (size_t p = 0; p < np; ++p) maxPiece = std::max(maxPiece, ends[p] - (p ? ends[p - 1] : 0));
+    int lanes = g_optLanes;
+    while (lanes > 1 && (uint64_t)lanes * maxPiece > c.slots) --lanes;
+    if (np < 2 || level == 0) lanes = 1;
+    const bool twoLanes = lanes > 1;
     // the copy streams must not touch the staging buffers before earlier work on the main stream is done with them
     CK(cudaEventRecord(c.ev[0], c.stream));
     CK(cudaStreamWaitEvent(c.copyIn, c.ev[0], 0));
     CK(cudaStreamWaitEvent(c.copyOut, c.ev[0], 0));
+    for (auto& x : c.extra) CK(cudaStreamWaitEvent(x, c.ev[0], 0));
     if (hist) CK(cudaMemcpyAsync(c.dIn, histSrc, hist, cudaMemcpyHostToDevice, c.copyIn));
     const uint8_t* d_src = c.dIn + hist;
     size_t inBlocks = 0, done = 0, nextDrain = 0, issued = 0;
@@ -504,12 +544,25 @@ int runHostSegment(Ctx& c, const uint8_t* src, size_t n, const uint8_t* histSrc,
                 CK(cudaEventRecord(c.stageInEv[sb], c.copyIn));
             }
         }
-        CK(cudaEventRecord(c.pieceEv[2 * p], c.copyIn));
-        CK(cudaStreamWaitEvent(c.stream, c.pieceEv[2 * p], 0));
-        int r = runChunks(c, d_src, n, hist, final, d_out, d_cap, level, chunk, dict, wantCk, firstChunk, ends[p], launches);
-        if (r) return r;
-        CK(cudaMemcpyAsync(c.hPiece + 4 * p, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
-        CK(cudaEventRecord(c.pieceEv[2 * p + 1], c.stream));
+        CK(cudaEventRecord(c.pieceEv[3 * p], c.copyIn));
+        const uint32_t ln = (uint32_t)(p % (size_t)lanes);
+        cudaStream_t st = ln ? c.extra[ln - 1] : c.stream;
+        CK(cudaStreamWaitEvent(st, c.pieceEv[3 * p], 0));
+        int r;
+        if (twoLanes) {
+            const Lane lane = { st, ln * (c.slots / lanes), c.slots / lanes, p ? c.pieceEv[3 * (p - 1) + 2] : nullptr,
+                                c.pieceEv[3 * p + 2], c.dPiece + 4 * p };
+            r = runChunks(c, d_src, n, hist, final, d_out, d_cap, level, chunk, dict, wantCk, firstChunk, ends[p], launches, &lane);
+            if (r) return r;
+            // offset, match and stored counts as this piece's K-OFFS left them; the flags as they are now
+            CK(cudaMemcpyAsync(c.hPiece + 4 * p, c.dPiece + 4 * p, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(c.hPiece + 4 * p + 1, c.total + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        } else {
+            r = runChunks(c, d_src, n, hist, final, d_out, d_cap, level, chunk, dict, wantCk, firstChunk, ends[p], launches);
+            if (r) return r;
+            CK(cudaMemcpyAsync(c.hPiece + 4 * p, c.total, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaEventRecord(c.pieceEv[3 * p + 1], st));
         firstChunk = ends[p];
         issued = p + 1;
         return ZZGPU_OK;
@@ -517,11 +570,11 @@ int runHostSegment(Ctx& c, const uint8_t* src, size_t n, const uint8_t* histSrc,
     // returns 0 when piece p was delivered, 1 when it is not ready yet (non-blocking mode), < 0 = -status
     auto drain = [&](size_t p, bool blocking) -> int {
         if (!blocking) {
-            const cudaError_t q = cudaEventQuery(c.pieceEv[2 * p + 1]);
+            const cudaError_t q = cudaEventQuery(c.pieceEv[3 * p + 1]);
             if (q == cudaErrorNotReady) { (void)cudaGetLastError(); return 1; }
             if (q != cudaSuccess) return -fail(ZZGPU_E_CUDA, "cudaEventQuery", q);
         } else {
-            const cudaError_t q = cudaEventSynchronize(c.pieceEv[2 * p + 1]);
+            const cudaError_t q = cudaEventSynchronize(c.pieceEv[3 * p + 1]);
             if (q != cudaSuccess) return -fail(ZZGPU_E_CUDA, "cudaEventSynchronize", q);
         }
         const uint64_t upto = c.hPiece[4 * p], flags = c.hPiece[4 * p + 1];
@@ -575,6 +628,7 @@ void drainStreams(Ctx& c)
 {
     if (c.copyIn) cudaStreamSynchronize(c.copyIn);
     if (c.stream) cudaStreamSynchronize(c.stream);
+    for (auto& x : c.extra) if (x) cudaStreamSynchronize(x);
     if (c.copyOut) cudaStreamSynchronize(c.copyOut);
     (void)cudaGetLastError();
 }
@@ -933,6 +987,10 @@ int zzgpu_checksums(const uint8_t* src, size_t n, int src_mem, uint32_t adler_st
 
 int zzgpu_set_option(const char* name, int value)
 {
+    if (name && !strcmp(name, "piece_first") && value >= 1 && value <= 65536) { g_pieceFirst = (uint64_t)value; return ZZGPU_OK; }
+    if (name && !strcmp(name, "piece_mid") && value >= 1 && value <= 65536) { g_pieceMid = (uint64_t)value; return ZZGPU_OK; }
+    if (name && !strcmp(name, "piece_last") && value >= 1 && value <= 65536) { g_pieceLast = (uint64_t)value; return ZZGPU_OK; }
+    if (name && !strcmp(name, "lanes") && value >= 1 && value <= kMaxLanes) { g_optLanes = (int)value; return ZZGPU_OK; }
     if (name && !strcmp(name, "segment_mib") && value >= 1 && value <= 65536) { g_segBytes = (size_t)value << 20; return ZZGPU_OK; }
     if (name && set_kernel_option(name, value)) return ZZGPU_OK;
     return fail(ZZGPU_E_ARG, "unknown option");

@@ -1650,7 +1650,10 @@ __global__ void __launch_bounds__(kHuffThreads) k_huffman(Job job)
 // this variant is used for launches large enough to fill the GPU several times over, the warp-per-chunk kernel
 // (half the latency) for the smaller pieces of the host-buffer pipeline.
 // ------------------------------------------------------------------------------------------------
-constexpr int kHuffLanes = 32;
+#ifndef ZZ_HUFF_LANES
+#define ZZ_HUFF_LANES 32
+#endif
+constexpr int kHuffLanes = ZZ_HUFF_LANES;
 #define HS(i) ((i) * kHuffLanes)
 
 __device__ __forceinline__ void heap_push_L(unsigned* h, int hole, int top, unsigned v)
@@ -1755,7 +1758,7 @@ __device__ __noinline__ void generate_codesL(const uint8_t* lens, int n, uint32_
     }
 }
 
-constexpr int kHuffLThreads = 32;
+constexpr int kHuffLThreads = kHuffLanes;
 constexpr int kHuffLSmem = 286 * kHuffLanes * 4;
 
 __global__ void __launch_bounds__(kHuffLThreads) k_huffman_lanes(Job job)
