@@ -14,7 +14,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"] + \
        [f"smsp__average_warps_issue_stalled_{k}_per_issue_active.ratio" for k in
         ("barrier", "long_scoreboard", "short_scoreboard", "wait", "mio_throttle", "lg_throttle", "branch_resolving", "math_pipe_throttle", "not_selected", "no_instruction")]
-short = {"k_candidates": "cand", "k_info": "info", "k_parse": "parse", "k_huffman": "huff", "k_huffman_lanes": "huff", "k_emit": "emit",
+short = {"k_lz": "lz", "k_stored": "stored", "k_candidates": "cand", "k_info": "info", "k_parse": "parse", "k_huffman": "huff", "k_huffman_lanes": "huff", "k_emit": "emit",
          "k_emit2": "emit", "k_checksums": "cksum", "k_offsets": "offs", "k_fixed": "fixed", "k_gather": "gather"}
 out = [f"# ncu --set full, {tag}\n", f"Command: `{cmd}` (after the same command exited 0 without ncu).\n"]
 traffic = {}
@@ -26,7 +26,7 @@ def tob(name, r):
 for r in rows[2:]:
     if not r or not r[0].isdigit():
         continue
-    k = r[H.index("Kernel Name")].replace("unnamed>::", "").split("(")[0]
+    k = r[H.index("Kernel Name")].replace("unnamed>::", "").split("(")[0].replace("void ", "").split("<")[0].strip()
     out.append(f"## {k}  grid {r[H.index('Grid Size')]} block {r[H.index('Block Size')]}\n")
     out.append("| metric | value | unit |\n|---|---|---|")
     for w in want:

@@ -188,6 +188,23 @@ __global__ void __launch_bounds__(32) k_candidates(Job job, int run)
                     const unsigned v = __funnelshift_r(swl[g4 * (G / 4) + u * 8], swl[g4 * (G / 4) + u * 8 + 1], sh) & 0xFFFFFFu;
                     h[u] = hash3(v);
                 }
+                // A run of one byte value (all G hashes equal): every position's candidate is its predecessor and the last
+                // one stays in the slot -- one exchange instead of G exchanges on the same word.
+                if (__all_sync(0xffffffffu, h[0] == h[U - 1] && h[0] == h[U / 2])) {
+                    bool uni = h[0] == (unsigned)__shfl_sync(0xffffffffu, (int)h[0], 0);
+#pragma unroll
+                    for (int u = 1; u < U; ++u) uni &= h[u] == h[0];
+                    if (__all_sync(0xffffffffu, uni)) {
+                        int pre = 0;
+                        if (lane == 0) pre = atomicExch(&table[h[0]], qs + G - 1);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int d = (u == 0 && lane == 0) ? qs - pre : 1;
+                            outp[g4 * G + u * 32] = (uint16_t)(d < kMaxDistance ? d : 0);
+                        }
+                        continue;
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < U; ++u) old[u] = atomicExch(&table[h[u]], qs + u * 32 + lane);
                 bool bad = false;
