@@ -81,7 +81,8 @@ ZZGPU_API int zzgpu_device_count(void);
 ZZGPU_API const char* zzgpu_strerror(int status);
 ZZGPU_API const char* zzgpu_last_error(void);
 
-/* Tuning knobs that do not change the produced bytes (A/B switches of kernel variants; see zz_cabi.cu for the names).
+/* Tuning knobs that do not change the produced bytes: "tma", "spec", "region" (K-LZ variants, 0/1), "lanes" (1-4 kernel
+ * streams of the host-buffer path), "piece_first" / "piece_mid" / "piece_last" (piece schedule, chunks), "segment_mib".
  * Unknown names return ZZGPU_E_ARG. */
 ZZGPU_API int zzgpu_set_option(const char* name, int value);
 
