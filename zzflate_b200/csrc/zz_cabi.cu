@@ -385,7 +385,9 @@ int runChunks(Ctx& c, const uint8_t* d_src, size_t n, size_t history, int final,
         }
         if (level == 1) { launches += launch_gather(job, st); rc = markStage(c, ZZGPU_STAGE_GATHER, st); if (rc) return rc; }
         else { launches += launch_emit(job, st); rc = markStage(c, ZZGPU_STAGE_EMIT, st); if (rc) return rc; }
-        if (wantCk) { launches += launch_checksums(job, st); rc = markStage(c, ZZGPU_STAGE_CKSUM, st); if (rc) return rc; }
+        if (wantCk && !(level >= 2 && wantCk == 1)) {       // levels 2/3 with Adler-32 only (zlib): the sum is taken inside K-LZ
+            launches += launch_checksums(job, st); rc = markStage(c, ZZGPU_STAGE_CKSUM, st); if (rc) return rc;
+        }
     }
     CK(cudaGetLastError());
     return ZZGPU_OK;

@@ -661,6 +661,10 @@ __device__ __forceinline__ unsigned lz_lookup(const unsigned* exList, int exN, i
     return nb;
 }
 
+// Adler-32 partial of the chunk (defined with K-CKSUM below).  The chunk went through this kernel's window a moment ago,
+// so the pass finds it in L2 instead of HBM, and the separate checksum launch is gone when only Adler-32 is wanted.
+__device__ __forceinline__ void lz_checksums(const uint8_t* p, int n, uint32_t* ck, uint8_t* scratch);
+
 __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int useSpec, int useRegion)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -1015,9 +1019,11 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                 }
                 chase_barrier();
                 if (warp == 0) {
+                    __syncwarp();
                     int cur = bIn, npre = 0;
                     const int tokBase = ps.ntok;
                     bool alive = true;
+
                     if (cur < base) {
                         // entry state far behind the arrays: every usable position of the sub-batch is far enough, the first one is taken
                         const unsigned w0 = nzw[0];
@@ -1033,6 +1039,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                             cur = nb;
                         }
                     }
+
                     int endsAt = -1;                                       // orbit state with succ == 0 that ended the walk (it yields no token)
                     if (alive && cur < s1) {
                         // bit t of okRun: segment t is entered through its link provided segment t-1's chain is the orbit and leaves into it
@@ -1042,6 +1049,12 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                         int guard3 = 0; (void)guard3;
                         for (;;) {
                             if (cur >= s1) break;
+                            // The lanes of this warp all carry the walk's state, but nothing makes them run in lockstep (a warp
+                            // that split at an `if (lane == 0)` or in the links may stay split: seen on the hardware, where one
+                            // group of lanes then missed the join another group had just recorded).  The walk is written so that
+                            // every group takes the same path whatever the skew: what it writes is idempotent (bitmap ORs, the
+                            // same values into segMp), and the one thing it reads back, segMp[i], counts as "not joined yet"
+                            // also when it already holds this very state (a faster group of the same warp put it there).
                             LZ_GUARD(guard3, 2 * kSub, 5, cur, base)
                             LZ_CHECK(cur >= base, 6, cur, base);
                             const int r = cur - base;
@@ -1053,7 +1066,8 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                             if (marked) {
                                 int i = r / kSegStates; if (i > kChains - 1) i = kChains - 1;
                                 const unsigned iKS = stopKS[i];
-                                if ((iKS >> 16) != 0u && segMp[i] == 0xFFFFu) {
+                                const unsigned mpNow = segMp[i];
+                                if ((iKS >> 16) != 0u && (mpNow == 0xFFFFu || mpNow == (unsigned)cur)) {
                                     // the walk stepped on chain i: the chain is the orbit from here on, and so are the chains of the
                                     // following segments as long as each one's link joined it
                                     joined = true;
@@ -1367,6 +1381,10 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
         job.hist[(size_t)slot * kHistStride + i] = s;
     }
     if (tid == 0) job.state[slot].ntok = ps.ntok;
+    if (job.want_checksums == 1) {
+        __syncthreads();                                            // the coverage bitmap is dead: its space is the scratch
+        lz_checksums(chunk0, g.n, job.ck + 2 * (job.first_chunk + slot), smem + 32768);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2427,15 +2445,18 @@ constexpr int kCkSlice = 256;
 // XOR-/sum-reduced.  The chunk's standard CRC adds the propagated 0xFFFFFFFF preset and the final inversion.
 // kWant: bit 0 Adler-32, bit 1 CRC-32 (the Zlib trailer needs only the first, the Gzip trailer only the second; the CRC's
 // table look-ups are the expensive half)
+// Scratch of checksum_chunk: 4 KiB + 160 B of shared memory (static in K-CKSUM / K-STORED, a dead part of the dynamic
+// allocation in K-LZ).  Works with any CTA of >= 256 threads: threads from 256 on have no slice.
+struct CkShared { uint32_t tab[4][256]; unsigned long long redA[8], redB[8]; uint32_t redC[8]; };
+
 template <int kWant>
-__device__ __forceinline__ void checksum_chunk(const Job& job, unsigned slot, const Geom& g)
+__device__ __forceinline__ void checksum_chunk(const Job& job, unsigned slot, const Geom& g, CkShared& cs)
 {
-    __shared__ uint32_t tab[4][256];
-    __shared__ unsigned long long redA[8], redB[8];
-    __shared__ uint32_t redC[8];
+    uint32_t (*tab)[256] = cs.tab;
+    unsigned long long* redA = cs.redA; unsigned long long* redB = cs.redB; uint32_t* redC = cs.redC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (kWant & 2) {
-        for (int k = 0; k < 4; ++k) tab[k][tid] = c_crcTable[k][tid];
+        if (tid < 256) for (int k = 0; k < 4; ++k) tab[k][tid] = c_crcTable[k][tid];
         __syncthreads();
     }
     const uint8_t* p = job.src + g.off;
@@ -2480,7 +2501,7 @@ __device__ __forceinline__ void checksum_chunk(const Job& job, unsigned slot, co
         s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         crc ^= __shfl_xor_sync(0xffffffffu, crc, o);
     }
-    if (lane == 0) { redA[warp] = s1; redB[warp] = s2; redC[warp] = crc; }
+    if (lane == 0 && warp < kCkThreads / 32) { redA[warp] = s1; redB[warp] = s2; redC[warp] = crc; }
     __syncthreads();
     if (tid == 0) {
         unsigned long long a = 0, b = 0; uint32_t c = 0;
@@ -2495,11 +2516,53 @@ __device__ __forceinline__ void checksum_chunk(const Job& job, unsigned slot, co
     }
 }
 
+// Adler-32 partial (start 0) of the chunk by all threads of a K-LZ CTA, in the tail of the kernel: coalesced 16-byte
+// loads, several in flight per thread (the slice layout of checksum_chunk needs ~19 us of latency per chunk, far too
+// long for a tail).  With b = sum (n - i) d_i:  a vector at offset o contributes (n - o) S - W, S = sum of its bytes,
+// W = sum j d_j over its 16 bytes.  Only the Adler sum is fused (zlib framing); a wanted CRC keeps its own launch.
+__device__ __forceinline__ void lz_checksums(const uint8_t* p, int n, uint32_t* ck, uint8_t* scratch)
+{
+    // (inlined, plain values: as a called function it cost K-LZ 0.9 ms per GiB, and a reference to the Job moved the kernel's
+    // parameters to the stack)
+    unsigned long long* redA = reinterpret_cast<unsigned long long*>(scratch);
+    unsigned long long* redB = redA + 32;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    int head = (int)((16u - (unsigned)(reinterpret_cast<uintptr_t>(p) & 15)) & 15u); if (head > n) head = n;
+    const int nvec = (n - head) >> 4;
+    const int tail0 = head + nvec * 16;
+    unsigned long long A = 0, B = 0;
+    if (tid < head) { const unsigned v = p[tid]; A += v; B += (unsigned long long)(n - tid) * v; }
+    if (tid < n - tail0) { const int i = tail0 + tid; const unsigned v = p[i]; A += v; B += (unsigned long long)(n - i) * v; }
+    const uint4* pv = reinterpret_cast<const uint4*>(p + head);
+    unsigned a32 = 0; unsigned long long b64 = 0;
+#pragma unroll 4
+    for (int v = tid; v < nvec; v += nthr) {
+        const uint4 q = __ldg(pv + v);
+        const unsigned s0 = __dp4a(q.x, 0x01010101u, 0u), s1 = __dp4a(q.y, 0x01010101u, 0u), s2 = __dp4a(q.z, 0x01010101u, 0u), s3 = __dp4a(q.w, 0x01010101u, 0u);
+        const unsigned S = s0 + s1 + s2 + s3;
+        const unsigned W = __dp4a(q.x, 0x03020100u, 0u) + __dp4a(q.y, 0x03020100u, 0u) + __dp4a(q.z, 0x03020100u, 0u) + __dp4a(q.w, 0x03020100u, 0u)
+                           + 4u * s1 + 8u * s2 + 12u * s3;
+        a32 += S;
+        b64 += (unsigned long long)(unsigned)(n - head - 16 * v) * S - W;
+    }
+    A += a32; B += b64;
+    for (int o = 16; o; o >>= 1) { A += __shfl_xor_sync(0xffffffffu, A, o); B += __shfl_xor_sync(0xffffffffu, B, o); }
+    if (lane == 0) { redA[warp] = A; redB[warp] = B; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long a = 0, b = 0;
+        for (int w = 0; w < nthr / 32; ++w) { a += redA[w]; b += redB[w]; }
+        ck[0] = (uint32_t)(((b % 65521ull) << 16) | (a % 65521ull));
+        ck[1] = 0;
+    }
+}
+
 template <int kWant>
 __global__ void __launch_bounds__(kCkThreads) k_checksums(Job job)
 {
+    __shared__ CkShared cs;
     const unsigned slot = blockIdx.x;
-    checksum_chunk<kWant>(job, slot, chunk_geom(job, slot));
+    checksum_chunk<kWant>(job, slot, chunk_geom(job, slot), cs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2542,7 +2605,7 @@ __global__ void __launch_bounds__(kCkThreads) k_stored(Job job)
         st.ntok = 0; st.block_type = 0; st.hdr_bits = 0; st.total_bits = 0; st.out_bytes = bytes; st.out_off = off;
         if (slot == job.nchunks - 1) { job.total[0] = off + bytes; job.total[3] += job.nchunks; }
     }
-    if (kWant) checksum_chunk<(kWant ? kWant : 3)>(job, slot, g);
+    if (kWant) { __shared__ CkShared cs; checksum_chunk<(kWant ? kWant : 3)>(job, slot, g, cs); }
 }
 
 }  // namespace
