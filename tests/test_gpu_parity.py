@@ -377,8 +377,8 @@ def test_device_resident_buffers(zz, oracle):
 def test_regressions_found_by_fuzzing(zz, oracle):
     """tests/golden/regress/*.bin: inputs on which tools/gpu_fuzz.py once found a mismatch (file name carries level,
     chunk and dictionary size).  fuzz_1_3613: a match of >= 32 bytes whose backward extension is so long that it ends
-    inside the tile of the state it was taken from (R6 territory, lb = 258).  lzwalk_*: inputs on which K-LZ's chase warps
-    once ran their named barrier while lane 0 was still split off by an `if (tid == 0)` store (tools/gpu_lz_check.py)."""
+    inside the tile of the state it was taken from (R6 territory, lb = 258).  lzwalk_*: inputs on which the lanes of K-LZ's walking warp ran as
+    two groups and the slower one missed a join the faster one had recorded (found by tools/gpu_lz_check.py)."""
     import re
     from pathlib import Path
     files = sorted((Path(__file__).parent / "golden" / "regress").glob("*.bin"))
