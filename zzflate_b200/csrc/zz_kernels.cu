@@ -431,10 +431,13 @@ constexpr int kLzWin = 32 + kLzBack + kSub + kLzAhead + 16;
 static_assert(kLzWin % 16 == 0 && kLzWin < 65536, "window offsets are kept in 16 bits");
 constexpr int kSubTiles = kSub / 32;
 constexpr int kSubWords = kSubTiles + 5;
-constexpr int kSegStates = 64;                            // states per lane in the speculative pass
+#ifndef ZZ_SEG_STATES
+#define ZZ_SEG_STATES 64
+#endif
+constexpr int kSegStates = ZZ_SEG_STATES;                 // states per lane in the speculative pass
 constexpr int kChains = kSub / kSegStates;
 constexpr int kChaseWarps = kChains / 32;
-static_assert(kChains % 32 == 0 && kChaseWarps <= 4 && kChaseWarps <= kLzWarps && kSubTiles <= kLzThreads && kSub % (4 * kLzThreads) == 0, "geometry");
+static_assert(kChains % 32 == 0 && kChaseWarps <= 8 && kChaseWarps < kLzWarps && kSubTiles <= kLzThreads && kSub % (4 * kLzThreads) == 0, "geometry");
 constexpr int kLzQueue = 32 + 128;
 constexpr int kExCap = 256;                               // exactly measured long matches remembered per sub-batch
 constexpr int kRegionMax = kSub + 512;                    // positions whose literals / match symbols are counted in one go beside the walk
@@ -446,6 +449,13 @@ static_assert(4 * kSubWords * 4 + 544 + (kSub / 4 + 40) * 2 <= kLzScratch, "bitm
 constexpr int kLzSmem = kLzWin + (kSub + 64) + (kSub + 64) * 2 + kLzScratch;
 static_assert(3 * (kLzSmem + 2048) <= 227 * 1024, "three K-LZ CTAs per SM");
 
+// phase shares of a K-LZ CTA (diagnostic build -DZZ_PHASE_TIMING: thread 0's clock at the phase boundaries)
+#ifdef ZZ_PHASE_TIMING
+__device__ unsigned long long g_lzPhase[12];
+#define PT(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); phaseAcc[k] += (unsigned long long)(t_ - phaseT); phaseT = t_; } } while (0)
+#else
+#define PT(k)
+#endif
 #ifdef ZZ_LZ_CHECKS
 __device__ unsigned g_lzDebug[8];
 #define LZ_CHECK(cond, code, a, b) do { if (!(cond)) { if (atomicCAS(&g_lzDebug[0], 0u, (unsigned)(code)) == 0u) { g_lzDebug[1] = (unsigned)(a); g_lzDebug[2] = (unsigned)(b); g_lzDebug[3] = blockIdx.x; g_lzDebug[4] = threadIdx.x; } } } while (0)
@@ -686,12 +696,17 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
     __shared__ uint16_t stopT[kChains];              // where the chain left its segment (kind 3)
     __shared__ uint16_t linkArr[kChains];            // state where the link joined the chain, 0xFFFF = it did not
     __shared__ uint16_t segMp[kChains];              // first state of the chain that belongs to the orbit, 0xFFFF = none
-    __shared__ unsigned k3Mask[4], lkMask[4], linkedW[4];
+    __shared__ unsigned k3Mask[8], lkMask[8], linkedW[8];      // one bit per chain: left its segment / its link joined / entered through the link
     __shared__ unsigned grpMin[kSubWords / 32 + 2];
     __shared__ unsigned hist4[kHistCopies * kHistStride];     // literal/length + distance histograms (private copies)
     __shared__ unsigned rcov[kRegionWords];                   // region: bit per position, covered by a match
     __shared__ uint16_t rbase[kRegionWords];                  // region: literals before each 32-position word
 
+#ifdef ZZ_PHASE_TIMING
+    __shared__ unsigned long long phaseAcc[12];
+    __shared__ long long phaseT;
+    if (threadIdx.x == 0) { for (int k = 0; k < 12; ++k) phaseAcc[k] = 0; phaseT = clock64(); }
+#endif
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -709,7 +724,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
     if (tid == 0) {
         ps.pos = 0; ps.ntok = 0; ps.nexcl = 0; ps.npend = 0; ps.exN = 0; ps.err = 0;
         ps.histPos = 0; ps.histTok = 0; ps.regEnd = 0; ps.regTok = 0; ps.histStop = 0; ps.nlits = 0; ps.regLits = 0;
-        for (int w = 0; w < 4; ++w) { k3Mask[w] = 0; lkMask[w] = 0; }
+        for (int w = 0; w < 8; ++w) { k3Mask[w] = 0; lkMask[w] = 0; }
         mbar_init(&mbar, 1);
     }
     __syncthreads();
@@ -768,6 +783,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                 parity ^= 1u;
             }
             __syncthreads();
+            PT(0);
             if (firstSub) {
                 // ---- first probe of the batch: j == backRefEnd, no backward room (encoder.cpp:384-386) ----
                 firstSub = false;
@@ -787,6 +803,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                 __syncthreads();
                 if (ps.b >= s1n) { __syncthreads(); s0 = s1n; continue; }
             }
+            PT(1);
             const int bIn = ps.b;
             int lowb = bIn > s0 - 64 ? bIn : s0 - 64; if (lowb > s0) lowb = s0;
             const int base = lowb & ~31;
@@ -897,10 +914,11 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                 if (tid < 16) *reinterpret_cast<unsigned*>(info + lim + 4 * tid) = 0u;      // look-ahead of the last states
             }
             __syncthreads();
+            PT(2);
             // the queues are drained: their space now holds the bitmaps, nzw and the state list
             for (int t = tid; t < kSubWords; t += kLzThreads) { Sb[t] = 0; Tb[t] = 0; Lb[t] = 0; }
             if (tid < kChains) segMp[tid] = 0xFFFFu;
-            if (tid < 4) linkedW[tid] = 0;
+            if (tid < 8) linkedW[tid] = 0;
             if (tid < ps.npend && tid < 8) {                      // positions whose candidate changes with the parse
                 const int pj = ps.pendJ[tid];
                 const int pd = lz_effective_cand(cand, &ps, pj, (int)dist[pj - base]);
@@ -935,6 +953,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
             const unsigned nlit0 = ps.nlits;
             const int regSpan = rB - (rA & ~31);
             const bool regionNow = useRegion && !ps.histStop && rB > rA && regSpan <= kRegionMax;
+            PT(3);
 
             // ---- C: the orbit of succ from the entry state ----
             if (warp < kChaseWarps) {
@@ -990,6 +1009,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                 stopKS[ci] = ((unsigned)kind << 16) | (unsigned)state;
                 stopT[ci] = (uint16_t)(tgt < 65535 ? tgt : 65535);
                 chase_barrier();
+                PT(4);
                 // links: lane i follows succ from the state where lane i-1's chain entered segment i until it steps on its own
                 // chain.  If lane i-1's chain turns out to be the orbit, so is lane i's from that state on.
                 int linkMp = -1;
@@ -1018,6 +1038,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                     if (lane == 0) { k3Mask[warp] = m1; lkMask[warp] = m2; }
                 }
                 chase_barrier();
+                PT(5);
                 if (warp == 0) {
                     __syncwarp();
                     int cur = bIn, npre = 0;
@@ -1043,9 +1064,9 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                     int endsAt = -1;                                       // orbit state with succ == 0 that ended the walk (it yields no token)
                     if (alive && cur < s1) {
                         // bit t of okRun: segment t is entered through its link provided segment t-1's chain is the orbit and leaves into it
-                        const unsigned long long k3lo = k3Mask[0] | ((unsigned long long)k3Mask[1] << 32), k3hi = k3Mask[2] | ((unsigned long long)k3Mask[3] << 32);
-                        const unsigned long long lklo = lkMask[0] | ((unsigned long long)lkMask[1] << 32), lkhi = lkMask[2] | ((unsigned long long)lkMask[3] << 32);
-                        const unsigned long long okLo = (k3lo << 1) & lklo, okHi = ((k3hi << 1) | (k3lo >> 63)) & lkhi;
+                        unsigned okW[kChaseWarps];
+#pragma unroll
+                        for (int w = 0; w < kChaseWarps; ++w) okW[w] = ((k3Mask[w] << 1) | (w ? k3Mask[w - 1] >> 31 : 0u)) & lkMask[w];
                         int guard3 = 0; (void)guard3;
                         for (;;) {
                             if (cur >= s1) break;
@@ -1074,11 +1095,18 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                                     // run of ones in okRun from bit i+1 on
                                     int last = i;
                                     if (i + 1 < kChains) {
-                                        const int t = i + 1;                          // 1 <= t <= 127
-                                        const unsigned long long v0 = t < 64 ? ((okLo >> t) | (okHi << (64 - t))) : (okHi >> (t - 64));
-                                        const unsigned long long v1 = t < 64 ? (okHi >> t) : 0ull;
-                                        const int run = ~v0 ? __ffsll((long long)~v0) - 1 : 64 + __ffsll((long long)~v1) - 1;
-                                        last = i + run;
+                                        int t = i + 1;                                // ends as the first index that is not in the run
+                                        bool stop = false;
+#pragma unroll
+                                        for (int w = 0; w < kChaseWarps; ++w) {
+                                            if (!stop && (t >> 5) == w) {
+                                                const int sh = t & 31, room = 32 - sh;
+                                                const unsigned inv = ~(okW[w] >> sh);         // the sh bits shifted in at the top read as "end of word"
+                                                const int z = inv ? __ffs(inv) - 1 : 32;
+                                                if (z < room) { t += z; stop = true; } else t += room;
+                                            }
+                                        }
+                                        last = t - 1;
                                     }
                                     if (lane == 0) segMp[i] = (uint16_t)cur;
                                     for (int t = i + 1 + lane; t <= last; t += 32) { segMp[t] = linkArr[t]; atomicOr(&linkedW[t >> 5], 1u << (t & 31)); }
@@ -1165,6 +1193,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                         __syncwarp();
                     }
                     if (lane == 0) { ps.b = cur; ps.npre = npre; ps.endsAt = endsAt; }
+                    PT(6);
                 }
             } else if (regionNow) {
                 // ---- beside the walk: GetFrequencies (encoder.cpp:442-471) for the region the previous sub-batches finished.  Its
@@ -1224,6 +1253,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
                 if (regionNow) { ps.histPos = rB; ps.histTok = tB; ps.nlits = nlit0 + ps.regLits; }
                 else if (regSpan > kRegionMax) ps.histStop = 1;        // too much at once: left to the end
             }
+            PT(7);
 
             // ---- D: the orbit's states, compacted, then expanded to tokens in parallel ----
             {
@@ -1285,6 +1315,7 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
             }
             __syncthreads();
             s0 = s1;
+            PT(8);
         }
         if (tid == 0) {
             const int finalB = ps.b;
@@ -1385,6 +1416,10 @@ __global__ void __launch_bounds__(kLzThreads, 3) k_lz(Job job, int useTma, int u
         __syncthreads();                                            // the coverage bitmap is dead: its space is the scratch
         lz_checksums(chunk0, g.n, job.ck + 2 * (job.first_chunk + slot), smem + 32768);
     }
+#ifdef ZZ_PHASE_TIMING
+    PT(9);
+    if (threadIdx.x == 0) for (int k = 0; k < 12; ++k) atomicAdd(&g_lzPhase[k], phaseAcc[k]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2682,6 +2717,18 @@ bool set_kernel_option(const char* name, int value)
 int launch_lz(const Job& job, cudaStream_t s)
 {
     k_lz<<<job.nchunks, kLzThreads, kLzSmem, s>>>(job, g_optTma, g_optSpec, g_optRegion);
+#ifdef ZZ_PHASE_TIMING
+    {
+        cudaStreamSynchronize(s);
+        unsigned long long h[12] = { 0 }; cudaMemcpyFromSymbol(h, g_lzPhase, sizeof h);
+        double tot = 0; for (int k = 0; k < 12; ++k) tot += (double)h[k];
+        static const char* names[12] = { "window", "firstprobe", "A", "preC", "chains", "links", "walk", "waitC", "D", "flush", "", "" };
+        fprintf(stderr, "K-LZ phases (share of CTA time, tid 0):");
+        for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1f%%", names[k], 100.0 * (double)h[k] / (tot > 0 ? tot : 1));
+        fprintf(stderr, "  | cycles per chunk %.0f\n", tot / (double)job.nchunks);
+        unsigned long long z[12] = { 0 }; cudaMemcpyToSymbol(g_lzPhase, z, sizeof z);
+    }
+#endif
 #ifdef ZZ_LZ_CHECKS
     {   // diagnostic build: bounds and loop guards inside K-LZ report the first violation
         const cudaError_t e = cudaStreamSynchronize(s);
