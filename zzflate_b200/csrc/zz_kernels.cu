@@ -2278,10 +2278,37 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K-FIXED (level 1) : WriteBlockFixedHuff, encoder.cpp:329-373.  The level-1 parse is sequential by
-// construction (only visited positions enter the hash table, and the hash is taken one byte ahead), so one
-// lane walks the chunk; the other lanes prime the table and verify long matches.  Bits go to the chunk's
-// scratch slot; K-OFFS + k_gather place them in the stream.
+// K-FIXED (level 1) : WriteBlockFixedHuff, encoder.cpp:329-373.  Only the positions the walk visits enter the hash table
+// (table[h(i+1)] = i), so the candidates depend on the parse and the chunk is one sequential chain.  A pair of warps
+// takes a chunk: the *walker* (warp 0) advances in steps of 32 positions and keeps everything the next step depends
+// on -- hash table, candidates, the step's matches; the *emitter* (warp 1) turns what the walker decided into codes,
+// scans the bit counts, packs and flushes.  Bits go to the chunk's scratch slot; K-OFFS + k_gather place them in the
+// stream.
+//
+// A step.  The walker presumes that all 32 positions are visited.  Every lane knows two match lengths before the step
+// is settled: mOld against the table's entry (its candidate if no lower lane of the step with the same hash is visited)
+// and mLow against the nearest lower lane of its hash group (its candidate if that lane is visited).  The matches of
+// the step are then settled one after the other without any further memory access, one shuffle per match: a lane
+// without a lower lane of its hash group has one possible candidate (the table's), so only the lanes that do are
+// evaluated against the visited set when the walk reaches them.  A lane whose true candidate is neither (a lower lane of
+// its group that is not the nearest one) ends the step in front of it; a match of >= 8 bytes (exact length needed: a
+// warp-wide gather) ends the step behind it.  On the text workload a step covers 32.7 positions (the first
+// formulation, which ended a step at its first match: 8.6).  tools/model/l1_model.c states the step logic in plain C
+// and is fuzzed against the sequential walk.
+//
+// Whether two lanes of a step share a hash is found out on the table itself: every lane reads its slot, then writes
+// its own position, then reads the slot back -- a lane that finds another position there shares the slot.  Only then is
+// the same-hash mask computed (13 ballots; __match_any_sync held the warp for ~300 cycles per step) and the slots put
+// back; otherwise (94 % of the steps on random bytes, 57 % on text) every lane owns its slot and the lanes that turn out
+// not to be visited restore what they found.  The bytes of the table's candidates are requested before that exchange
+// and used after it.
+//
+// The input is staged through a 1 KiB shared-memory ring in 256-byte tiles (cp.async, 16 bytes per lane, two tiles
+// ahead of the walk), the walker leaves one word per lane (nothing / literal / match / end of block) in a two-slot
+// queue, two named barriers per slot (full / empty: barrier.sync on one side, barrier.arrive on the other) order it.
+// 17.3 KiB of shared memory and five barriers per chunk: twelve chunks per SM (the hash table sets that limit).
+// ncu (profiles/r02m_fixed.md): the walker is one dependent chain at one warp per scheduler -- the gather of the
+// candidates' bytes is 11-16 % of it, the rest is fixed-latency dependencies spread over the whole step.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned fixed_lit_code(unsigned v, int& len)     // fixedhuffmanluts.cpp:5 (RFC 1951 3.2.6)
 {
@@ -2291,46 +2318,261 @@ __device__ __forceinline__ unsigned fixed_lit_code(unsigned v, int& len)     // 
     len = 8; return __brev(0xC0u + (v - 280)) >> 24;
 }
 
-// One warp per chunk.  The level-1 walk inserts only the positions it visits, so candidates depend on the parse;
-// the warp speculates that the next 32 positions are all visited (true up to and including the first match of the
-// step), finds candidates like K-CAND (same-hash lower lane, else the table), verifies them, commits the lanes up
-// to the first match and jumps behind it.  Bits of a step are assembled in a small shared-memory window and
-// written to the chunk's scratch slot word by word.
-__global__ void __launch_bounds__(32) k_fixed(Job job)
+constexpr int kFxTile = 256, kFxRing = 4 * kFxTile, kFxAhead = 2;
+
+__device__ __forceinline__ void cp_async16(void* smemDst, const void* gsrc)
 {
-    // The table holds positions modulo 65536 in 16 bits (16 KiB per warp: twice the resident warps of an int table).
-    // age = (i - entry) & 0xFFFF is exact while it stays below 65536: a sweep every 8192 positions turns the entries that
-    // are more than 32768 behind (invalid from then on, encoder.cpp:347) into "empty" ones of age 40000, so no entry ever
-    // gets older than ~48500 positions.
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+struct FxRing {
+    uint8_t* ring;            // kFxRing bytes, 16-byte aligned; byte u of the chunk's staging coordinate lives at ring[u & (kFxRing-1)]
+    long long gb;             // global address of u = 0 (16-byte aligned; may lie before the readable stream)
+    long long lo, hi;         // readable stream as addresses
+    int issued;               // next tile to stage
+    int ready;                // tiles <= ready are visible to the warp
+};
+
+__device__ __forceinline__ void fx_issue_tile(const FxRing& r, int t, int lane)
+{
+    const int u0 = t * kFxTile + 16 * lane;
+    const long long ga = r.gb + u0;
+    uint8_t* dst = r.ring + (u0 & (kFxRing - 1));
+    if (lane >= kFxTile / 16) {
+    } else if (ga >= r.lo && ga + 16 <= r.hi) {
+        cp_async16(dst, reinterpret_cast<const void*>(ga));
+    } else {
+        unsigned w[4] = { 0, 0, 0, 0 };
+        for (int k = 0; k < 16; ++k)
+            if (ga + k >= r.lo && ga + k < r.hi) w[k >> 2] |= (unsigned)*reinterpret_cast<const uint8_t*>(ga + k) << (8 * (k & 3));
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    cp_async_commit();
+}
+
+// makes the bytes up to staging coordinate uHi readable (a step looks at most 38 bytes ahead of its first position, so it
+// touches two tiles at most: the four slots hold those and the two tiles being fetched; a long match may carry the walk
+// over a whole tile, the tiles it skips are fetched all the same)
+__device__ __forceinline__ void fx_ensure(FxRing& r, int uHi, int lane)
+{
+    const int tNeed = uHi / kFxTile;
+    if (tNeed > r.ready) {
+        while (r.issued <= tNeed + kFxAhead) { fx_issue_tile(r, r.issued, lane); ++r.issued; }
+        cp_async_wait_group<kFxAhead>();
+        __syncwarp();
+        r.ready = tNeed;
+    }
+}
+
+__device__ __forceinline__ unsigned long long fx_load8(const FxRing& r, int u)
+{
+    const unsigned* w = reinterpret_cast<const unsigned*>(r.ring);
+    const int i0 = (u >> 2) & (kFxRing / 4 - 1), i1 = (i0 + 1) & (kFxRing / 4 - 1), i2 = (i0 + 2) & (kFxRing / 4 - 1);
+    const unsigned a = w[i0], b = w[i1], c = w[i2];
+    const int sh = (u & 3) * 8;
+    return (unsigned long long)__funnelshift_r(a, b, sh) | ((unsigned long long)__funnelshift_r(b, c, sh) << 32);
+}
+
+__device__ __forceinline__ int equal_bytes8(unsigned long long x) { return x ? ((__ffsll((long long)x) - 1) >> 3) : 8; }
+
+constexpr int kFxQ = 2;
+constexpr unsigned kFxLit = 0x80000000u, kFxMatch = 0x40000000u, kFxEob = 0x20000000u;
+
+// barrier ids are immediates: with ids in registers ptxas reserves all 16 named barriers for the CTA, and the SM's barrier
+// pool then admits four CTAs instead of twelve (measured: 24.8 instead of 32.7 GB/s on random bytes)
+template <int ID> __device__ __forceinline__ void fx_bar_sync_c() { asm volatile("barrier.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <int ID> __device__ __forceinline__ void fx_bar_arrive_c() { asm volatile("barrier.arrive %0, 64;" ::"n"(ID) : "memory"); }
+// slot s of the queue: barrier 1 + s = "full", barrier 1 + kFxQ + s = "empty" (kFxQ == 2)
+__device__ __forceinline__ void fx_wait_full(unsigned s) { __syncwarp(); if (s == 0) fx_bar_sync_c<1>(); else fx_bar_sync_c<2>(); }
+__device__ __forceinline__ void fx_wait_empty(unsigned s) { __syncwarp(); if (s == 0) fx_bar_sync_c<3>(); else fx_bar_sync_c<4>(); }
+__device__ __forceinline__ void fx_post_full(unsigned s) { __syncwarp(); if (s == 0) fx_bar_arrive_c<1>(); else fx_bar_arrive_c<2>(); }
+__device__ __forceinline__ void fx_post_empty(unsigned s) { __syncwarp(); if (s == 0) fx_bar_arrive_c<3>(); else fx_bar_arrive_c<4>(); }
+
+// gload8 in two halves, so that the loads are in flight while the step does other things: the two aligned words now, the value later
+struct Raw8 { unsigned long long x, y; int sh; };
+__device__ __forceinline__ Raw8 gload8_issue(const uint8_t* p, const uint8_t* lo, const uint8_t* hi)
+{
+    Raw8 r;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint8_t* al = reinterpret_cast<const uint8_t*>(a & ~(uintptr_t)7);
+    if (al >= lo && al + 16 <= hi) {
+        r.x = __ldg(reinterpret_cast<const unsigned long long*>(al));
+        r.y = __ldg(reinterpret_cast<const unsigned long long*>(al) + 1);
+        r.sh = (int)(a & 7) * 8;
+    } else {
+        r.x = gload8(p, lo, hi); r.y = 0; r.sh = 0;
+    }
+    return r;
+}
+__device__ __forceinline__ unsigned long long gload8_value(const Raw8& r) { return r.sh ? ((r.x >> r.sh) | (r.y << (64 - r.sh))) : r.x; }
+
+// lanes whose 13-bit value equals mine (the result of __match_any_sync among the valid lanes), from 13 ballots
+__device__ __forceinline__ unsigned fx_same_hash(unsigned h, bool valid, int lane)
+{
+    unsigned m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < kHashBits; ++b) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (h >> b) & 1u);
+        m &= ((h >> b) & 1u) ? bal : ~bal;
+    }
+    return valid ? m : (1u << lane);
+}
+
+__global__ void __launch_bounds__(64) k_fixed(Job job)
+{
+    // The table holds positions modulo 65536 in 16 bits (16 KiB per chunk).  age = (i - entry) & 0xFFFF is exact while it
+    // stays below 65536: a sweep every 8192 positions turns the entries that are more than 32768 behind (invalid from then
+    // on, encoder.cpp:347) into "empty" ones of age 40000, so no entry ever gets older than ~48500 positions.
     __shared__ unsigned short table[kHashSize];
+    __shared__ __align__(16) uint8_t ringMem[kFxRing];
+    __shared__ unsigned queue[kFxQ * 32];
     __shared__ unsigned obuf[16];
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool walker = threadIdx.x < 32;
     const unsigned ltMask = (1u << lane) - 1u;
     constexpr int kEmptyAge = 40000, kSweep = 8192;
-    for (int i = lane; i < kHashSize; i += 32) table[i] = (unsigned short)(0 - kEmptyAge);
-    if (lane < 16) obuf[lane] = 0;
-    __syncwarp();
+    for (int i = threadIdx.x; i < kHashSize; i += 64) table[i] = (unsigned short)(0 - kEmptyAge);
+    if (threadIdx.x < 16) obuf[threadIdx.x] = 0;
+    __syncthreads();
     const uint8_t* base = job.src + g.off;
     const uint8_t* lo = job.src - job.history;
     const uint8_t* hi = job.src + job.n;
-    // level-1 priming convention: table[h(i+1)] = i for every dictionary position
-    for (int i0 = -g.dict; i0 < 0; i0 += 32) {
-        const int i = i0 + lane;
-        const bool v = i < 0;
-        const unsigned h = v ? hash3((unsigned)(gload8(base + i, lo, hi) >> 8) & 0xFFFFFFu) : 0x10000u + lane;
-        const unsigned grp = __match_any_sync(0xffffffffu, h);
-        if (v && (grp >> lane) == 1u) table[h] = (unsigned short)i;       // the highest position of a group owns the slot
-        __syncwarp();
-    }
     ChunkState& st = job.state[slot];
-    unsigned* out32 = reinterpret_cast<unsigned*>(job.cand + (size_t)slot * job.chunk);
     const int n = g.body;
-    unsigned long long bitpos = 0;           // bits of the chunk emitted so far (warp-uniform)
-    unsigned matches = 0;
 
-    // appends `nbits` (<= 31, lane-private) at step-relative offset `off`; all lanes call it
+    if (walker) {
+        // staging coordinate of chunk position q: u = q + uOff (>= 0 for the whole dictionary, 16-byte phase of the global address kept)
+        const int uOff = (int)(reinterpret_cast<uintptr_t>(base) & 15) + kMaxDict;
+        FxRing r;
+        r.ring = ringMem;
+        r.gb = (long long)reinterpret_cast<uintptr_t>(base) - uOff;
+        r.lo = (long long)reinterpret_cast<uintptr_t>(lo); r.hi = (long long)reinterpret_cast<uintptr_t>(hi);
+        r.issued = (uOff - g.dict) / kFxTile; r.ready = r.issued - 1;
+        // level-1 priming convention: table[h(i+1)] = i for every dictionary position
+        for (int i0 = -g.dict; i0 < 0; i0 += 32) {
+            fx_ensure(r, i0 + uOff + 31 + 3, lane);
+            const int i = i0 + lane;
+            const bool v = i < 0;
+            const unsigned h = hash3((unsigned)(fx_load8(r, i + uOff) >> 8) & 0xFFFFFFu);
+            const unsigned grp = fx_same_hash(h, v, lane);
+            if (v && (grp >> lane) == 1u) table[h] = (unsigned short)i;       // the highest position of a group owns the slot
+            __syncwarp();
+        }
+        unsigned matches = 0, step = 0;
+        if (n > 0) {
+            int i0 = 0, nextSweep = kSweep;
+            while (i0 < n) {
+                if (i0 >= nextSweep) {
+                    for (int k = lane; k < kHashSize; k += 32)
+                        if (((i0 - (int)table[k]) & 0xFFFF) > kMaxDistance) table[k] = (unsigned short)(i0 - kEmptyAge);
+                    nextSweep = i0 + kSweep;
+                    __syncwarp();
+                }
+                fx_ensure(r, i0 + uOff + 31 + 7, lane);
+                const int i = i0 + lane;
+                const bool valid = i < n;
+                const int remaining = n - i;
+                const unsigned long long v8 = fx_load8(r, i + uOff);
+                const unsigned h = hash3((unsigned)(v8 >> 8) & 0xFFFFFFu);
+                const unsigned short old16 = table[h];
+                const int dOld = valid ? ((i - (int)old16) & 0xFFFF) : 0xFFFF;
+                const bool hasOld = dOld <= kMaxDistance;                     // unsigned(distance) <= maxDistance, encoder.cpp:347
+                Raw8 cb; cb.x = cb.y = 0; cb.sh = 0;
+                if (hasOld) cb = gload8_issue(base + i - dOld, lo, hi);      // the candidates' bytes are on their way ...
+                // ... while the lanes find out whether any two of them share a slot
+                __syncwarp();
+                if (valid) table[h] = (unsigned short)i;                      // as if every lane were visited
+                __syncwarp();
+                const bool shared = __any_sync(0xffffffffu, valid && table[h] != (unsigned short)i);
+                unsigned grp = 1u << lane, lower = 0;
+                int lowN = -1, mOld = 0, mLow = 0;
+                if (shared) {
+                    if (valid) table[h] = old16;                              // lanes of one slot found the same value there
+                    grp = fx_same_hash(h, valid, lane);
+                    lower = grp & ltMask;
+                    lowN = lower ? 31 - __clz(lower) : -1;
+                    const unsigned long long vl = __shfl_sync(0xffffffffu, v8, lowN < 0 ? lane : lowN);
+                    if (valid && lowN >= 0) { mLow = equal_bytes8(v8 ^ vl); if (mLow > remaining) mLow = remaining; }
+                }
+                if (hasOld) {
+                    mOld = equal_bytes8(v8 ^ gload8_value(cb));
+                    if (mOld > remaining) mOld = remaining;                   // R2 clamp (short) / remain() clamp (long)
+                }
+                const unsigned packOld = (unsigned)mOld | ((unsigned)dOld << 8);
+                const unsigned packLow = (unsigned)mLow | ((unsigned)(lane - lowN) << 8);
+                // lanes whose outcome does not depend on the visited set and that start a match / lanes that have to be looked at
+                const unsigned fixedAcc = __ballot_sync(0xffffffffu, valid && lower == 0 && mOld > 3);
+                const unsigned depends = __ballot_sync(0xffffffffu, valid && lower != 0 && (mOld > 3 || mLow > 3 || (lower & (lower - 1)) != 0));
+                // settle the step: p = first lane not decided yet, V = visited lanes
+                unsigned V = 0, starts = 0;
+                int p = 0, adv = 32, myLen = 0, myDist = 0;
+                for (;;) {
+                    const unsigned fromP = 0xffffffffu << p;
+                    const unsigned stop = (fixedAcc | depends) & fromP;
+                    if (!stop) { V |= fromP; break; }
+                    const int f = __ffs(stop) - 1;
+                    V |= fromP & ((1u << f) - 1u);                          // the lanes in between are literals
+                    unsigned pk;
+                    if ((depends >> f) & 1u) {
+                        const unsigned elig = lower & V;                     // visited lower lanes of my group (V is complete below f)
+                        const unsigned mine = !elig ? packOld : (31 - __clz(elig) == lowN ? packLow : 0x80000000u);
+                        pk = __shfl_sync(0xffffffffu, mine, f);
+                    } else {
+                        pk = __shfl_sync(0xffffffffu, packOld, f);
+                    }
+                    if (pk & 0x80000000u) { adv = f; break; }                // its candidate is a lower lane that is not the nearest: next step
+                    V |= 1u << f;
+                    int L = (int)(pk & 0xFFu);
+                    const int D = (int)(pk >> 8);
+                    if (L <= 3) { p = f + 1; if (p >= 32) break; continue; }  // a literal after all
+                    starts |= 1u << f;
+                    const bool isLong = L == 8;
+                    if (isLong) {                                             // remain(a, b, 8, n - i), encoder.cpp:352
+                        const int fi = i0 + f;
+                        const int maxLen = min(n - fi, kMaxMatch);
+                        const unsigned long long xa = gload8(base + fi + 8 + lane * 8, lo, hi) ^ gload8(base + fi - D + 8 + lane * 8, lo, hi);
+                        const unsigned mm = __ballot_sync(0xffffffffu, xa != 0);
+                        int ext = 256;
+                        if (mm) { const int src = __ffs(mm) - 1; const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src); ext = src * 8 + ((__ffsll((long long)xs) - 1) >> 3); }
+                        L = 8 + ext; if (L > maxLen) L = maxLen;
+                    }
+                    if (lane == f) { myLen = L; myDist = D; }
+                    p = f + L;
+                    if (isLong || p >= 32) { adv = p; break; }
+                }
+                // commit: the highest visited lane of a hash group owns the slot
+                __syncwarp();
+                const bool vis = valid && ((V >> lane) & 1u);
+                if (shared) { if (vis && (grp & ~ltMask & ~(1u << lane) & V) == 0) table[h] = (unsigned short)i; }
+                else if (valid && !vis) table[h] = old16;
+                // hand the step to the emitter
+                unsigned w = 0;
+                if (vis) w = ((starts >> lane) & 1u) ? (kFxMatch | ((unsigned)myLen << 15) | (unsigned)(myDist - 1)) : (kFxLit | (unsigned)(v8 & 0xFF));
+                const unsigned qs = step & (kFxQ - 1);
+                fx_wait_empty(qs);
+                queue[qs * 32 + lane] = w;
+                fx_post_full(qs);
+                ++step;
+                matches += __popc(starts);
+                i0 += adv;
+            }
+            const unsigned qs = step & (kFxQ - 1);
+            fx_wait_empty(qs);
+            queue[qs * 32 + lane] = kFxEob;
+            fx_post_full(qs);
+        }
+        if (lane == 0) st.ntok = matches;
+        return;
+    }
+
+    // ---- emitter ----
+    unsigned* out32 = reinterpret_cast<unsigned*>(job.cand + (size_t)slot * job.chunk);
+    unsigned long long bitpos = 0;           // bits of the chunk emitted so far (warp-uniform)
+    // the step's bits sit in obuf from bit (bitpos & 31) on: full words leave for the scratch slot, the rest is carried
     auto stepFlush = [&](unsigned stepBits) {
         __syncwarp();
         const unsigned startBit = (unsigned)(bitpos & 31);
@@ -2339,89 +2581,47 @@ __global__ void __launch_bounds__(32) k_fixed(Job job)
         const unsigned mine = lane < 16 ? obuf[lane] : 0u;
         if ((unsigned)lane < full) out32[wbase + lane] = mine;
         const unsigned carry = __shfl_sync(0xffffffffu, mine, full & 15);
-        __syncwarp();
-        if (lane < 16) obuf[lane] = lane == 0 ? carry : 0u;
+        if (lane < 16) obuf[lane] = lane == 0 ? carry : 0u;          // every lane resets the word it has just read
         bitpos += stepBits;
         __syncwarp();
     };
-    auto putAt = [&](unsigned off, unsigned bits, int nb) {          // off relative to bitpos, nb <= 31
+    auto putAt = [&](unsigned off, unsigned bits, int nb) {          // off relative to bitpos, nb <= 32
         const unsigned o = (unsigned)(bitpos & 31) + off;
         const unsigned long long v = (unsigned long long)bits << (o & 31);
         atomicOr(&obuf[o >> 5], (unsigned)v);
         if ((o & 31) + nb > 32) atomicOr(&obuf[(o >> 5) + 1], (unsigned)(v >> 32));
     };
-
     if (n > 0) {
         if (lane == 0) putAt(0, (g.final ? 1u : 0u) | (1u << 1), 3);     // StartBlock(FixedHuffman, final)
         stepFlush(3);
-        int i0 = 0, nextSweep = kSweep;
-        while (i0 < n) {
-            if (i0 >= nextSweep) {
-                for (int k = lane; k < kHashSize; k += 32)
-                    if (((i0 - (int)table[k]) & 0xFFFF) > kMaxDistance) table[k] = (unsigned short)(i0 - kEmptyAge);
-                nextSweep = i0 + kSweep;
-                __syncwarp();
-            }
-            const int i = i0 + lane;
-            const bool valid = i < n;
-            const unsigned long long v8 = valid ? gload8(base + i, lo, hi) : 0ull;
-            const unsigned h = hash3((unsigned)(v8 >> 8) & 0xFFFFFFu);
-            const unsigned grp = __match_any_sync(0xffffffffu, valid ? h : (0x10000u + lane));
-            const unsigned lower = grp & ltMask;
-            const int old = i - (valid ? ((i - (int)table[h]) & 0xFFFF) : 0xFFFF);
-            const int cand = lower ? (i0 + 31 - __clz(lower)) : old;
-            const int d = i - cand;
-            int m = 0;
-            const int remaining = n - i;
-            if (valid && (unsigned)d <= (unsigned)kMaxDistance) {
-                const unsigned long long x = v8 ^ gload8(base + cand, lo, hi);
-                m = x ? ((__ffsll((long long)x) - 1) >> 3) : 8;
-                if (m > remaining) m = remaining;                     // R2 clamp (short) / remain() clamp (long)
-            }
-            const unsigned accMask = __ballot_sync(0xffffffffu, m > 3);
-            const int first = accMask ? __ffs(accMask) - 1 : 32;
-            // commit: lanes <= first were visited; the highest visited lane of a hash group owns the slot
-            const unsigned visited = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
-            __syncwarp();
-            if (valid && ((visited >> lane) & 1u) && (grp & ~ltMask & ~(1u << lane) & visited) == 0) table[h] = (unsigned short)i;
-            // exact length of the winning match (remain(a, b, 8, n - i), encoder.cpp:352)
-            int mlen = 0, mdist = 0;
-            if (first < 32) {
-                mlen = __shfl_sync(0xffffffffu, m, first);
-                mdist = __shfl_sync(0xffffffffu, d, first);
-                if (mlen == 8) {
-                    const int fi = i0 + first;
-                    const int maxLen = min(n - fi, kMaxMatch);
-                    const unsigned long long xa = gload8(base + fi + 8 + lane * 8, lo, hi) ^ gload8(base + fi - mdist + 8 + lane * 8, lo, hi);
-                    const unsigned mm = __ballot_sync(0xffffffffu, xa != 0);
-                    int ext = 256;
-                    if (mm) { const int src = __ffs(mm) - 1; const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src); ext = src * 8 + ((__ffsll((long long)xs) - 1) >> 3); }
-                    mlen = 8 + ext; if (mlen > maxLen) mlen = maxLen;
-                }
-            }
-            // emission: literals of the lanes before the match, then the match
+        fx_post_empty(0); fx_post_empty(1);                              // both slots start empty
+        for (unsigned step = 0;; ++step) {
+            const unsigned qs = step & (kFxQ - 1);
+            fx_wait_full(qs);
+            const unsigned w = queue[qs * 32 + lane];
+            fx_post_empty(qs);
             unsigned bits1 = 0, bits2 = 0; int n1 = 0, n2 = 0;
-            if (valid && lane < first) {
-                bits1 = fixed_lit_code((unsigned)(v8 & 0xFF), n1);
-            } else if (lane == first) {
+            if (w & kFxLit) {
+                bits1 = fixed_lit_code(w & 0xFFu, n1);
+            } else if (w & kFxMatch) {
                 int eb, ev, cl;
-                const int ls = len_symbol(mlen, eb, ev);
+                const int ls = len_symbol((int)((w >> 15) & 0x1FFu), eb, ev);
                 const unsigned lc = fixed_lit_code((unsigned)ls, cl);
                 bits1 = lc | ((unsigned)ev << cl); n1 = cl + eb;
-                const int ds = dist_symbol(mdist, eb, ev);
+                const int ds = dist_symbol((int)(w & 0x7FFFu) + 1, eb, ev);
                 bits2 = (__brev((unsigned)ds) >> 27) | ((unsigned)ev << 5); n2 = 5 + eb;
+            } else if ((w & kFxEob) && lane == 0) {
+                bits1 = fixed_lit_code(256u, n1);
             }
             unsigned incl = (unsigned)(n1 + n2);
             for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
             const unsigned off = incl - (unsigned)(n1 + n2);
             const unsigned stepBits = __shfl_sync(0xffffffffu, incl, 31);
-            __syncwarp();
             if (n1) putAt(off, bits1, n1);
             if (n2) putAt(off + n1, bits2, n2);
             stepFlush(stepBits);
-            if (first < 32) { i0 += first + mlen; ++matches; } else i0 += 32;
+            if (w & kFxEob) break;                                       // every lane of the last step carries the flag
         }
-        { int cl; const unsigned c = fixed_lit_code(256u, cl); if (lane == 0) putAt(0, c, cl); stepFlush((unsigned)cl); }
     }
     const unsigned long long q = bitpos;
     unsigned bytes = (unsigned)((q + 7) >> 3);
@@ -2439,7 +2639,7 @@ __global__ void __launch_bounds__(32) k_fixed(Job job)
         __syncwarp();
         if (lane == 0 && (bitpos & 31)) out32[bitpos >> 5] = obuf[0];
     }
-    if (lane == 0) { st.ntok = matches; st.block_type = 1; st.hdr_bits = 0; st.total_bits = q; st.out_bytes = bytes; }
+    if (lane == 0) { st.block_type = 1; st.hdr_bits = 0; st.total_bits = q; st.out_bytes = bytes; }
 }
 
 __global__ void __launch_bounds__(256) k_gather(Job job)
@@ -2769,7 +2969,7 @@ int launch_stored(const Job& job, cudaStream_t s)
 
 int launch_fixed(const Job& job, cudaStream_t s)
 {
-    k_fixed<<<job.nchunks, 32, 0, s>>>(job);
+    k_fixed<<<job.nchunks, 64, 0, s>>>(job);
     return 1;
 }
 
