@@ -23,7 +23,10 @@ def one(name, data, chunk=S, dict_size=D):
     print('  MISMATCH', name, 'len', len(data), 'out', len(got), len(want), 'chunk', chunk, dict_size, 'first differing byte', k, flush=True)
     return 1
 
-from fuzz_model import gen, rng     # the same structured generator the CPU models were fuzzed with
+import fuzz_model
+from fuzz_model import gen     # the same structured generator the CPU models were fuzzed with
+import os
+fuzz_model.rng = rng = np.random.default_rng(int(os.environ.get('L1_SEED', '1')))
 
 budget = float(sys.argv[1]); timing = int(sys.argv[2])
 total_bad = 0

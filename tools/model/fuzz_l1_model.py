@@ -6,7 +6,7 @@ import numpy as np
 from zzflate_b200 import synth
 subprocess.check_call("gcc -O2 -shared -fPIC -o tools/model/libl1model.so tools/model/l1_model.c".split())
 lib = C.CDLL('tools/model/libl1model.so')
-for f in (lib.l1m_seq, lib.l1m_warp):
+for f in (lib.l1m_seq, lib.l1m_warp, lib.l1m_warp2):
     f.restype = C.c_int; f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 30
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -28,6 +28,12 @@ def check(data, chunk=65536, dict_size=32768):
         if ka != kb or not np.array_equal(a[:3 * ka], b[:3 * kb]):
             bad += 1
             print("MISMATCH chunk at", off, ka, kb, flush=True)
+        kb = lib.l1m_warp2(buf.ctypes.data + off, body, d, b.ctypes.data, 70000)
+        if ka != kb or not np.array_equal(a[:3 * ka], b[:3 * kb]):
+            bad += 1
+            m = min(ka, kb); x = a[:3 * m].reshape(-1, 3); y = b[:3 * m].reshape(-1, 3)
+            df = np.nonzero((x != y).any(axis=1))[0]
+            print("MISMATCH (warp2) chunk at", off, ka, kb, (df[0], x[df[0]], y[df[0]]) if len(df) else None, flush=True)
     return bad
 
 cases = fails = 0
@@ -38,6 +44,8 @@ for name in ("text", "random", "zeros", "pattern"):
     fails += check(data); cases += 1
     lib.l1m_stats(st)
     print(f"{name}: {len(data)} bytes, steps {st[0]} ({len(data) / st[0]:.1f} positions per step), ambiguous ends {st[1]}, long matches {st[2]}")
+    s2 = (C.c_long * 3)(); lib.l1m_stats2(s2)
+    print(f"   settled in parallel: {s2[0]} steps, {s2[1]} doubling rounds; sequential iterations {s2[2]}")
 t0 = time.time()
 while time.time() - t0 < budget:
     data = fm.gen()

@@ -2288,9 +2288,11 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
 // A step.  The walker presumes that all 32 positions are visited.  Every lane knows two match lengths before the step
 // is settled: mOld against the table's entry (its candidate if no lower lane of the step with the same hash is visited)
 // and mLow against the nearest lower lane of its hash group (its candidate if that lane is visited).  The matches of
-// the step are then settled one after the other without any further memory access, one shuffle per match: a lane
-// without a lower lane of its hash group has one possible candidate (the table's), so only the lanes that do are
-// evaluated against the visited set when the walk reaches them.  A lane whose true candidate is neither (a lower lane of
+// the step are then settled without any further memory access.  A lane without a lower lane of its hash group has one
+// possible candidate (the table's), so the window in front of the first lane that does have one is settled in parallel
+// (the real match starts are an orbit, collected by pointer doubling: two REDUX / SHFL rounds on average); behind it
+// the walk takes one match per turn (one shuffle), and the lanes that depend on the visited set are evaluated against
+// it when the walk reaches them (0.5 turns per step on text).  A lane whose true candidate is neither (a lower lane of
 // its group that is not the nearest one) ends the step in front of it; a match of >= 8 bytes (exact length needed: a
 // warp-wide gather) ends the step behind it.  On the text workload a step covers 32.7 positions (the first
 // formulation, which ended a step at its first match: 8.6).  tools/model/l1_model.c states the step logic in plain C
@@ -2507,10 +2509,63 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
                 // lanes whose outcome does not depend on the visited set and that start a match / lanes that have to be looked at
                 const unsigned fixedAcc = __ballot_sync(0xffffffffu, valid && lower == 0 && mOld > 3);
                 const unsigned depends = __ballot_sync(0xffffffffu, valid && lower != 0 && (mOld > 3 || mLow > 3 || (lower & (lower - 1)) != 0));
-                // settle the step: p = first lane not decided yet, V = visited lanes
-                unsigned V = 0, starts = 0;
-                int p = 0, adv = 32, myLen = 0, myDist = 0;
-                for (;;) {
+                // exact length of a match of >= 8 bytes that starts at lane f (remain(a, b, 8, n - i), encoder.cpp:352)
+                auto exactLength = [&](int f, int D) {
+                    const int fi = i0 + f;
+                    const int maxLen = min(n - fi, kMaxMatch);
+                    const unsigned long long xa = gload8(base + fi + 8 + lane * 8, lo, hi) ^ gload8(base + fi - D + 8 + lane * 8, lo, hi);
+                    const unsigned mm = __ballot_sync(0xffffffffu, xa != 0);
+                    int ext = 256;
+                    if (mm) { const int src = __ffs(mm) - 1; const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src); ext = src * 8 + ((__ffsll((long long)xs) - 1) >> 3); }
+                    return min(8 + ext, maxLen);
+                };
+                // settle the step: p = first lane not decided yet, V = visited lanes, starts = lanes that start a match
+                unsigned V, starts = 0;
+                int p, adv = 32, myLen = 0, myDist = 0;
+                bool done;
+                // (1) In front of the first lane that has to be looked at (q) every outcome is known, so that part is settled in
+                // parallel: G = the first match start at or behind the end of my own match, the real match starts are the orbit of
+                // G from the first match start, collected by pointer doubling (three rounds cover the eight matches of a window).
+                const int q = depends ? __ffs(depends) - 1 : 32;
+                const unsigned belowQ = q >= 32 ? 0xffffffffu : ((1u << q) - 1u);
+                const unsigned accP = fixedAcc & belowQ;
+                if (accP) {
+                    const int x = lane + mOld;
+                    const unsigned behind = x >= 32 ? 0u : (accP & (0xffffffffu << x));
+                    int G = (mOld == 8 || !behind) ? 32 : __ffs(behind) - 1;     // a match of >= 8 bytes ends the step
+                    unsigned R = accP & (0u - accP);
+                    for (;;) {
+                        const unsigned add = __reduce_or_sync(0xffffffffu, (((R >> lane) & 1u) && G < 32) ? (1u << G) : 0u);
+                        if ((add & ~R) == 0) break;
+                        R |= add;
+                        const int G2 = __shfl_sync(0xffffffffu, G, G & 31);
+                        G = G >= 32 ? 32 : G2;
+                    }
+                    const bool inR = (R >> lane) & 1u;
+                    const unsigned covered = __reduce_or_sync(0xffffffffu, inR ? (((1u << mOld) - 2u) << lane) : 0u);
+                    if (inR) { myLen = mOld; myDist = dOld; }
+                    starts = R;
+                    const int last = 31 - __clz(R);
+                    const unsigned pkLast = __shfl_sync(0xffffffffu, packOld, last);
+                    int L = (int)(pkLast & 0xFFu);
+                    if (L == 8) {
+                        L = exactLength(last, (int)(pkLast >> 8));
+                        if (lane == last) myLen = L;
+                        adv = last + L; done = true; p = 32;
+                        V = ~covered & ((2u << last) - 1u);
+                    } else if (last + L >= 32) {
+                        adv = last + L; done = true; p = 32;
+                        V = ~covered;
+                    } else {
+                        p = max(last + L, q);
+                        V = ~covered & (p >= 32 ? 0xffffffffu : ((1u << p) - 1u));
+                        done = p >= 32;
+                    }
+                } else {
+                    p = q; V = belowQ; done = p >= 32;
+                }
+                // (2) the rest of the window, one match (or one lane that has to be looked at) per turn
+                while (!done) {
                     const unsigned fromP = 0xffffffffu << p;
                     const unsigned stop = (fixedAcc | depends) & fromP;
                     if (!stop) { V |= fromP; break; }
@@ -2531,15 +2586,7 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
                     if (L <= 3) { p = f + 1; if (p >= 32) break; continue; }  // a literal after all
                     starts |= 1u << f;
                     const bool isLong = L == 8;
-                    if (isLong) {                                             // remain(a, b, 8, n - i), encoder.cpp:352
-                        const int fi = i0 + f;
-                        const int maxLen = min(n - fi, kMaxMatch);
-                        const unsigned long long xa = gload8(base + fi + 8 + lane * 8, lo, hi) ^ gload8(base + fi - D + 8 + lane * 8, lo, hi);
-                        const unsigned mm = __ballot_sync(0xffffffffu, xa != 0);
-                        int ext = 256;
-                        if (mm) { const int src = __ffs(mm) - 1; const unsigned long long xs = __shfl_sync(0xffffffffu, xa, src); ext = src * 8 + ((__ffsll((long long)xs) - 1) >> 3); }
-                        L = 8 + ext; if (L > maxLen) L = maxLen;
-                    }
+                    if (isLong) L = exactLength(f, D);
                     if (lane == f) { myLen = L; myDist = D; }
                     p = f + L;
                     if (isLong || p >= 32) { adv = p; break; }
