@@ -45,7 +45,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up; the summary uses the samples
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the input is generated; the summary uses the samples
     whose timestamps fall inside the timed region (and, if the region was shorter than the sampling jitter, the
     load-carrying warm-up right before it)."""
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -55,7 +55,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
-        self.t0 = self.t1 = None
+        self.t0 = self.t1 = self.tw = None
 
     def start(self):
         try:
@@ -68,6 +68,13 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def wait_ready(self, timeout: float = 5.0):
+        """blocks until the first sample has arrived (the timed region of the default run is under 100 ms)"""
+        t = time.time()
+        while self.proc is not None and not self.rows and time.time() - t < timeout:
+            time.sleep(0.01)
+        self.tw = time.time()                  # the warm-up starts here
 
     def mark_begin(self):
         self.t0 = time.time()
@@ -96,8 +103,9 @@ class ClockSampler:
         inside = [x for x in self.rows if self.t0 is not None and self.t0 - 0.02 <= x[0] <= (self.t1 or x[0]) + 0.02]
         window = "timed region"
         if len(inside) < 3:
-            inside = [x for x in self.rows if self.t0 is None or x[0] >= self.t0 - 1.0]
-            window = "timed region and the warm-up second before it"
+            lo = self.tw if self.tw is not None else (self.t0 - 1.0 if self.t0 is not None else 0.0)
+            inside = [x for x in self.rows if x[0] >= lo - 0.02]
+            window = "timed region and the warm-up steps before it"
         sm, mx, reasons = summarise(inside)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
@@ -207,6 +215,8 @@ def main():
         config.setdefault("options", {})[k] = int(v)
 
     nbytes = args.shard_mib << 20
+    sampler = ClockSampler(local_rank)          # started early: nvidia-smi needs a moment before its first sample
+    sampler.start()
     host, hist = make_shard(args.workload, rank, nbytes)
     final = rank == world - 1
     pinned_src = torch.from_numpy(host).pin_memory()
@@ -225,8 +235,7 @@ def main():
         return zz.deflate_device(d_src.data_ptr() + hist, nbytes, d_dst.data_ptr(), cap, level=args.level,
                                  history=hist, final=final, checksums=1)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.wait_ready()
     for _ in range(args.warmup):
         out_len, _, _, st = device_step()
     barrier()
