@@ -2386,11 +2386,13 @@ constexpr unsigned kFxLit = 0x80000000u, kFxMatch = 0x40000000u, kFxEob = 0x2000
 // pool then admits four CTAs instead of twelve (measured: 24.8 instead of 32.7 GB/s on random bytes)
 template <int ID> __device__ __forceinline__ void fx_bar_sync_c() { asm volatile("barrier.sync %0, 64;" ::"n"(ID) : "memory"); }
 template <int ID> __device__ __forceinline__ void fx_bar_arrive_c() { asm volatile("barrier.arrive %0, 64;" ::"n"(ID) : "memory"); }
-// slot s of the queue: barrier 1 + s = "full", barrier 1 + kFxQ + s = "empty" (kFxQ == 2)
-__device__ __forceinline__ void fx_wait_full(unsigned s) { __syncwarp(); if (s == 0) fx_bar_sync_c<1>(); else fx_bar_sync_c<2>(); }
-__device__ __forceinline__ void fx_wait_empty(unsigned s) { __syncwarp(); if (s == 0) fx_bar_sync_c<3>(); else fx_bar_sync_c<4>(); }
-__device__ __forceinline__ void fx_post_full(unsigned s) { __syncwarp(); if (s == 0) fx_bar_arrive_c<1>(); else fx_bar_arrive_c<2>(); }
-__device__ __forceinline__ void fx_post_empty(unsigned s) { __syncwarp(); if (s == 0) fx_bar_arrive_c<3>(); else fx_bar_arrive_c<4>(); }
+// slot s of the two-slot queue: barrier 1 + s = "full", barrier 3 + s = "empty" (s is warp-uniform).  barrier.sync is the
+// non-aligned form (it tolerates a split warp), and it orders the memory accesses of the threads that take part in it --
+// the walker's 32 lanes among them, so it also stands between a step's table commit and the next step's table reads.
+__device__ __forceinline__ void fx_wait_full(unsigned s) { if (s == 0) fx_bar_sync_c<1>(); else fx_bar_sync_c<2>(); }
+__device__ __forceinline__ void fx_wait_empty(unsigned s) { if (s == 0) fx_bar_sync_c<3>(); else fx_bar_sync_c<4>(); }
+__device__ __forceinline__ void fx_post_full(unsigned s) { if (s == 0) fx_bar_arrive_c<1>(); else fx_bar_arrive_c<2>(); }
+__device__ __forceinline__ void fx_post_empty(unsigned s) { if (s == 0) fx_bar_arrive_c<3>(); else fx_bar_arrive_c<4>(); }
 
 // gload8 in two halves, so that the loads are in flight while the step does other things: the two aligned words now, the value later
 struct Raw8 { unsigned long long x, y; int sh; };
@@ -2406,6 +2408,15 @@ __device__ __forceinline__ Raw8 gload8_issue(const uint8_t* p, const uint8_t* lo
     } else {
         r.x = gload8(p, lo, hi); r.y = 0; r.sh = 0;
     }
+    return r;
+}
+// the same for an address whose two aligned words are known to lie inside the stream
+__device__ __forceinline__ Raw8 gload8_issue_inner(const uint8_t* p)
+{
+    Raw8 r;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned long long* al = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+    r.x = __ldg(al); r.y = __ldg(al + 1); r.sh = (int)(a & 7) * 8;
     return r;
 }
 __device__ __forceinline__ unsigned long long gload8_value(const Raw8& r) { return r.sh ? ((r.x >> r.sh) | (r.y << (64 - r.sh))) : r.x; }
@@ -2454,14 +2465,25 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
         r.gb = (long long)reinterpret_cast<uintptr_t>(base) - uOff;
         r.lo = (long long)reinterpret_cast<uintptr_t>(lo); r.hi = (long long)reinterpret_cast<uintptr_t>(hi);
         r.issued = (uOff - g.dict) / kFxTile; r.ready = r.issued - 1;
+        // every candidate of the chunk (and the aligned words around it) inside the stream: all chunks but the first and the last
+        const bool inner = (long long)reinterpret_cast<uintptr_t>(base) - (kMaxDict + 8) >= r.lo && (long long)reinterpret_cast<uintptr_t>(base) + g.n + 24 <= r.hi;
         // level-1 priming convention: table[h(i+1)] = i for every dictionary position
         for (int i0 = -g.dict; i0 < 0; i0 += 32) {
             fx_ensure(r, i0 + uOff + 31 + 3, lane);
             const int i = i0 + lane;
             const bool v = i < 0;
             const unsigned h = hash3((unsigned)(fx_load8(r, i + uOff) >> 8) & 0xFFFFFFu);
-            const unsigned grp = fx_same_hash(h, v, lane);
-            if (v && (grp >> lane) == 1u) table[h] = (unsigned short)i;       // the highest position of a group owns the slot
+            // the highest position of a hash group owns the slot: everybody writes; a lane that then finds a lower position of
+            // this step in its slot writes again (the holder of a contested slot moves up every round)
+            if (v) table[h] = (unsigned short)i;
+            __syncwarp();
+            bool again = v && (unsigned)((i - (int)table[h]) & 0xFFFF) - 1u < 31u;
+            while (__any_sync(0xffffffffu, again)) {
+                __syncwarp();
+                if (again) table[h] = (unsigned short)i;
+                __syncwarp();
+                again = v && (unsigned)((i - (int)table[h]) & 0xFFFF) - 1u < 31u;
+            }
             __syncwarp();
         }
         unsigned matches = 0, step = 0;
@@ -2469,6 +2491,7 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
             int i0 = 0, nextSweep = kSweep;
             while (i0 < n) {
                 if (i0 >= nextSweep) {
+#pragma unroll 8
                     for (int k = lane; k < kHashSize; k += 32)
                         if (((i0 - (int)table[k]) & 0xFFFF) > kMaxDistance) table[k] = (unsigned short)(i0 - kEmptyAge);
                     nextSweep = i0 + kSweep;
@@ -2484,7 +2507,7 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
                 const int dOld = valid ? ((i - (int)old16) & 0xFFFF) : 0xFFFF;
                 const bool hasOld = dOld <= kMaxDistance;                     // unsigned(distance) <= maxDistance, encoder.cpp:347
                 Raw8 cb; cb.x = cb.y = 0; cb.sh = 0;
-                if (hasOld) cb = gload8_issue(base + i - dOld, lo, hi);      // the candidates' bytes are on their way ...
+                if (hasOld) cb = inner ? gload8_issue_inner(base + i - dOld) : gload8_issue(base + i - dOld, lo, hi);   // the candidates' bytes are on their way ...
                 // ... while the lanes find out whether any two of them share a slot
                 __syncwarp();
                 if (valid) table[h] = (unsigned short)i;                      // as if every lane were visited
