@@ -2310,7 +2310,8 @@ __global__ void __launch_bounds__(kEmit2Threads, 2) k_emit2(Job job)
 // queue, two named barriers per slot (full / empty: barrier.sync on one side, barrier.arrive on the other) order it.
 // 17.3 KiB of shared memory and five barriers per chunk: twelve chunks per SM (the hash table sets that limit).
 // ncu (profiles/r02m_fixed.md): the walker is one dependent chain at one warp per scheduler -- the gather of the
-// candidates' bytes is 11-16 % of it, the rest is fixed-latency dependencies spread over the whole step.
+// candidates' bytes is 11-16 % of it, the rest is fixed-latency dependencies spread over the whole step; at twelve
+// chunks per SM the issue slots are ~70 % busy, so every instruction taken out of a step shows in the throughput.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned fixed_lit_code(unsigned v, int& len)     // fixedhuffmanluts.cpp:5 (RFC 1951 3.2.6)
 {
@@ -2318,6 +2319,13 @@ __device__ __forceinline__ unsigned fixed_lit_code(unsigned v, int& len)     // 
     if (v < 256) { len = 9; return __brev(0x190u + (v - 144)) >> 23; }
     if (v < 280) { len = 7; return __brev(v - 256) >> 25; }
     len = 8; return __brev(0xC0u + (v - 280)) >> 24;
+}
+
+__device__ __forceinline__ unsigned fixed_literal_code(unsigned v, int& len)     // the same for v < 256 (two ranges only)
+{
+    const bool low = v < 144;
+    len = low ? 8 : 9;
+    return __brev(v + (low ? 0x30u : 0x100u)) >> (low ? 24 : 23);
 }
 
 constexpr int kFxTile = 256, kFxRing = 4 * kFxTile, kFxAhead = 2;
@@ -2377,7 +2385,14 @@ __device__ __forceinline__ unsigned long long fx_load8(const FxRing& r, int u)
     return (unsigned long long)__funnelshift_r(a, b, sh) | ((unsigned long long)__funnelshift_r(b, c, sh) << 32);
 }
 
-__device__ __forceinline__ int equal_bytes8(unsigned long long x) { return x ? ((__ffsll((long long)x) - 1) >> 3) : 8; }
+// number of equal low bytes of two 8-byte words, from their XOR (two 32-bit halves: the 64-bit __ffsll costs twice as much)
+__device__ __forceinline__ int equal_bytes8(unsigned long long x)
+{
+    const unsigned lo = (unsigned)x, hi = (unsigned)(x >> 32);
+    if (lo) return (__ffs((int)lo) - 1) >> 3;
+    if (hi) return 4 + ((__ffs((int)hi) - 1) >> 3);
+    return 8;
+}
 
 constexpr int kFxQ = 2;
 constexpr unsigned kFxLit = 0x80000000u, kFxMatch = 0x40000000u, kFxEob = 0x20000000u;
@@ -2441,7 +2456,7 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
     __shared__ unsigned short table[kHashSize];
     __shared__ __align__(16) uint8_t ringMem[kFxRing];
     __shared__ unsigned queue[kFxQ * 32];
-    __shared__ unsigned obuf[16];
+    __shared__ unsigned obuf[32];                 // a step emits <= 341 bits from bit (bitpos & 31) on: words 0..11 are used
     const unsigned slot = blockIdx.x;
     const Geom g = chunk_geom(job, slot);
     const int lane = threadIdx.x & 31;
@@ -2449,7 +2464,7 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
     const unsigned ltMask = (1u << lane) - 1u;
     constexpr int kEmptyAge = 40000, kSweep = 8192;
     for (int i = threadIdx.x; i < kHashSize; i += 64) table[i] = (unsigned short)(0 - kEmptyAge);
-    if (threadIdx.x < 16) obuf[threadIdx.x] = 0;
+    if (threadIdx.x < 32) obuf[threadIdx.x] = 0;
     __syncthreads();
     const uint8_t* base = job.src + g.off;
     const uint8_t* lo = job.src - job.history;
@@ -2543,9 +2558,10 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
                     return min(8 + ext, maxLen);
                 };
                 // settle the step: p = first lane not decided yet, V = visited lanes, starts = lanes that start a match
-                unsigned V, starts = 0;
-                int p, adv = 32, myLen = 0, myDist = 0;
-                bool done;
+                unsigned V = 0xffffffffu, starts = 0;
+                int p = 32, adv = 32, myLen = 0, myDist = 0;
+                bool done = true;
+                if (fixedAcc | depends) {                                     // (no lane starts a match or has to be looked at: 32 literals)
                 // (1) In front of the first lane that has to be looked at (q) every outcome is known, so that part is settled in
                 // parallel: G = the first match start at or behind the end of my own match, the real match starts are the orbit of
                 // G from the first match start, collected by pointer doubling (three rounds cover the eight matches of a window).
@@ -2586,6 +2602,7 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
                     }
                 } else {
                     p = q; V = belowQ; done = p >= 32;
+                }
                 }
                 // (2) the rest of the window, one match (or one lane that has to be looked at) per turn
                 while (!done) {
@@ -2648,10 +2665,10 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
         const unsigned startBit = (unsigned)(bitpos & 31);
         const unsigned full = (startBit + stepBits) >> 5;
         const unsigned wbase = (unsigned)(bitpos >> 5);
-        const unsigned mine = lane < 16 ? obuf[lane] : 0u;
+        const unsigned mine = obuf[lane];
         if ((unsigned)lane < full) out32[wbase + lane] = mine;
-        const unsigned carry = __shfl_sync(0xffffffffu, mine, full & 15);
-        if (lane < 16) obuf[lane] = lane == 0 ? carry : 0u;          // every lane resets the word it has just read
+        const unsigned carry = __shfl_sync(0xffffffffu, mine, full);
+        obuf[lane] = lane == 0 ? carry : 0u;                          // every lane resets the word it has just read
         bitpos += stepBits;
         __syncwarp();
     };
@@ -2672,7 +2689,7 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
             fx_post_empty(qs);
             unsigned bits1 = 0, bits2 = 0; int n1 = 0, n2 = 0;
             if (w & kFxLit) {
-                bits1 = fixed_lit_code(w & 0xFFu, n1);
+                bits1 = fixed_literal_code(w & 0xFFu, n1);
             } else if (w & kFxMatch) {
                 int eb, ev, cl;
                 const int ls = len_symbol((int)((w >> 15) & 0x1FFu), eb, ev);
@@ -2683,10 +2700,18 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
             } else if ((w & kFxEob) && lane == 0) {
                 bits1 = fixed_lit_code(256u, n1);
             }
-            unsigned incl = (unsigned)(n1 + n2);
-            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            const unsigned off = incl - (unsigned)(n1 + n2);
-            const unsigned stepBits = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned off, stepBits;
+            if (__ballot_sync(0xffffffffu, (w & (kFxMatch | kFxEob)) != 0) == 0) {
+                // literals only (8 or 9 bits each): the offsets come from two ballots
+                const unsigned lit = __ballot_sync(0xffffffffu, n1 != 0), nine = __ballot_sync(0xffffffffu, n1 == 9);
+                off = 8u * __popc(lit & ltMask) + __popc(nine & ltMask);
+                stepBits = 8u * __popc(lit) + __popc(nine);
+            } else {
+                unsigned incl = (unsigned)(n1 + n2);
+                for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                off = incl - (unsigned)(n1 + n2);
+                stepBits = __shfl_sync(0xffffffffu, incl, 31);
+            }
             if (n1) putAt(off, bits1, n1);
             if (n2) putAt(off + n1, bits2, n2);
             stepFlush(stepBits);
