@@ -2562,47 +2562,47 @@ __global__ void __launch_bounds__(64) k_fixed(Job job)
                 int p = 32, adv = 32, myLen = 0, myDist = 0;
                 bool done = true;
                 if (fixedAcc | depends) {                                     // (no lane starts a match or has to be looked at: 32 literals)
-                // (1) In front of the first lane that has to be looked at (q) every outcome is known, so that part is settled in
-                // parallel: G = the first match start at or behind the end of my own match, the real match starts are the orbit of
-                // G from the first match start, collected by pointer doubling (three rounds cover the eight matches of a window).
-                const int q = depends ? __ffs(depends) - 1 : 32;
-                const unsigned belowQ = q >= 32 ? 0xffffffffu : ((1u << q) - 1u);
-                const unsigned accP = fixedAcc & belowQ;
-                if (accP) {
-                    const int x = lane + mOld;
-                    const unsigned behind = x >= 32 ? 0u : (accP & (0xffffffffu << x));
-                    int G = (mOld == 8 || !behind) ? 32 : __ffs(behind) - 1;     // a match of >= 8 bytes ends the step
-                    unsigned R = accP & (0u - accP);
-                    for (;;) {
-                        const unsigned add = __reduce_or_sync(0xffffffffu, (((R >> lane) & 1u) && G < 32) ? (1u << G) : 0u);
-                        if ((add & ~R) == 0) break;
-                        R |= add;
-                        const int G2 = __shfl_sync(0xffffffffu, G, G & 31);
-                        G = G >= 32 ? 32 : G2;
-                    }
-                    const bool inR = (R >> lane) & 1u;
-                    const unsigned covered = __reduce_or_sync(0xffffffffu, inR ? (((1u << mOld) - 2u) << lane) : 0u);
-                    if (inR) { myLen = mOld; myDist = dOld; }
-                    starts = R;
-                    const int last = 31 - __clz(R);
-                    const unsigned pkLast = __shfl_sync(0xffffffffu, packOld, last);
-                    int L = (int)(pkLast & 0xFFu);
-                    if (L == 8) {
-                        L = exactLength(last, (int)(pkLast >> 8));
-                        if (lane == last) myLen = L;
-                        adv = last + L; done = true; p = 32;
-                        V = ~covered & ((2u << last) - 1u);
-                    } else if (last + L >= 32) {
-                        adv = last + L; done = true; p = 32;
-                        V = ~covered;
+                    // (1) In front of the first lane that has to be looked at (q) every outcome is known, so that part is settled in
+                    // parallel: G = the first match start at or behind the end of my own match, the real match starts are the orbit of
+                    // G from the first match start, collected by pointer doubling (three rounds cover the eight matches of a window).
+                    const int q = depends ? __ffs(depends) - 1 : 32;
+                    const unsigned belowQ = q >= 32 ? 0xffffffffu : ((1u << q) - 1u);
+                    const unsigned accP = fixedAcc & belowQ;
+                    if (accP) {
+                        const int x = lane + mOld;
+                        const unsigned behind = x >= 32 ? 0u : (accP & (0xffffffffu << x));
+                        int G = (mOld == 8 || !behind) ? 32 : __ffs(behind) - 1;     // a match of >= 8 bytes ends the step
+                        unsigned R = accP & (0u - accP);
+                        for (;;) {
+                            const unsigned add = __reduce_or_sync(0xffffffffu, (((R >> lane) & 1u) && G < 32) ? (1u << G) : 0u);
+                            if ((add & ~R) == 0) break;
+                            R |= add;
+                            const int G2 = __shfl_sync(0xffffffffu, G, G & 31);
+                            G = G >= 32 ? 32 : G2;
+                        }
+                        const bool inR = (R >> lane) & 1u;
+                        const unsigned covered = __reduce_or_sync(0xffffffffu, inR ? (((1u << mOld) - 2u) << lane) : 0u);
+                        if (inR) { myLen = mOld; myDist = dOld; }
+                        starts = R;
+                        const int last = 31 - __clz(R);
+                        const unsigned pkLast = __shfl_sync(0xffffffffu, packOld, last);
+                        int L = (int)(pkLast & 0xFFu);
+                        if (L == 8) {
+                            L = exactLength(last, (int)(pkLast >> 8));
+                            if (lane == last) myLen = L;
+                            adv = last + L; done = true; p = 32;
+                            V = ~covered & ((2u << last) - 1u);
+                        } else if (last + L >= 32) {
+                            adv = last + L; done = true; p = 32;
+                            V = ~covered;
+                        } else {
+                            p = max(last + L, q);
+                            V = ~covered & (p >= 32 ? 0xffffffffu : ((1u << p) - 1u));
+                            done = p >= 32;
+                        }
                     } else {
-                        p = max(last + L, q);
-                        V = ~covered & (p >= 32 ? 0xffffffffu : ((1u << p) - 1u));
-                        done = p >= 32;
+                        p = q; V = belowQ; done = p >= 32;
                     }
-                } else {
-                    p = q; V = belowQ; done = p >= 32;
-                }
                 }
                 // (2) the rest of the window, one match (or one lane that has to be looked at) per turn
                 while (!done) {
