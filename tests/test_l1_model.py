@@ -119,3 +119,53 @@ def test_step_walks_equal_the_sequential_walk_and_the_oracle(model, oracle, gold
                 if chunk == S or off < 3 * chunk:                                   # the bit writer is plain Python: a few chunks per geometry
                     want = oracle.chunk_encode(buf, off, ln, d, 1, final)["bytes"]
                     assert fixed_block(data[off: off + ln], body, seq.tolist(), final) == want, (name, chunk, off)
+
+
+def test_step_walks_on_structured_random_inputs(model):
+    """A short seeded run of the structured generator the model was fuzzed with (text, random, runs, short periods, few
+    symbols, copies of earlier stretches at long distances), default and odd geometries."""
+    from zzflate_b200 import synth
+    rng = np.random.default_rng(20261018)
+    text = synth.markov_text(1 << 19, seg0=11, threads=1).tobytes()
+
+    def piece(kind, n):
+        if kind == 0:
+            s = int(rng.integers(0, len(text) - n)); return text[s: s + n]
+        if kind == 1: return rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        if kind == 2: return bytes([int(rng.integers(0, 256))]) * n
+        if kind == 3:
+            p = rng.integers(0, 256, int(rng.integers(1, 2000)), dtype=np.uint8).tobytes()
+            return (p * (n // len(p) + 1))[:n]
+        if kind == 4: return rng.integers(0, int(rng.integers(2, 6)), n, dtype=np.uint8).tobytes()
+        if kind == 6: return (rng.integers(0, 64, n, dtype=np.uint8) + 48).astype(np.uint8).tobytes()
+        p = rng.integers(97, 123, 7, dtype=np.uint8).tobytes()
+        return (p * (n // 7 + 1))[:n]
+
+    chunks = 0
+    for _ in range(40):
+        total = int(rng.choice([300, 5000, 65536, 65537, 70000, 131072]))
+        buf = bytearray()
+        while len(buf) < total:
+            kind = int(rng.integers(0, 8))
+            n = int(rng.choice([1, 3, 17, 258, 259, 300, 1000, 5000, 16384, 20000]))
+            if kind == 5:
+                if len(buf) > 600:
+                    back = int(rng.integers(8, min(len(buf), 40000)))
+                    ln = int(rng.integers(4, min(back + 1, 3000) + 1))
+                    s = len(buf) - back
+                    buf += buf[s: s + ln]
+            else:
+                buf += piece(kind, n)
+        data = bytes(buf[:total])
+        chunk, dict_size = (S, D) if rng.random() < 0.7 else (int(rng.choice([4096, 8192, 32768])), int(rng.choice([0, 2048, 32768])))
+        b = _padded(data)
+        for off in range(0, len(data), chunk):
+            ln = min(chunk, len(data) - off); final = off + ln == len(data)
+            body = ln if final else ln - 1
+            d = min(dict_size, off)
+            seq = walk(model, model.l1m_seq, b, off, body, d)
+            for fn in (model.l1m_warp, model.l1m_warp2):
+                got = walk(model, fn, b, off, body, d)
+                assert got.shape == seq.shape and np.array_equal(got, seq), (chunk, dict_size, off, len(data))
+            chunks += 1
+    assert chunks > 60
